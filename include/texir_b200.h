@@ -1,0 +1,159 @@
+/* texir_b200.h -- C ABI of libtexir_b200.so: the B200 (sm_100a) implementation of TexIR's
+ * irradiance-texture / per-pixel BRDF hot path.
+ *
+ * The reference (LZleejean/TexIR_code) is pure Python; it has no FFI of its own.  Each entry
+ * point below replaces one piece of reference Python (file:line cited per function) and is what
+ * the ctypes binding in texir_code_b200/_lib.py -- or a binding a reference maintainer would add,
+ * see INTEGRATION.md -- calls.
+ *
+ * Conventions
+ *   - every pointer is a CUDA DEVICE pointer unless the name ends in _host;
+ *   - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream);
+ *     every call is asynchronous on that stream and performs no host synchronisation,
+ *     except texir_scene_create / texir_scene_set_texture(host source), which upload;
+ *   - tensors are dense row-major float32 unless stated otherwise;
+ *   - return value 0 = ok; non-zero = error, text from texir_last_error() (thread-local);
+ *   - no C++ exception crosses this boundary;
+ *   - a scene is immutable after creation apart from set_texture / set_bvh, which must not race
+ *     with launches that use the scene.
+ */
+#ifndef TEXIR_B200_H
+#define TEXIR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define TEXIR_API __declspec(dllexport)
+#else
+#define TEXIR_API __attribute__((visibility("default")))
+#endif
+
+typedef struct texir_scene texir_scene;
+
+/* sampling modes of generate_dir (utils/sample_util.py:115-143) */
+enum { TEXIR_MODE_UNIFORM = 0, TEXIR_MODE_COSINE = 1, TEXIR_MODE_IMPORTANCE = 2 };
+/* radiance texture source layouts */
+enum { TEXIR_TEX_CHW = 0 /* [3,H,W], the reference's self.texture[0] */, TEXIR_TEX_HWC = 1 /* [H,W,3] */ };
+/* BVH layout a scene's kernels traverse */
+enum { TEXIR_BVH2 = 2, TEXIR_BVH8 = 8 };
+
+typedef struct texir_scene_info {
+    int64_t num_tris;
+    int64_t num_nodes2, num_nodes8;
+    int32_t depth2, depth8;
+    int32_t tex_h, tex_w;
+    int32_t bvh_kind;       /* TEXIR_BVH2 or TEXIR_BVH8 */
+    int32_t device;
+    double sah2, sah8;
+    double build_seconds;
+    int64_t device_bytes;   /* HBM held by the scene (BVHs + triangles + uvs + texture) */
+} texir_scene_info;
+
+TEXIR_API const char* texir_last_error(void);
+TEXIR_API int texir_version(void);
+/* number of kernels this library has launched in this process (all scenes, all streams) */
+TEXIR_API int64_t texir_launch_count(void);
+
+/* ---- scene: replaces o3d.t.geometry.RaycastingScene() + add_triangles + self.triangle_uvs
+ *      (models/mat_nvdiffrast.py:87,97-101; models/tracer_o3d_irt.py:75,85-89) ------------------
+ * verts_host [nv,3] f32, tris_host [nt,3] i32, tri_uvs_host [3*nt,2] f64 (np.asarray(mesh.triangle_uvs),
+ * may be NULL for a pure cast_rays scene).  Builds the BVHs on the host (build_threads <= 0: all
+ * cores) and uploads them to `device`. */
+TEXIR_API int texir_scene_create(const float* verts_host, int64_t nv, const int32_t* tris_host, int64_t nt,
+                                 const double* tri_uvs_host, int device, int build_threads, texir_scene** out);
+TEXIR_API int texir_scene_destroy(texir_scene* scene);
+TEXIR_API int texir_scene_get_info(const texir_scene* scene, texir_scene_info* info);
+TEXIR_API int texir_scene_set_bvh(texir_scene* scene, int bvh_kind);
+
+/* ---- radiance texture: replaces self.texture (mat_nvdiffrast.py:89-93), already flipped and
+ *      exposed by the caller.  tex is f32, layout TEXIR_TEX_*; src_on_device != 0: device pointer. */
+TEXIR_API int texir_scene_set_texture(texir_scene* scene, const float* tex, int H, int W, int layout,
+                                      int src_on_device, void* stream);
+
+/* ---- cast_rays: replaces RaycastingScene.cast_rays (mat_nvdiffrast.py:294-295).
+ * rays [R,6] = (origin, direction).  Outputs: t_hit [R] (inf on miss, units of |d|),
+ * prim_id [R] u32 (0xFFFFFFFF on miss), prim_uv [R,2] (0 on miss), prim_normal [R,3] (unit
+ * geometric normal e1 x e2 orientation of Open3D, 0 on miss; may be NULL). */
+TEXIR_API int texir_cast_rays(const texir_scene* scene, const float* rays, int64_t R, float* t_hit,
+                              uint32_t* prim_id, float* prim_uv, float* prim_normal, void* stream);
+/* same, plus per-ray traversal counters (nodes visited, triangles tested) for profiling */
+TEXIR_API int texir_cast_rays_stats(const texir_scene* scene, const float* rays, int64_t R, float* t_hit,
+                                    uint32_t* prim_id, uint32_t* nodes_visited, uint32_t* tris_tested,
+                                    void* stream);
+
+/* ---- generate_dir: utils/sample_util.py:63-146 (pre_mode='Hammersley').
+ * nrm [P,3], rough [P] (importance mode only, else NULL), shift [P,2] = the torch.rand(b,1,2)
+ * Cranley-Patterson shift drawn by the caller; out [P,N,3]. */
+TEXIR_API int texir_generate_dir(const float* nrm, const float* rough, const float* shift, int64_t P, int N,
+                                 int mode, float* out, void* stream);
+/* gradient of generate_dir w.r.t. roughness (importance mode): g_out [P,N,3] -> g_rough [P] */
+TEXIR_API int texir_generate_dir_bwd(const float* nrm, const float* rough, const float* shift, int64_t P, int N,
+                                     const float* g_out, float* g_rough, void* stream);
+
+/* ---- query_irf: models/mat_nvdiffrast.py:292-320 / models/tracer_o3d_irt.py:240-269.
+ * org [P,3] (one origin per point, the reference expands it), dir [P,N,3]; rad [P,N,3]. */
+TEXIR_API int texir_query_irf(const texir_scene* scene, const float* org, const float* dir, int64_t P, int N,
+                              float* rad, void* stream);
+
+/* ---- fused IrT batch: models/tracer_o3d_irt.py:165-173 for P points at once.
+ * E[p] = sum_i L_i * clamp(n.l_i, 0, 1) * 2*pi / N  with l_i = generate_dir(nrm, N, mode). */
+TEXIR_API int texir_irradiance_fwd(const texir_scene* scene, const float* pos, const float* nrm,
+                                   const float* shift, int64_t P, int N, int mode, float* E, void* stream);
+
+/* ---- fused render: MaterialModel.render, models/mat_nvdiffrast.py:201-249 (and the relighting
+ *      variant models/test_nvdiffrast.py:256-303 when N_diff > 0).
+ * nrm, albedo, pos, irr [P,3]; rough [P]; cam [3]; shift_spec [P,2]; shift_diff [P,2] (N_diff > 0).
+ * eps = 1e-14 (mat_nvdiffrast.py) or 1e-6 (test_nvdiffrast.py and the baseline variants).
+ * rgb [P,3].  Optional stashes that make the backward pass free of ray casts:
+ *   drgb_drough [P,3] = d rgb / d roughness,  ediff [P,3] = MC diffuse irradiance term (N_diff > 0). */
+TEXIR_API int texir_shade_fwd(const texir_scene* scene, const float* nrm, const float* albedo, const float* rough,
+                              const float* pos, const float* cam, const float* irr, const float* shift_spec,
+                              const float* shift_diff, int64_t P, int N_spec, int N_diff, int mode_spec,
+                              int mode_diff, float eps, float* rgb, float* drgb_drough, float* ediff,
+                              void* stream);
+/* backward of texir_shade_fwd.  g_rgb [P,3] -> g_albedo [P,3], g_rough [P], g_irr [P,3] (each may
+ * be NULL).  If drgb_drough (and ediff when N_diff > 0) from the forward call are given they are
+ * used; otherwise the kernel re-generates the samples and re-casts every ray. */
+TEXIR_API int texir_shade_bwd(const texir_scene* scene, const float* nrm, const float* albedo, const float* rough,
+                              const float* pos, const float* cam, const float* irr, const float* shift_spec,
+                              const float* shift_diff, int64_t P, int N_spec, int N_diff, int mode_spec,
+                              int mode_diff, float eps, const float* g_rgb, const float* drgb_drough,
+                              const float* ediff, float* g_albedo, float* g_rough, float* g_irr, void* stream);
+
+/* ---- stand-alone BRDF reductions with the reference's tensor signatures --------------------
+ * specular_reflectance(lighting, h, n, v, l, roughness): mat_nvdiffrast.py:260-279.
+ * lighting, h, l [P,N,3]; n, v [P,3]; rough [P]; out [P,3] (NOT divided by N, as in the reference). */
+TEXIR_API int texir_specular_reflectance(const float* lighting, const float* h, const float* n, const float* v,
+                                         const float* l, const float* rough, int64_t P, int N, float eps,
+                                         float* out, void* stream);
+/* g_out [P,3] -> g_lighting, g_h, g_l [P,N,3], g_rough [P] (each may be NULL) */
+TEXIR_API int texir_specular_reflectance_bwd(const float* lighting, const float* h, const float* n, const float* v,
+                                             const float* l, const float* rough, int64_t P, int N, float eps,
+                                             const float* g_out, float* g_lighting, float* g_h, float* g_l,
+                                             float* g_rough, void* stream);
+/* diffuse_reflectance(lighting, l, n, albedo, sample_type): mat_nvdiffrast.py:252-258; cosine != 0
+ * selects the 'cosine' branch. */
+TEXIR_API int texir_diffuse_reflectance(const float* lighting, const float* l, const float* n, const float* albedo,
+                                        int64_t P, int N, int cosine, float* out, void* stream);
+TEXIR_API int texir_diffuse_reflectance_bwd(const float* lighting, const float* l, const float* n,
+                                            const float* albedo, int64_t P, int N, int cosine, const float* g_out,
+                                            float* g_lighting, float* g_l, float* g_albedo, void* stream);
+
+/* ---- texture-space material fetch / gradient scatter (dr.texture(..., filter_mode='linear'),
+ *      models/mat_nvdiffrast.py:131-139) ------------------------------------
+ * tex [H,W,C] f32, uv [P,2] in [0,1] (nvdiffrast convention: texel centres at (i+0.5)/W, wrap
+ * boundary mode), out [P,C]. */
+TEXIR_API int texir_texture_fetch(const float* tex, int H, int W, int C, const float* uv, int64_t P, float* out,
+                                  void* stream);
+/* g_out [P,C] scattered with atomics into g_tex [H,W,C] (caller zero-initialises) */
+TEXIR_API int texir_texture_scatter(const float* g_out, int H, int W, int C, const float* uv, int64_t P,
+                                    float* g_tex, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TEXIR_B200_H */

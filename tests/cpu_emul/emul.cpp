@@ -1,0 +1,173 @@
+// emul.cpp -- TEST INFRASTRUCTURE.  Compiles the kernels' host/device headers (texir_math.h,
+// texir_bvh.h, texir_point.h) and the host BVH builder with g++ so that the exact per-sample code
+// of the sm_100a kernels can be checked against the oracle on a machine without a GPU.
+// Never loaded by the product package.  Build: see tests/cpu_emul/build.py (-ffp-contract=off).
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../texir_code_b200/csrc/bvh_build.h"
+#include "../../texir_code_b200/csrc/texir_point.h"
+
+using namespace texir;
+
+struct EmulScene {
+    HostBVH bvh;
+    std::vector<double> uvs;
+    std::vector<float4> tex;
+    SceneView view{};
+    std::string err;
+};
+
+static int group_lanes(int N) {
+    int g = 1;
+    while (g < N && g < 32) g <<= 1;
+    return g;
+}
+
+extern "C" {
+
+EmulScene* emul_scene_create(const float* verts, int64_t nv, const int32_t* tris, int64_t nt, const double* uvs,
+                             int threads) {
+    EmulScene* s = new EmulScene();
+    if (!build_bvh(verts, nv, tris, nt, threads, s->bvh, s->err)) {
+        delete s;
+        return nullptr;
+    }
+    if (uvs) s->uvs.assign(uvs, uvs + 6 * (size_t)nt);
+    s->view.nodes2 = s->bvh.nodes2.data();
+    s->view.tris2 = s->bvh.tris2.data();
+    s->view.prim2 = s->bvh.prim2.data();
+    s->view.nodes8 = s->bvh.nodes8.data();
+    s->view.tris8 = s->bvh.tris8.data();
+    s->view.prim8 = s->bvh.prim8.data();
+    s->view.tri_uvs = s->uvs.empty() ? nullptr : s->uvs.data();
+    s->view.num_tris = (uint32_t)nt;
+    return s;
+}
+void emul_scene_destroy(EmulScene* s) { delete s; }
+
+void emul_scene_stats(EmulScene* s, double* out /* nodes2, nodes8, depth2, depth8, sah2, sah8, build_s */) {
+    out[0] = (double)s->bvh.nodes2.size() / 4;
+    out[1] = (double)s->bvh.nodes8.size() / 5;
+    out[2] = s->bvh.depth2;
+    out[3] = s->bvh.depth8;
+    out[4] = s->bvh.sah2;
+    out[5] = s->bvh.sah8;
+    out[6] = s->bvh.build_seconds;
+}
+
+void emul_set_texture(EmulScene* s, const float* chw, int H, int W) {
+    s->tex.resize((size_t)H * W);
+    size_t n = (size_t)H * W;
+    for (size_t i = 0; i < n; ++i) s->tex[i] = float4{chw[i], chw[n + i], chw[2 * n + i], 0.f};
+    s->view.tex = s->tex.data();
+    s->view.tex_h = H;
+    s->view.tex_w = W;
+}
+
+void emul_cast_rays(EmulScene* s, int kind, const float* rays, int64_t R, float* t, uint32_t* id, float* uv,
+                    uint32_t* nvis, uint32_t* ntri) {
+    for (int64_t r = 0; r < R; ++r) {
+        V3 o = v3(rays[6 * r], rays[6 * r + 1], rays[6 * r + 2]);
+        V3 d = v3(rays[6 * r + 3], rays[6 * r + 4], rays[6 * r + 5]);
+        uint32_t a = 0, b = 0;
+        Hit h = kind == 8 ? trace_bvh8(s->view, o, d, &a, &b) : trace_bvh2(s->view, o, d, &a, &b);
+        t[r] = h.t;
+        id[r] = h.prim;
+        uv[2 * r] = h.u;
+        uv[2 * r + 1] = h.v;
+        if (nvis) nvis[r] = a;
+        if (ntri) ntri[r] = b;
+    }
+}
+
+void emul_generate_dir(const float* nrm, const float* rough, const float* shift, int64_t P, int N, int mode,
+                       float* out) {
+    for (int64_t p = 0; p < P; ++p) {
+        Frame f = make_frame(v3(nrm[3 * p], nrm[3 * p + 1], nrm[3 * p + 2]));
+        for (int i = 0; i < N; ++i) {
+            float s0 = shift_wrap_clamp(hammersley0((uint32_t)i, (uint32_t)N), shift[2 * p]);
+            float s1 = shift_wrap_clamp(radical_inverse((uint32_t)i), shift[2 * p + 1]);
+            DirSample ds = sample_dir<false>(f, mode, s0, s1, rough ? rough[p] : 0.f);
+            float* o = out + 3 * (p * N + i);
+            o[0] = ds.d.x;
+            o[1] = ds.d.y;
+            o[2] = ds.d.z;
+        }
+    }
+}
+
+void emul_query_irf(EmulScene* s, int kind, const float* org, const float* dir, int64_t P, int N, float* rad) {
+    for (int64_t p = 0; p < P; ++p)
+        for (int i = 0; i < N; ++i) {
+            int64_t q = p * N + i;
+            V3 o = v3(org[3 * p], org[3 * p + 1], org[3 * p + 2]);
+            V3 d = v3(dir[3 * q], dir[3 * q + 1], dir[3 * q + 2]);
+            Hit h = kind == 8 ? trace<8>(s->view, o, d) : trace<2>(s->view, o, d);
+            V3 L = fetch_radiance(s->view, h);
+            rad[3 * q] = L.x;
+            rad[3 * q + 1] = L.y;
+            rad[3 * q + 2] = L.z;
+        }
+}
+
+void emul_irradiance(EmulScene* s, int kind, const float* pos, const float* nrm, const float* shift, int64_t P,
+                     int N, int mode, float* E) {
+    const int G = group_lanes(N), ab = coherent_bits(N);
+    for (int64_t p = 0; p < P; ++p) {
+        float sum[3] = {0.f, 0.f, 0.f};
+        for (int gl = 0; gl < G; ++gl) {
+            float acc[3];
+            V3 n = v3(nrm[3 * p], nrm[3 * p + 1], nrm[3 * p + 2]), o = v3(pos[3 * p], pos[3 * p + 1], pos[3 * p + 2]);
+            if (kind == 8)
+                irradiance_lane<8>(s->view, n, o, shift[2 * p], shift[2 * p + 1], N, mode, gl, G, ab, acc);
+            else
+                irradiance_lane<2>(s->view, n, o, shift[2 * p], shift[2 * p + 1], N, mode, gl, G, ab, acc);
+            for (int c = 0; c < 3; ++c) sum[c] += acc[c];
+        }
+        for (int c = 0; c < 3; ++c) E[3 * p + c] = irradiance_finish(sum[c], N);
+    }
+}
+
+// forward render with the forward-mode roughness tangent; outputs rgb [P,3], drgb [P,3], ediff [P,3]
+void emul_shade(EmulScene* s, int kind, const float* nrm, const float* albedo, const float* rough, const float* pos,
+                const float* cam, const float* irr, const float* shift_spec, const float* shift_diff, int64_t P,
+                int N_spec, int N_diff, int mode_spec, int mode_diff, float eps, float* rgb, float* drgb,
+                float* ediff) {
+    int gs = group_lanes(N_spec), gd = N_diff > 0 ? group_lanes(N_diff) : gs;
+    const int G = gs > gd ? gs : gd;
+    const int abs_ = coherent_bits(N_spec), abd = N_diff > 0 ? coherent_bits(N_diff) : 0;
+    V3 c = v3(cam[0], cam[1], cam[2]);
+    for (int64_t p = 0; p < P; ++p) {
+        float sp[3] = {0, 0, 0}, dsp[3] = {0, 0, 0}, df[3] = {0, 0, 0};
+        V3 n = v3(nrm[3 * p], nrm[3 * p + 1], nrm[3 * p + 2]), o = v3(pos[3 * p], pos[3 * p + 1], pos[3 * p + 2]);
+        for (int gl = 0; gl < G; ++gl) {
+            ShadeLaneOut lo;
+            float d0 = N_diff > 0 ? shift_diff[2 * p] : 0.f, d1 = N_diff > 0 ? shift_diff[2 * p + 1] : 0.f;
+            if (kind == 8)
+                shade_lane<8, true>(s->view, n, o, c, rough[p], eps, shift_spec[2 * p], shift_spec[2 * p + 1], N_spec,
+                                    mode_spec, abs_, d0, d1, N_diff, mode_diff, abd, gl, G, lo);
+            else
+                shade_lane<2, true>(s->view, n, o, c, rough[p], eps, shift_spec[2 * p], shift_spec[2 * p + 1], N_spec,
+                                    mode_spec, abs_, d0, d1, N_diff, mode_diff, abd, gl, G, lo);
+            for (int k = 0; k < 3; ++k) {
+                sp[k] += lo.spec[k];
+                dsp[k] += lo.dspec[k];
+                df[k] += lo.diff[k];
+            }
+        }
+        float ir[3] = {0, 0, 0}, dfac[3];
+        if (N_diff == 0)
+            for (int k = 0; k < 3; ++k) ir[k] = irr[3 * p + k];
+        diffuse_factor(ir, df, N_diff, mode_diff, dfac);
+        for (int k = 0; k < 3; ++k) {
+            rgb[3 * p + k] = albedo[3 * p + k] * dfac[k] + sp[k] / (float)N_spec;
+            drgb[3 * p + k] = dsp[k] / (float)N_spec;
+            ediff[3 * p + k] = dfac[k];
+        }
+    }
+}
+
+}  // extern "C"

@@ -1,0 +1,32 @@
+// bvh_build.h -- host-side BVH builder (C++17, std::thread).  Replaces the Embree BVH that
+// Open3D builds lazily inside RaycastingScene.add_triangles / first cast_rays
+// (reference call sites: models/mat_nvdiffrast.py:98-101, models/tracer_o3d_irt.py:85-89).
+#pragma once
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "texir_bvh.h"
+
+namespace texir {
+
+struct HostBVH {
+    // BVH2 (layout: texir_bvh.h)
+    std::vector<float4> nodes2;
+    std::vector<float4> tris2;  // 3 per slot
+    std::vector<uint32_t> prim2;
+    // BVH8 compressed wide (layout: texir_bvh.h)
+    std::vector<uint4> nodes8;  // 5 per node
+    std::vector<float4> tris8;
+    std::vector<uint32_t> prim8;
+    int depth2 = 0, depth8 = 0;
+    int top_nodes2 = 0;  // nodes2[0 .. top_nodes2) are the top levels in breadth-first order
+    double sah2 = 0.0, sah8 = 0.0;
+    double build_seconds = 0.0;
+    float scene_lo[3], scene_hi[3];
+};
+
+// verts: [nv][3] float32, tris: [nt][3] int32.  Returns false and fills err on bad input.
+bool build_bvh(const float* verts, int64_t nv, const int32_t* tris, int64_t nt, int threads, HostBVH& out,
+               std::string& err);
+
+}  // namespace texir

@@ -1,0 +1,1045 @@
+// texir_kernels.cu -- sm_100a kernels of the TexIR hot path and the C ABI of include/texir_b200.h.
+//
+// Work decomposition: a group of G lanes (G = 32 for N >= 32 samples, else the next power of two
+// >= N) owns one surface point; each lane walks its own rays through the BVH (one ray per thread,
+// coherent 32-sample patches per warp iteration, see coherent_bits) and the per-point Monte-Carlo
+// sum is a warp-shuffle reduction.  No [P,N,.] tensor ever exists in the fused kernels.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/texir_b200.h"
+#include "bvh_build.h"
+#include "texir_point.h"
+
+using namespace texir;
+
+// ------------------------------------------------------------------------------------------------
+// host-side state
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static std::atomic<int64_t> g_launches{0};
+
+struct texir_scene {
+    SceneView view{};
+    texir_scene_info info{};
+    void* d_nodes2 = nullptr;
+    void* d_tris2 = nullptr;
+    void* d_prim2 = nullptr;
+    void* d_nodes8 = nullptr;
+    void* d_tris8 = nullptr;
+    void* d_prim8 = nullptr;
+    void* d_uvs = nullptr;
+    void* d_slot_of_prim = nullptr;  // original primitive id -> BVH2 slot
+    void* d_tex = nullptr;
+    int64_t geom_bytes = 0, tex_bytes = 0;
+};
+
+#define TX_FAIL(msg)                 \
+    do {                             \
+        g_err = (msg);               \
+        return 1;                    \
+    } while (0)
+#define TX_CUDA(call)                                                                          \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess) {                                                               \
+            g_err = std::string(#call) + ": " + cudaGetErrorString(e_);                        \
+            return 2;                                                                          \
+        }                                                                                      \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) ok = false;
+        if (ok && prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+static int device_of(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess || a.type != cudaMemoryTypeDevice) {
+        cudaGetLastError();
+        int d = 0;
+        cudaGetDevice(&d);
+        return d;
+    }
+    return a.device;
+}
+
+static int finish_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        g_err = std::string(what) + ": " + cudaGetErrorString(e);
+        return 2;
+    }
+    g_launches.fetch_add(1);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ V3 load3(const float* __restrict__ p, int64_t i) {
+    return v3(__ldg(p + 3 * i + 0), __ldg(p + 3 * i + 1), __ldg(p + 3 * i + 2));
+}
+__device__ __forceinline__ float group_sum(float v, int G) {
+    for (int o = G >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    return v;
+}
+__host__ __device__ __forceinline__ int group_lanes(int N) {
+    int g = 1;
+    while (g < N && g < 32) g <<= 1;
+    return g;
+}
+
+// ------------------------------------------------------------------------------------------------
+// cast_rays
+// ------------------------------------------------------------------------------------------------
+template <int KIND, bool STATS>
+__global__ void __launch_bounds__(128) k_cast_rays(SceneView s, const float* __restrict__ rays, int64_t R,
+                                                   float* __restrict__ t_hit, uint32_t* __restrict__ prim_id,
+                                                   float* __restrict__ prim_uv, uint32_t* __restrict__ nvis,
+                                                   uint32_t* __restrict__ ntri) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    V3 o = v3(__ldg(rays + 6 * r + 0), __ldg(rays + 6 * r + 1), __ldg(rays + 6 * r + 2));
+    V3 d = v3(__ldg(rays + 6 * r + 3), __ldg(rays + 6 * r + 4), __ldg(rays + 6 * r + 5));
+    Hit h;
+    if (STATS) {
+        uint32_t a = 0, b = 0;
+        h = (KIND == 8) ? trace_bvh8(s, o, d, &a, &b) : trace_bvh2(s, o, d, &a, &b);
+        nvis[r] = a;
+        ntri[r] = b;
+    } else {
+        h = trace<KIND>(s, o, d);
+    }
+    t_hit[r] = h.t;
+    prim_id[r] = h.prim;
+    if (prim_uv) {
+        prim_uv[2 * r + 0] = h.u;
+        prim_uv[2 * r + 1] = h.v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// generate_dir (forward, and gradient w.r.t. roughness)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_generate_dir(const float* __restrict__ nrm, const float* __restrict__ rough,
+                                                      const float* __restrict__ shift, int64_t P, int N, int mode,
+                                                      float* __restrict__ out) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P * (int64_t)N) return;
+    int64_t p = idx / N;
+    uint32_t i = (uint32_t)(idx - p * N);
+    Frame f = make_frame(load3(nrm, p));
+    float s0 = shift_wrap_clamp(hammersley0(i, (uint32_t)N), __ldg(shift + 2 * p + 0));
+    float s1 = shift_wrap_clamp(radical_inverse(i), __ldg(shift + 2 * p + 1));
+    float r = (mode == MODE_IMPORTANCE) ? __ldg(rough + p) : 0.f;
+    DirSample ds = sample_dir<false>(f, mode, s0, s1, r);
+    out[3 * idx + 0] = ds.d.x;
+    out[3 * idx + 1] = ds.d.y;
+    out[3 * idx + 2] = ds.d.z;
+}
+
+// one warp per point: g_rough[p] = sum_i g_out[p,i] . dL_i/dr
+__global__ void __launch_bounds__(128) k_generate_dir_bwd(const float* __restrict__ nrm, const float* __restrict__ rough,
+                                                          const float* __restrict__ shift, int64_t P, int N,
+                                                          const float* __restrict__ g_out, float* __restrict__ g_rough) {
+    int64_t p = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (p >= P) return;
+    Frame f = make_frame(load3(nrm, p));
+    float r = __ldg(rough + p);
+    float sh0 = __ldg(shift + 2 * p + 0), sh1 = __ldg(shift + 2 * p + 1);
+    float acc = 0.f;
+    for (int i = lane; i < N; i += 32) {
+        float s0 = shift_wrap_clamp(hammersley0((uint32_t)i, (uint32_t)N), sh0);
+        float s1 = shift_wrap_clamp(radical_inverse((uint32_t)i), sh1);
+        DirSample ds = sample_dir<true>(f, MODE_IMPORTANCE, s0, s1, r);
+        V3 g = load3(g_out, p * N + i);
+        float ax = f.v.x * ds.sphi - f.u.x * ds.cphi, ay = f.v.y * ds.sphi - f.u.y * ds.cphi,
+              az = f.v.z * ds.sphi - f.u.z * ds.cphi;
+        acc += g.x * (ax * ds.dst + f.n.x * ds.dc) + g.y * (ay * ds.dst + f.n.y * ds.dc) +
+               g.z * (az * ds.dst + f.n.z * ds.dc);
+    }
+    acc = group_sum(acc, 32);
+    if (lane == 0) g_rough[p] = acc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// query_irf: one thread per (point, sample) ray
+// ------------------------------------------------------------------------------------------------
+template <int KIND>
+__global__ void __launch_bounds__(128) k_query_irf(SceneView s, const float* __restrict__ org,
+                                                   const float* __restrict__ dir, int64_t P, int N,
+                                                   float* __restrict__ rad) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P * (int64_t)N) return;
+    int64_t p = idx / N;
+    V3 o = load3(org, p);
+    V3 d = load3(dir, idx);
+    Hit h = trace<KIND>(s, o, d);
+    V3 L = fetch_radiance(s, h);
+    rad[3 * idx + 0] = L.x;
+    rad[3 * idx + 1] = L.y;
+    rad[3 * idx + 2] = L.z;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused IrT: E = sum_i L_i clamp(n.l_i) * 2 pi / N       (models/tracer_o3d_irt.py:168-171)
+// ------------------------------------------------------------------------------------------------
+template <int KIND>
+__global__ void __launch_bounds__(128) k_irradiance(SceneView s, const float* __restrict__ pos,
+                                                    const float* __restrict__ nrm, const float* __restrict__ shift,
+                                                    int64_t P, int N, int mode, int G, int abits,
+                                                    float* __restrict__ E) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int gl = lane & (G - 1);
+    int64_t p = warp * (32 / G) + lane / G;
+    const bool live = p < P;
+    if (!live) p = P - 1;
+    float acc[3];
+    irradiance_lane<KIND>(s, load3(nrm, p), load3(pos, p), __ldg(shift + 2 * p + 0), __ldg(shift + 2 * p + 1), N, mode,
+                          gl, G, abits, acc);
+    float ax = group_sum(acc[0], G), ay = group_sum(acc[1], G), az = group_sum(acc[2], G);
+    if (live && gl == 0) {
+        E[3 * p + 0] = irradiance_finish(ax, N);
+        E[3 * p + 1] = irradiance_finish(ay, N);
+        E[3 * p + 2] = irradiance_finish(az, N);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused render / its backward with ray recomputation   (models/mat_nvdiffrast.py:201-249)
+// ------------------------------------------------------------------------------------------------
+struct ShadeArgs {
+    const float* nrm;
+    const float* albedo;
+    const float* rough;
+    const float* pos;
+    const float* cam;
+    const float* irr;
+    const float* shift_spec;
+    const float* shift_diff;
+    int64_t P;
+    int N_spec, N_diff, mode_spec, mode_diff;
+    float eps;
+    int G_spec, a_spec, G_diff, a_diff, G;
+    // forward outputs
+    float* rgb;
+    float* drgb_drough;
+    float* ediff;
+    // backward
+    const float* g_rgb;
+    float* g_albedo;
+    float* g_rough;
+    float* g_irr;
+};
+
+template <int KIND, bool TANGENT>
+__global__ void __launch_bounds__(128) k_shade(SceneView s, ShadeArgs a) {
+    const int G = a.G;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int gl = lane & (G - 1);
+    int64_t p = warp * (32 / G) + lane / G;
+    const bool live = p < a.P;
+    if (!live) p = a.P - 1;
+    const V3 cam = v3(__ldg(a.cam + 0), __ldg(a.cam + 1), __ldg(a.cam + 2));
+    float shd0 = 0.f, shd1 = 0.f;
+    if (a.N_diff > 0) {
+        shd0 = __ldg(a.shift_diff + 2 * p + 0);
+        shd1 = __ldg(a.shift_diff + 2 * p + 1);
+    }
+    ShadeLaneOut lo;
+    shade_lane<KIND, TANGENT>(s, load3(a.nrm, p), load3(a.pos, p), cam, __ldg(a.rough + p), a.eps,
+                              __ldg(a.shift_spec + 2 * p + 0), __ldg(a.shift_spec + 2 * p + 1), a.N_spec, a.mode_spec,
+                              a.a_spec, shd0, shd1, a.N_diff, a.mode_diff, a.a_diff, gl, G, lo);
+    float sx = group_sum(lo.spec[0], G), sy = group_sum(lo.spec[1], G), sz = group_sum(lo.spec[2], G);
+    float dx = 0.f, dy = 0.f, dz = 0.f;
+    if (TANGENT) {
+        dx = group_sum(lo.dspec[0], G);
+        dy = group_sum(lo.dspec[1], G);
+        dz = group_sum(lo.dspec[2], G);
+    }
+    float dsum[3] = {0.f, 0.f, 0.f};
+    if (a.N_diff > 0) {
+        dsum[0] = group_sum(lo.diff[0], G);
+        dsum[1] = group_sum(lo.diff[1], G);
+        dsum[2] = group_sum(lo.diff[2], G);
+    }
+    if (!live || gl != 0) return;
+    const float inv_ns = 1.0f / (float)a.N_spec;
+    float irr[3] = {0.f, 0.f, 0.f}, dfac[3];
+    if (a.N_diff == 0) {
+        irr[0] = __ldg(a.irr + 3 * p + 0);
+        irr[1] = __ldg(a.irr + 3 * p + 1);
+        irr[2] = __ldg(a.irr + 3 * p + 2);
+    }
+    diffuse_factor(irr, dsum, a.N_diff, a.mode_diff, dfac);
+    if (a.g_rgb == nullptr) {
+        V3 al = load3(a.albedo, p);
+        a.rgb[3 * p + 0] = al.x * dfac[0] + sx * inv_ns;
+        a.rgb[3 * p + 1] = al.y * dfac[1] + sy * inv_ns;
+        a.rgb[3 * p + 2] = al.z * dfac[2] + sz * inv_ns;
+        if (TANGENT && a.drgb_drough) {
+            a.drgb_drough[3 * p + 0] = dx * inv_ns;
+            a.drgb_drough[3 * p + 1] = dy * inv_ns;
+            a.drgb_drough[3 * p + 2] = dz * inv_ns;
+        }
+        if (a.ediff && a.N_diff > 0) {
+            a.ediff[3 * p + 0] = dfac[0];
+            a.ediff[3 * p + 1] = dfac[1];
+            a.ediff[3 * p + 2] = dfac[2];
+        }
+    } else {
+        V3 g = load3(a.g_rgb, p);
+        if (a.g_albedo) {
+            a.g_albedo[3 * p + 0] = g.x * dfac[0];
+            a.g_albedo[3 * p + 1] = g.y * dfac[1];
+            a.g_albedo[3 * p + 2] = g.z * dfac[2];
+        }
+        if (a.g_rough) a.g_rough[p] = (g.x * dx + g.y * dy + g.z * dz) * inv_ns;
+        if (a.g_irr) {
+            V3 al = load3(a.albedo, p);
+            bool lit = a.N_diff == 0;
+            a.g_irr[3 * p + 0] = lit ? g.x * al.x / kPi : 0.f;
+            a.g_irr[3 * p + 1] = lit ? g.y * al.y / kPi : 0.f;
+            a.g_irr[3 * p + 2] = lit ? g.z * al.z / kPi : 0.f;
+        }
+    }
+}
+
+// backward from the forward-mode stash: no rays
+__global__ void __launch_bounds__(256) k_shade_bwd_stash(ShadeArgs a) {
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= a.P) return;
+    V3 g = load3(a.g_rgb, p);
+    if (a.g_albedo) {
+        V3 fac;
+        if (a.N_diff > 0) {
+            fac = load3(a.ediff, p);
+        } else {
+            V3 irr = load3(a.irr, p);
+            fac = v3(irr.x / kPi, irr.y / kPi, irr.z / kPi);
+        }
+        a.g_albedo[3 * p + 0] = g.x * fac.x;
+        a.g_albedo[3 * p + 1] = g.y * fac.y;
+        a.g_albedo[3 * p + 2] = g.z * fac.z;
+    }
+    if (a.g_rough) {
+        V3 d = load3(a.drgb_drough, p);
+        a.g_rough[p] = g.x * d.x + g.y * d.y + g.z * d.z;
+    }
+    if (a.g_irr) {
+        V3 al = load3(a.albedo, p);
+        bool lit = a.N_diff == 0;
+        a.g_irr[3 * p + 0] = lit ? g.x * al.x / kPi : 0.f;
+        a.g_irr[3 * p + 1] = lit ? g.y * al.y / kPi : 0.f;
+        a.g_irr[3 * p + 2] = lit ? g.z * al.z / kPi : 0.f;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// stand-alone specular / diffuse reductions (reference tensor signatures), one warp per point
+// ------------------------------------------------------------------------------------------------
+struct SpecTerms {
+    float w;                 // sample weight
+    float dw_dvdh, dw_dndl, dw_dndh, dw_dk;
+    bool m_vdh, m_ndl, m_ndh;
+};
+__device__ __forceinline__ SpecTerms spec_terms(V3 n, V3 v, V3 h, V3 l, float k, float eps, bool grads) {
+    SpecTerms t;
+    float vdh_raw = rn_dot(h, v), ndl_raw = rn_dot(n, l), ndh_raw = rn_dot(n, h);
+    float ndv = clamp01(rn_dot(n, v));
+    float vdh = clamp01(vdh_raw), ndl = clamp01(ndl_raw), ndh = clamp01(ndh_raw);
+    t.m_vdh = vdh_raw >= 0.f && vdh_raw <= 1.f;
+    t.m_ndl = ndl_raw >= 0.f && ndl_raw <= 1.f;
+    t.m_ndh = ndh_raw >= 0.f && ndh_raw <= 1.f;
+    float e = (-5.55472f * vdh - 6.98316f) * vdh;
+    float p2 = exp2f(e);
+    float F = 0.04f + 0.96f * p2;
+    float denv = ndv * (1.0f - k) + k, denvc = fmaxf(denv, eps);
+    float denl = ndl * (1.0f - k) + k, denlc = fmaxf(denl, eps);
+    float g1v = ndv / denvc, g1l = ndl / denlc;
+    float g = g1l * g1v;
+    float q4 = 4.0f * ndl * ndv, q4c = fmaxf(q4, eps);
+    float brdf = F * g / q4c;
+    float ndhc = fmaxf(ndh, eps);
+    t.w = brdf * ndl * 4.0f * vdh / ndhc;
+    t.dw_dvdh = t.dw_dndl = t.dw_dndh = t.dw_dk = 0.f;
+    if (grads) {
+        float dF = 0.96f * p2 * 0.6931471805599453f * (-2.0f * 5.55472f * vdh - 6.98316f);
+        float dg1l_dndl = 1.0f / denlc - ndl / (denlc * denlc) * ((denl >= eps) ? (1.0f - k) : 0.f);
+        float dg1l_dk = -ndl / (denlc * denlc) * ((denl >= eps) ? (1.0f - ndl) : 0.f);
+        float dg1v_dk = -ndv / (denvc * denvc) * ((denv >= eps) ? (1.0f - ndv) : 0.f);
+        float dbrdf_dndl = F * g1v * dg1l_dndl / q4c - F * g / (q4c * q4c) * ((q4 >= eps) ? 4.0f * ndv : 0.f);
+        t.dw_dvdh = 4.0f * ndl / ndhc * (brdf + vdh * dF * g / q4c);
+        t.dw_dndl = 4.0f * vdh / ndhc * (brdf + ndl * dbrdf_dndl);
+        t.dw_dndh = (ndh >= eps) ? -t.w / ndhc : 0.f;
+        t.dw_dk = 4.0f * ndl * vdh / ndhc * F / q4c * (dg1l_dk * g1v + g1l * dg1v_dk);
+    }
+    return t;
+}
+
+__global__ void __launch_bounds__(128) k_specular(const float* __restrict__ lighting, const float* __restrict__ h,
+                                                  const float* __restrict__ n, const float* __restrict__ v,
+                                                  const float* __restrict__ l, const float* __restrict__ rough,
+                                                  int64_t P, int N, float eps, float* __restrict__ out) {
+    int64_t p = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (p >= P) return;
+    V3 nn = load3(n, p), vv = load3(v, p);
+    float r1 = __ldg(rough + p) + 1.0f;
+    float k = r1 * r1 / 8.0f;
+    float ax = 0.f, ay = 0.f, az = 0.f;
+    for (int i = lane; i < N; i += 32) {
+        int64_t q = p * N + i;
+        SpecTerms t = spec_terms(nn, vv, load3(h, q), load3(l, q), k, eps, false);
+        V3 L = load3(lighting, q);
+        ax += L.x * t.w;
+        ay += L.y * t.w;
+        az += L.z * t.w;
+    }
+    ax = group_sum(ax, 32);
+    ay = group_sum(ay, 32);
+    az = group_sum(az, 32);
+    if (lane == 0) {
+        out[3 * p + 0] = ax;
+        out[3 * p + 1] = ay;
+        out[3 * p + 2] = az;
+    }
+}
+
+__global__ void __launch_bounds__(128)
+    k_specular_bwd(const float* __restrict__ lighting, const float* __restrict__ h, const float* __restrict__ n,
+                   const float* __restrict__ v, const float* __restrict__ l, const float* __restrict__ rough,
+                   int64_t P, int N, float eps, const float* __restrict__ g_out, float* __restrict__ g_lighting,
+                   float* __restrict__ g_h, float* __restrict__ g_l, float* __restrict__ g_rough) {
+    int64_t p = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (p >= P) return;
+    V3 nn = load3(n, p), vv = load3(v, p), go = load3(g_out, p);
+    float r1 = __ldg(rough + p) + 1.0f;
+    float k = r1 * r1 / 8.0f;
+    float gk = 0.f;
+    for (int i = lane; i < N; i += 32) {
+        int64_t q = p * N + i;
+        SpecTerms t = spec_terms(nn, vv, load3(h, q), load3(l, q), k, eps, true);
+        V3 L = load3(lighting, q);
+        float gw = go.x * L.x + go.y * L.y + go.z * L.z;
+        if (g_lighting) {
+            g_lighting[3 * q + 0] = go.x * t.w;
+            g_lighting[3 * q + 1] = go.y * t.w;
+            g_lighting[3 * q + 2] = go.z * t.w;
+        }
+        if (g_h) {
+            float cv = t.m_vdh ? gw * t.dw_dvdh : 0.f, cn = t.m_ndh ? gw * t.dw_dndh : 0.f;
+            g_h[3 * q + 0] = cv * vv.x + cn * nn.x;
+            g_h[3 * q + 1] = cv * vv.y + cn * nn.y;
+            g_h[3 * q + 2] = cv * vv.z + cn * nn.z;
+        }
+        if (g_l) {
+            float cl = t.m_ndl ? gw * t.dw_dndl : 0.f;
+            g_l[3 * q + 0] = cl * nn.x;
+            g_l[3 * q + 1] = cl * nn.y;
+            g_l[3 * q + 2] = cl * nn.z;
+        }
+        gk += gw * t.dw_dk;
+    }
+    gk = group_sum(gk, 32);
+    if (lane == 0 && g_rough) g_rough[p] = gk * r1 / 4.0f;
+}
+
+__global__ void __launch_bounds__(128) k_diffuse(const float* __restrict__ lighting, const float* __restrict__ l,
+                                                 const float* __restrict__ n, const float* __restrict__ albedo,
+                                                 int64_t P, int N, int cosine, float* __restrict__ out) {
+    int64_t p = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (p >= P) return;
+    V3 nn = load3(n, p), al = load3(albedo, p);
+    float ax = 0.f, ay = 0.f, az = 0.f;
+    for (int i = lane; i < N; i += 32) {
+        int64_t q = p * N + i;
+        V3 L = load3(lighting, q);
+        float wgt = cosine ? 1.0f : clamp01(rn_dot(nn, load3(l, q)));
+        ax += L.x * wgt;
+        ay += L.y * wgt;
+        az += L.z * wgt;
+    }
+    ax = group_sum(ax, 32);
+    ay = group_sum(ay, 32);
+    az = group_sum(az, 32);
+    if (lane == 0) {
+        float kf = cosine ? 1.0f : 2.0f;  // (albedo/pi) * pi  |  (albedo/pi) * 2 pi
+        out[3 * p + 0] = al.x * ax * kf;
+        out[3 * p + 1] = al.y * ay * kf;
+        out[3 * p + 2] = al.z * az * kf;
+    }
+}
+
+__global__ void __launch_bounds__(128)
+    k_diffuse_bwd(const float* __restrict__ lighting, const float* __restrict__ l, const float* __restrict__ n,
+                  const float* __restrict__ albedo, int64_t P, int N, int cosine, const float* __restrict__ g_out,
+                  float* __restrict__ g_lighting, float* __restrict__ g_l, float* __restrict__ g_albedo) {
+    int64_t p = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (p >= P) return;
+    V3 nn = load3(n, p), al = load3(albedo, p), go = load3(g_out, p);
+    float kf = cosine ? 1.0f : 2.0f;
+    float ax = 0.f, ay = 0.f, az = 0.f;
+    for (int i = lane; i < N; i += 32) {
+        int64_t q = p * N + i;
+        V3 L = load3(lighting, q);
+        float raw = rn_dot(nn, load3(l, q));
+        float wgt = cosine ? 1.0f : clamp01(raw);
+        ax += L.x * wgt;
+        ay += L.y * wgt;
+        az += L.z * wgt;
+        if (g_lighting) {
+            g_lighting[3 * q + 0] = go.x * al.x * kf * wgt;
+            g_lighting[3 * q + 1] = go.y * al.y * kf * wgt;
+            g_lighting[3 * q + 2] = go.z * al.z * kf * wgt;
+        }
+        if (g_l) {
+            float c = (!cosine && raw >= 0.f && raw <= 1.f)
+                          ? kf * (go.x * al.x * L.x + go.y * al.y * L.y + go.z * al.z * L.z)
+                          : 0.f;
+            g_l[3 * q + 0] = c * nn.x;
+            g_l[3 * q + 1] = c * nn.y;
+            g_l[3 * q + 2] = c * nn.z;
+        }
+    }
+    ax = group_sum(ax, 32);
+    ay = group_sum(ay, 32);
+    az = group_sum(az, 32);
+    if (lane == 0 && g_albedo) {
+        g_albedo[3 * p + 0] = go.x * ax * kf;
+        g_albedo[3 * p + 1] = go.y * ay * kf;
+        g_albedo[3 * p + 2] = go.z * az * kf;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// bilinear material-texture fetch and gradient scatter (nvdiffrast 'linear' filter, wrap boundary)
+// ------------------------------------------------------------------------------------------------
+struct TexTap {
+    int i00, i10, i01, i11;
+    float w00, w10, w01, w11;
+};
+__device__ __forceinline__ TexTap tex_tap(float u, float v, int H, int W) {
+    // nvdiffrast: texel centres at (i + 0.5) / size; uv scaled by size, minus 0.5, wrap addressing
+    float x = u * (float)W - 0.5f, y = v * (float)H - 0.5f;
+    float fx = floorf(x), fy = floorf(y);
+    float ax = x - fx, ay = y - fy;
+    int x0 = (int)fx, y0 = (int)fy;
+    int x1 = x0 + 1, y1 = y0 + 1;
+    x0 = ((x0 % W) + W) % W;
+    x1 = ((x1 % W) + W) % W;
+    y0 = ((y0 % H) + H) % H;
+    y1 = ((y1 % H) + H) % H;
+    TexTap t;
+    t.i00 = y0 * W + x0;
+    t.i10 = y0 * W + x1;
+    t.i01 = y1 * W + x0;
+    t.i11 = y1 * W + x1;
+    t.w00 = (1.f - ax) * (1.f - ay);
+    t.w10 = ax * (1.f - ay);
+    t.w01 = (1.f - ax) * ay;
+    t.w11 = ax * ay;
+    return t;
+}
+__global__ void __launch_bounds__(256) k_texture_fetch(const float* __restrict__ tex, int H, int W, int C,
+                                                       const float* __restrict__ uv, int64_t P,
+                                                       float* __restrict__ out) {
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    TexTap t = tex_tap(__ldg(uv + 2 * p), __ldg(uv + 2 * p + 1), H, W);
+    for (int c = 0; c < C; ++c)
+        out[p * C + c] = __ldg(tex + (int64_t)t.i00 * C + c) * t.w00 + __ldg(tex + (int64_t)t.i10 * C + c) * t.w10 +
+                         __ldg(tex + (int64_t)t.i01 * C + c) * t.w01 + __ldg(tex + (int64_t)t.i11 * C + c) * t.w11;
+}
+__global__ void __launch_bounds__(256) k_texture_scatter(const float* __restrict__ g_out, int H, int W, int C,
+                                                         const float* __restrict__ uv, int64_t P,
+                                                         float* __restrict__ g_tex) {
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    TexTap t = tex_tap(__ldg(uv + 2 * p), __ldg(uv + 2 * p + 1), H, W);
+    for (int c = 0; c < C; ++c) {
+        float g = __ldg(g_out + p * C + c);
+        atomicAdd(g_tex + (int64_t)t.i00 * C + c, g * t.w00);
+        atomicAdd(g_tex + (int64_t)t.i10 * C + c, g * t.w10);
+        atomicAdd(g_tex + (int64_t)t.i01 * C + c, g * t.w01);
+        atomicAdd(g_tex + (int64_t)t.i11 * C + c, g * t.w11);
+    }
+}
+
+// texture upload: planar [3,H,W] or interleaved [H,W,3] -> RGBA float4 [H,W]
+__global__ void __launch_bounds__(256) k_pack_texture(const float* __restrict__ src, int H, int W, int layout,
+                                                      float4* __restrict__ dst) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t n = (int64_t)H * W;
+    if (i >= n) return;
+    float4 t;
+    if (layout == TEXIR_TEX_CHW) {
+        t.x = src[i];
+        t.y = src[n + i];
+        t.z = src[2 * n + i];
+    } else {
+        t.x = src[3 * i + 0];
+        t.y = src[3 * i + 1];
+        t.z = src[3 * i + 2];
+    }
+    t.w = 0.f;
+    dst[i] = t;
+}
+
+// per-primitive unit geometric normal for cast_rays' primitive_normals output
+__global__ void __launch_bounds__(256) k_prim_normals(const float4* __restrict__ tris, const uint32_t* __restrict__ prim,
+                                                      int64_t T, const uint32_t* __restrict__ prim_id, int64_t R,
+                                                      const uint32_t* __restrict__ slot_of_prim,
+                                                      float* __restrict__ out) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    uint32_t id = prim_id[r];
+    float x = 0.f, y = 0.f, z = 0.f;
+    if (id != kInvalidId && id < (uint32_t)T) {
+        uint32_t slot = slot_of_prim[id];
+        float4 c = tris[3 * (int64_t)slot + 2];
+        float len = sqrtf(c.y * c.y + c.z * c.z + c.w * c.w);
+        if (len > 0.f) {
+            x = c.y / len;
+            y = c.z / len;
+            z = c.w / len;
+        }
+    }
+    out[3 * r + 0] = x;
+    out[3 * r + 1] = y;
+    out[3 * r + 2] = z;
+}
+
+// ================================================================================================
+// C ABI (include/texir_b200.h)
+// ================================================================================================
+static inline unsigned grid_for(int64_t threads, int block) { return (unsigned)((threads + block - 1) / block); }
+
+template <typename T>
+static int upload(const std::vector<T>& v, void** dptr, int64_t* bytes_acc) {
+    size_t bytes = v.size() * sizeof(T);
+    if (bytes == 0) bytes = 16;
+    TX_CUDA(cudaMalloc(dptr, bytes));
+    if (!v.empty()) TX_CUDA(cudaMemcpy(*dptr, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *bytes_acc += (int64_t)bytes;
+    return 0;
+}
+
+extern "C" {
+
+const char* texir_last_error(void) { return g_err.c_str(); }
+int texir_version(void) { return 100; }
+int64_t texir_launch_count(void) { return g_launches.load(); }
+
+int texir_scene_destroy(texir_scene* sc) {
+    if (!sc) return 0;
+    DeviceGuard guard(sc->info.device);
+    void* ptrs[] = {sc->d_nodes2, sc->d_tris2, sc->d_prim2, sc->d_nodes8, sc->d_tris8,
+                    sc->d_prim8,  sc->d_uvs,   sc->d_slot_of_prim, sc->d_tex};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    delete sc;
+    return 0;
+}
+
+int texir_scene_create(const float* verts_host, int64_t nv, const int32_t* tris_host, int64_t nt,
+                       const double* tri_uvs_host, int device, int build_threads, texir_scene** out) {
+    if (!out) TX_FAIL("texir_scene_create: out is NULL");
+    *out = nullptr;
+    HostBVH bvh;
+    std::string err;
+    try {
+        if (!build_bvh(verts_host, nv, tris_host, nt, build_threads, bvh, err)) TX_FAIL(err);
+    } catch (const std::exception& e) {
+        TX_FAIL(std::string("texir_scene_create: ") + e.what());
+    }
+    int ndev = 0;
+    TX_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) TX_FAIL("texir_scene_create: bad device index");
+    DeviceGuard guard(device);
+    if (!guard.ok) TX_FAIL("texir_scene_create: cannot select device");
+    texir_scene* sc = new texir_scene();
+    sc->info.device = device;
+    int rc = 0;
+    int64_t bytes = 0;
+    std::vector<uint32_t> slot_of_prim((size_t)nt, 0u);
+    for (size_t s = 0; s < bvh.prim2.size(); ++s) slot_of_prim[bvh.prim2[s]] = (uint32_t)s;
+    std::vector<double> uvs;
+    if (tri_uvs_host) uvs.assign(tri_uvs_host, tri_uvs_host + 6 * (size_t)nt);
+    if ((rc = upload(bvh.nodes2, &sc->d_nodes2, &bytes)) || (rc = upload(bvh.tris2, &sc->d_tris2, &bytes)) ||
+        (rc = upload(bvh.prim2, &sc->d_prim2, &bytes)) || (rc = upload(bvh.nodes8, &sc->d_nodes8, &bytes)) ||
+        (rc = upload(bvh.tris8, &sc->d_tris8, &bytes)) || (rc = upload(bvh.prim8, &sc->d_prim8, &bytes)) ||
+        (rc = upload(slot_of_prim, &sc->d_slot_of_prim, &bytes)) || (rc = upload(uvs, &sc->d_uvs, &bytes))) {
+        std::string keep = g_err;
+        texir_scene_destroy(sc);
+        g_err = keep;
+        return rc;
+    }
+    sc->geom_bytes = bytes;
+    sc->view.nodes2 = (const float4*)sc->d_nodes2;
+    sc->view.tris2 = (const float4*)sc->d_tris2;
+    sc->view.prim2 = (const uint32_t*)sc->d_prim2;
+    sc->view.nodes8 = (const uint4*)sc->d_nodes8;
+    sc->view.tris8 = (const float4*)sc->d_tris8;
+    sc->view.prim8 = (const uint32_t*)sc->d_prim8;
+    sc->view.tri_uvs = tri_uvs_host ? (const double*)sc->d_uvs : nullptr;
+    sc->view.tex = nullptr;
+    sc->view.tex_w = sc->view.tex_h = 0;
+    sc->view.num_tris = (uint32_t)nt;
+    sc->info.num_tris = nt;
+    sc->info.num_nodes2 = (int64_t)bvh.nodes2.size() / 4;
+    sc->info.num_nodes8 = (int64_t)bvh.nodes8.size() / 5;
+    sc->info.depth2 = bvh.depth2;
+    sc->info.depth8 = bvh.depth8;
+    sc->info.sah2 = bvh.sah2;
+    sc->info.sah8 = bvh.sah8;
+    sc->info.build_seconds = bvh.build_seconds;
+    sc->info.bvh_kind = TEXIR_BVH8;
+    sc->info.device_bytes = bytes;
+    *out = sc;
+    return 0;
+}
+
+int texir_scene_get_info(const texir_scene* sc, texir_scene_info* info) {
+    if (!sc || !info) TX_FAIL("texir_scene_get_info: NULL argument");
+    *info = sc->info;
+    info->tex_h = sc->view.tex_h;
+    info->tex_w = sc->view.tex_w;
+    info->device_bytes = sc->geom_bytes + sc->tex_bytes;
+    return 0;
+}
+
+int texir_scene_set_bvh(texir_scene* sc, int kind) {
+    if (!sc) TX_FAIL("texir_scene_set_bvh: NULL scene");
+    if (kind != TEXIR_BVH2 && kind != TEXIR_BVH8) TX_FAIL("texir_scene_set_bvh: kind must be 2 or 8");
+    sc->info.bvh_kind = kind;
+    return 0;
+}
+
+int texir_scene_set_texture(texir_scene* sc, const float* tex, int H, int W, int layout, int src_on_device,
+                            void* stream) {
+    if (!sc || !tex) TX_FAIL("texir_scene_set_texture: NULL argument");
+    if (H <= 0 || W <= 0) TX_FAIL("texir_scene_set_texture: empty texture");
+    if (layout != TEXIR_TEX_CHW && layout != TEXIR_TEX_HWC) TX_FAIL("texir_scene_set_texture: bad layout");
+    DeviceGuard guard(sc->info.device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n = (int64_t)H * W;
+    if (sc->view.tex_h != H || sc->view.tex_w != W || !sc->d_tex) {
+        if (sc->d_tex) {
+            TX_CUDA(cudaStreamSynchronize(st));
+            TX_CUDA(cudaFree(sc->d_tex));
+            sc->d_tex = nullptr;
+        }
+        TX_CUDA(cudaMalloc(&sc->d_tex, (size_t)n * sizeof(float4)));
+        sc->tex_bytes = n * (int64_t)sizeof(float4);
+    }
+    const float* src = tex;
+    float* staging = nullptr;
+    if (!src_on_device) {
+        TX_CUDA(cudaMalloc((void**)&staging, (size_t)n * 3 * sizeof(float)));
+        TX_CUDA(cudaMemcpyAsync(staging, tex, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+        src = staging;
+    }
+    k_pack_texture<<<grid_for(n, 256), 256, 0, st>>>(src, H, W, layout, (float4*)sc->d_tex);
+    int rc = finish_launch("k_pack_texture");
+    if (staging) {
+        cudaStreamSynchronize(st);
+        cudaFree(staging);
+    }
+    if (rc) return rc;
+    sc->view.tex = (const float4*)sc->d_tex;
+    sc->view.tex_h = H;
+    sc->view.tex_w = W;
+    return 0;
+}
+
+static int cast_impl(const texir_scene* sc, const float* rays, int64_t R, float* t_hit, uint32_t* prim_id,
+                     float* prim_uv, uint32_t* nvis, uint32_t* ntri, void* stream) {
+    if (!sc || !rays || !t_hit || !prim_id) TX_FAIL("texir_cast_rays: NULL argument");
+    if (R < 0) TX_FAIL("texir_cast_rays: negative ray count");
+    if (R == 0) return 0;
+    DeviceGuard guard(sc->info.device);
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned g = grid_for(R, 128);
+    bool stats = nvis && ntri;
+    if (sc->info.bvh_kind == TEXIR_BVH8) {
+        if (stats)
+            k_cast_rays<8, true><<<g, 128, 0, st>>>(sc->view, rays, R, t_hit, prim_id, prim_uv, nvis, ntri);
+        else
+            k_cast_rays<8, false><<<g, 128, 0, st>>>(sc->view, rays, R, t_hit, prim_id, prim_uv, nullptr, nullptr);
+    } else {
+        if (stats)
+            k_cast_rays<2, true><<<g, 128, 0, st>>>(sc->view, rays, R, t_hit, prim_id, prim_uv, nvis, ntri);
+        else
+            k_cast_rays<2, false><<<g, 128, 0, st>>>(sc->view, rays, R, t_hit, prim_id, prim_uv, nullptr, nullptr);
+    }
+    return finish_launch("k_cast_rays");
+}
+
+int texir_cast_rays(const texir_scene* sc, const float* rays, int64_t R, float* t_hit, uint32_t* prim_id,
+                    float* prim_uv, float* prim_normal, void* stream) {
+    int rc = cast_impl(sc, rays, R, t_hit, prim_id, prim_uv, nullptr, nullptr, stream);
+    if (rc || !prim_normal || R == 0) return rc;
+    DeviceGuard guard(sc->info.device);
+    k_prim_normals<<<grid_for(R, 256), 256, 0, (cudaStream_t)stream>>>(
+        sc->view.tris2, sc->view.prim2, (int64_t)sc->view.num_tris, prim_id, R, (const uint32_t*)sc->d_slot_of_prim,
+        prim_normal);
+    return finish_launch("k_prim_normals");
+}
+
+int texir_cast_rays_stats(const texir_scene* sc, const float* rays, int64_t R, float* t_hit, uint32_t* prim_id,
+                          uint32_t* nodes_visited, uint32_t* tris_tested, void* stream) {
+    if (!nodes_visited || !tris_tested) TX_FAIL("texir_cast_rays_stats: NULL counters");
+    return cast_impl(sc, rays, R, t_hit, prim_id, nullptr, nodes_visited, tris_tested, stream);
+}
+
+static int check_pn(const char* fn, int64_t P, int N) {
+    if (P < 0 || N <= 0) {
+        g_err = std::string(fn) + ": need P >= 0 and N > 0";
+        return 1;
+    }
+    if (N >= (1 << 24)) {
+        g_err = std::string(fn) + ": N must be < 2^24";
+        return 1;
+    }
+    return 0;
+}
+static int check_mode(const char* fn, int mode) {
+    if (mode < 0 || mode > 2) {
+        g_err = std::string(fn) + ": unknown sampling mode";
+        return 1;
+    }
+    return 0;
+}
+
+int texir_generate_dir(const float* nrm, const float* rough, const float* shift, int64_t P, int N, int mode,
+                       float* out, void* stream) {
+    if (check_pn("texir_generate_dir", P, N) || check_mode("texir_generate_dir", mode)) return 1;
+    if (P == 0) return 0;
+    if (!nrm || !shift || !out) TX_FAIL("texir_generate_dir: NULL argument");
+    if (mode == TEXIR_MODE_IMPORTANCE && !rough) TX_FAIL("texir_generate_dir: importance mode needs roughness");
+    DeviceGuard guard(device_of(out));
+    k_generate_dir<<<grid_for(P * N, 256), 256, 0, (cudaStream_t)stream>>>(nrm, rough, shift, P, N, mode, out);
+    return finish_launch("k_generate_dir");
+}
+
+int texir_generate_dir_bwd(const float* nrm, const float* rough, const float* shift, int64_t P, int N,
+                           const float* g_out, float* g_rough, void* stream) {
+    if (check_pn("texir_generate_dir_bwd", P, N)) return 1;
+    if (P == 0) return 0;
+    if (!nrm || !rough || !shift || !g_out || !g_rough) TX_FAIL("texir_generate_dir_bwd: NULL argument");
+    DeviceGuard guard(device_of(g_rough));
+    k_generate_dir_bwd<<<grid_for(P * 32, 128), 128, 0, (cudaStream_t)stream>>>(nrm, rough, shift, P, N, g_out,
+                                                                                  g_rough);
+    return finish_launch("k_generate_dir_bwd");
+}
+
+static int check_scene_tex(const char* fn, const texir_scene* sc) {
+    if (!sc) {
+        g_err = std::string(fn) + ": NULL scene";
+        return 1;
+    }
+    if (!sc->view.tex || !sc->view.tri_uvs) {
+        g_err = std::string(fn) + ": scene has no radiance texture / triangle uvs";
+        return 1;
+    }
+    return 0;
+}
+
+int texir_query_irf(const texir_scene* sc, const float* org, const float* dir, int64_t P, int N, float* rad,
+                    void* stream) {
+    if (check_scene_tex("texir_query_irf", sc) || check_pn("texir_query_irf", P, N)) return 1;
+    if (P == 0) return 0;
+    if (!org || !dir || !rad) TX_FAIL("texir_query_irf: NULL argument");
+    DeviceGuard guard(sc->info.device);
+    unsigned g = grid_for(P * N, 128);
+    if (sc->info.bvh_kind == TEXIR_BVH8)
+        k_query_irf<8><<<g, 128, 0, (cudaStream_t)stream>>>(sc->view, org, dir, P, N, rad);
+    else
+        k_query_irf<2><<<g, 128, 0, (cudaStream_t)stream>>>(sc->view, org, dir, P, N, rad);
+    return finish_launch("k_query_irf");
+}
+
+int texir_irradiance_fwd(const texir_scene* sc, const float* pos, const float* nrm, const float* shift, int64_t P,
+                         int N, int mode, float* E, void* stream) {
+    if (check_scene_tex("texir_irradiance_fwd", sc) || check_pn("texir_irradiance_fwd", P, N) ||
+        check_mode("texir_irradiance_fwd", mode))
+        return 1;
+    if (mode == TEXIR_MODE_IMPORTANCE) TX_FAIL("texir_irradiance_fwd: importance mode needs roughness; use uniform/cosine");
+    if (P == 0) return 0;
+    if (!pos || !nrm || !shift || !E) TX_FAIL("texir_irradiance_fwd: NULL argument");
+    DeviceGuard guard(sc->info.device);
+    const int G = group_lanes(N), ab = coherent_bits(N);
+    const int64_t warps = (P + (32 / G) - 1) / (32 / G);
+    unsigned g = grid_for(warps * 32, 128);
+    if (sc->info.bvh_kind == TEXIR_BVH8)
+        k_irradiance<8><<<g, 128, 0, (cudaStream_t)stream>>>(sc->view, pos, nrm, shift, P, N, mode, G, ab, E);
+    else
+        k_irradiance<2><<<g, 128, 0, (cudaStream_t)stream>>>(sc->view, pos, nrm, shift, P, N, mode, G, ab, E);
+    return finish_launch("k_irradiance");
+}
+
+static int shade_common(const char* fn, const texir_scene* sc, ShadeArgs& a) {
+    if (check_scene_tex(fn, sc) || check_pn(fn, a.P, a.N_spec) || check_mode(fn, a.mode_spec) ||
+        check_mode(fn, a.mode_diff))
+        return 1;
+    if (a.N_diff < 0 || a.N_diff >= (1 << 24)) {
+        g_err = std::string(fn) + ": bad N_diff";
+        return 1;
+    }
+    if (a.N_diff > 0 && a.mode_diff == TEXIR_MODE_IMPORTANCE) {
+        g_err = std::string(fn) + ": diffuse sampling must be uniform or cosine";
+        return 1;
+    }
+    if (!a.nrm || !a.albedo || !a.rough || !a.pos || !a.cam || !a.shift_spec || (a.N_diff == 0 && !a.irr) ||
+        (a.N_diff > 0 && !a.shift_diff)) {
+        g_err = std::string(fn) + ": NULL argument";
+        return 1;
+    }
+    int gs = group_lanes(a.N_spec);
+    int gd = a.N_diff > 0 ? group_lanes(a.N_diff) : gs;
+    a.G = gs > gd ? gs : gd;
+    a.a_spec = coherent_bits(a.N_spec);
+    a.a_diff = a.N_diff > 0 ? coherent_bits(a.N_diff) : 0;
+    return 0;
+}
+
+}  // extern "C"
+
+template <bool TANGENT>
+static int launch_shade(const texir_scene* sc, const ShadeArgs& a, void* stream) {
+    const int64_t warps = (a.P + (32 / a.G) - 1) / (32 / a.G);
+    unsigned g = grid_for(warps * 32, 128);
+    if (sc->info.bvh_kind == TEXIR_BVH8)
+        k_shade<8, TANGENT><<<g, 128, 0, (cudaStream_t)stream>>>(sc->view, a);
+    else
+        k_shade<2, TANGENT><<<g, 128, 0, (cudaStream_t)stream>>>(sc->view, a);
+    return finish_launch("k_shade");
+}
+
+extern "C" {
+
+int texir_shade_fwd(const texir_scene* sc, const float* nrm, const float* albedo, const float* rough,
+                    const float* pos, const float* cam, const float* irr, const float* shift_spec,
+                    const float* shift_diff, int64_t P, int N_spec, int N_diff, int mode_spec, int mode_diff,
+                    float eps, float* rgb, float* drgb_drough, float* ediff, void* stream) {
+    ShadeArgs a{};
+    a.nrm = nrm; a.albedo = albedo; a.rough = rough; a.pos = pos; a.cam = cam; a.irr = irr;
+    a.shift_spec = shift_spec; a.shift_diff = shift_diff;
+    a.P = P; a.N_spec = N_spec; a.N_diff = N_diff; a.mode_spec = mode_spec; a.mode_diff = mode_diff; a.eps = eps;
+    a.rgb = rgb; a.drgb_drough = drgb_drough; a.ediff = ediff;
+    if (shade_common("texir_shade_fwd", sc, a)) return 1;
+    if (P == 0) return 0;
+    if (!rgb) TX_FAIL("texir_shade_fwd: rgb is NULL");
+    DeviceGuard guard(sc->info.device);
+    return drgb_drough ? launch_shade<true>(sc, a, stream) : launch_shade<false>(sc, a, stream);
+}
+
+int texir_shade_bwd(const texir_scene* sc, const float* nrm, const float* albedo, const float* rough,
+                    const float* pos, const float* cam, const float* irr, const float* shift_spec,
+                    const float* shift_diff, int64_t P, int N_spec, int N_diff, int mode_spec, int mode_diff,
+                    float eps, const float* g_rgb, const float* drgb_drough, const float* ediff, float* g_albedo,
+                    float* g_rough, float* g_irr, void* stream) {
+    ShadeArgs a{};
+    a.nrm = nrm; a.albedo = albedo; a.rough = rough; a.pos = pos; a.cam = cam; a.irr = irr;
+    a.shift_spec = shift_spec; a.shift_diff = shift_diff;
+    a.P = P; a.N_spec = N_spec; a.N_diff = N_diff; a.mode_spec = mode_spec; a.mode_diff = mode_diff; a.eps = eps;
+    a.g_rgb = g_rgb; a.g_albedo = g_albedo; a.g_rough = g_rough; a.g_irr = g_irr;
+    a.drgb_drough = const_cast<float*>(drgb_drough);
+    a.ediff = const_cast<float*>(ediff);
+    if (shade_common("texir_shade_bwd", sc, a)) return 1;
+    if (P == 0) return 0;
+    if (!g_rgb) TX_FAIL("texir_shade_bwd: g_rgb is NULL");
+    DeviceGuard guard(sc->info.device);
+    const bool have_stash = drgb_drough && (N_diff == 0 || ediff);
+    if (have_stash) {
+        k_shade_bwd_stash<<<grid_for(P, 256), 256, 0, (cudaStream_t)stream>>>(a);
+        return finish_launch("k_shade_bwd_stash");
+    }
+    return launch_shade<true>(sc, a, stream);
+}
+
+int texir_specular_reflectance(const float* lighting, const float* h, const float* n, const float* v, const float* l,
+                               const float* rough, int64_t P, int N, float eps, float* out, void* stream) {
+    if (check_pn("texir_specular_reflectance", P, N)) return 1;
+    if (P == 0) return 0;
+    if (!lighting || !h || !n || !v || !l || !rough || !out) TX_FAIL("texir_specular_reflectance: NULL argument");
+    DeviceGuard guard(device_of(out));
+    k_specular<<<grid_for(P * 32, 128), 128, 0, (cudaStream_t)stream>>>(lighting, h, n, v, l, rough, P, N, eps, out);
+    return finish_launch("k_specular");
+}
+
+int texir_specular_reflectance_bwd(const float* lighting, const float* h, const float* n, const float* v,
+                                   const float* l, const float* rough, int64_t P, int N, float eps,
+                                   const float* g_out, float* g_lighting, float* g_h, float* g_l, float* g_rough,
+                                   void* stream) {
+    if (check_pn("texir_specular_reflectance_bwd", P, N)) return 1;
+    if (P == 0) return 0;
+    if (!lighting || !h || !n || !v || !l || !rough || !g_out) TX_FAIL("texir_specular_reflectance_bwd: NULL argument");
+    DeviceGuard guard(device_of(g_out));
+    k_specular_bwd<<<grid_for(P * 32, 128), 128, 0, (cudaStream_t)stream>>>(lighting, h, n, v, l, rough, P, N, eps,
+                                                                              g_out, g_lighting, g_h, g_l, g_rough);
+    return finish_launch("k_specular_bwd");
+}
+
+int texir_diffuse_reflectance(const float* lighting, const float* l, const float* n, const float* albedo, int64_t P,
+                              int N, int cosine, float* out, void* stream) {
+    if (check_pn("texir_diffuse_reflectance", P, N)) return 1;
+    if (P == 0) return 0;
+    if (!lighting || !l || !n || !albedo || !out) TX_FAIL("texir_diffuse_reflectance: NULL argument");
+    DeviceGuard guard(device_of(out));
+    k_diffuse<<<grid_for(P * 32, 128), 128, 0, (cudaStream_t)stream>>>(lighting, l, n, albedo, P, N, cosine, out);
+    return finish_launch("k_diffuse");
+}
+
+int texir_diffuse_reflectance_bwd(const float* lighting, const float* l, const float* n, const float* albedo,
+                                  int64_t P, int N, int cosine, const float* g_out, float* g_lighting, float* g_l,
+                                  float* g_albedo, void* stream) {
+    if (check_pn("texir_diffuse_reflectance_bwd", P, N)) return 1;
+    if (P == 0) return 0;
+    if (!lighting || !l || !n || !albedo || !g_out) TX_FAIL("texir_diffuse_reflectance_bwd: NULL argument");
+    DeviceGuard guard(device_of(g_out));
+    k_diffuse_bwd<<<grid_for(P * 32, 128), 128, 0, (cudaStream_t)stream>>>(lighting, l, n, albedo, P, N, cosine,
+                                                                             g_out, g_lighting, g_l, g_albedo);
+    return finish_launch("k_diffuse_bwd");
+}
+
+int texir_texture_fetch(const float* tex, int H, int W, int C, const float* uv, int64_t P, float* out, void* stream) {
+    if (H <= 0 || W <= 0 || C <= 0 || P < 0) TX_FAIL("texir_texture_fetch: bad shape");
+    if (P == 0) return 0;
+    if (!tex || !uv || !out) TX_FAIL("texir_texture_fetch: NULL argument");
+    DeviceGuard guard(device_of(out));
+    k_texture_fetch<<<grid_for(P, 256), 256, 0, (cudaStream_t)stream>>>(tex, H, W, C, uv, P, out);
+    return finish_launch("k_texture_fetch");
+}
+
+int texir_texture_scatter(const float* g_out, int H, int W, int C, const float* uv, int64_t P, float* g_tex,
+                          void* stream) {
+    if (H <= 0 || W <= 0 || C <= 0 || P < 0) TX_FAIL("texir_texture_scatter: bad shape");
+    if (P == 0) return 0;
+    if (!g_out || !uv || !g_tex) TX_FAIL("texir_texture_scatter: NULL argument");
+    DeviceGuard guard(device_of(g_tex));
+    k_texture_scatter<<<grid_for(P, 256), 256, 0, (cudaStream_t)stream>>>(g_out, H, W, C, uv, P, g_tex);
+    return finish_launch("k_texture_scatter");
+}
+
+}  // extern "C"
