@@ -1,0 +1,387 @@
+#!/usr/bin/env python
+"""bench.py -- ray-samples/s of the TexIR hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            our CUDA path (one process per GPU)
+    python bench.py --impl reference [--steps K] [--warmup W]      the reference's CPU algorithm (oracle port)
+
+Workload (BASELINE.json configs[1], SURVEY.md section 8d "C2"): IrT generation on the synthetic closed room,
+T = 2^20 triangles, 4096^2 HDR radiance texture, P = 1 048 576 texels, 2048 uniform samples per texel
+-> 2 147 483 648 ray-samples per step per GPU.  A "step" is one pass of the fused kernel over all P texels
+(the reference walks them in 2048 batches of 512, models/tracer_o3d_irt.py:156-173).  Multi-GPU: every rank
+holds the scene and processes its own P texels (weak scaling, no data-path collective).
+
+One JSON line on stdout (rank 0); see the task contract for the keys.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "ray-samples/sec (fwd+bwd) at 1M tris / 2048 spp; HBM roofline %"
+UNIT = "ray-samples/s"
+NUM_TRIS = 1 << 20
+TEX_RES = 4096
+SPP = 2048
+
+
+def b_alg(num_tris: int) -> int:
+    """algorithmic bytes per ray-sample: single root-to-leaf BVH2 path of 64-byte nodes,
+    one 4-triangle leaf (192 B), per-corner UVs (24 B), 4 bilinear taps of 12 B"""
+    import math
+    return 64 * math.ceil(math.log2(num_tris / 4)) + 192 + 24 + 48
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic_bytes_per_launch(points: int, spp: int):
+    """dram bytes of the dominant kernel from the committed ncu --set full capture (profiles/traffic.json),
+    scaled per ray-sample to this launch; None if no capture has been committed"""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return None
+    try:
+        d = json.load(open(p))
+        return float(d["dram_bytes_per_ray_sample"]) * points * spp
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)"""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.path = "/tmp/texir_clocks_%d_%d.csv" % (os.getpid(), index)
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+                power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        if sm:
+            out.update({"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                        "power_w_max": max(power), "samples": len(sm)})
+        return out
+
+
+def make_workload(seed_offset: int = 0):
+    from texir_code_b200 import synth
+    sc = synth.make_room_scene(NUM_TRIS, seed=666)
+    tex = synth.make_radiance_texture(TEX_RES, seed=666)
+    return sc, tex
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference arm: the reference's CPU algorithm (oracle port; Open3D/Embree cannot be installed here)
+# ---------------------------------------------------------------------------------------------------
+def cpu_reference_rate(sc, tex, points: int, spp: int, steps: int, warmup: int, threads: int):
+    """ray-samples/s of the reference IrT loop body on the host: reference Python restated in torch
+    (single torch thread, as the reference sets) + the C BVH closest hit on `threads` cores"""
+    import numpy as np
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import texir_oracle as O
+    from texir_code_b200 import synth
+    torch.set_num_threads(1)  # trainer/generate_ir_texture.py:34
+    oscene = O.OracleScene(sc.vertices, sc.triangles, threads=threads)
+    pos, nrm = synth.sample_surface_points(sc, points, seed=21)
+    tpos, tnrm, ttex = torch.from_numpy(pos), torch.from_numpy(nrm), torch.from_numpy(tex)
+    torch.manual_seed(666)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        O.irt_forward(oscene, sc.triangle_uvs, ttex, tpos, tnrm, spp, "uniform", 512, None)
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    return points * spp * len(times) / total, total / len(times)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    threads = os.cpu_count() or 1
+    sc, tex = make_workload()
+    points = 512  # one batch of the reference loop (tracer_o3d_irt.py:156) = 1 048 576 ray-samples per step
+    rate, sec = cpu_reference_rate(sc, tex, points, SPP, args.steps, args.warmup, threads)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "IrT generation, synthetic closed room, T=2^20 triangles, 4096^2 radiance texture, "
+                               "2048 spp uniform (BASELINE configs[1])",
+                   "step": "one 512-texel batch of the reference loop (bounded sample of the 1 048 576-texel job)"},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": "512 texels x 2048 spp per step; reference Python restated in torch (1 torch thread, "
+                                   "as the reference sets) + C BVH closest hit on %d threads; NOT Embree" % threads},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from texir_code_b200 import launch_count, models, ops, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    P = args.points
+    sc, tex = make_workload()
+    t_build = time.perf_counter()
+    tracer = models.TracerO3d(sc.vertices, sc.triangles, sc.triangle_uvs, torch.from_numpy(tex), sample_l=[SPP, 64],
+                              device=dev)
+    tracer.scene.set_texture(tracer.texture)
+    t_build = time.perf_counter() - t_build
+    info = tracer.scene.info()
+    # per-rank texel set (weak scaling: every rank has its own P texels)
+    pos, nrm = synth.sample_surface_points(sc, P, seed=666 + 1000 * rank)
+    torch.manual_seed(666 + rank)
+    shift = torch.rand(P, 1, 2)
+    h_pos, h_nrm, h_shift = (torch.from_numpy(pos).pin_memory(), torch.from_numpy(nrm).pin_memory(), shift.pin_memory())
+    h_out = torch.empty(P, 3).pin_memory()
+    d_pos, d_nrm, d_shift = h_pos.to(dev), h_nrm.to(dev), h_shift.to(dev)
+    d_out = torch.empty(P, 3, device=dev)
+    stream = torch.cuda.current_stream(dev)
+
+    def step_resident():
+        ops.irradiance(tracer.scene, d_pos, d_nrm, d_shift, SPP, "uniform", out=d_out)
+
+    def step_e2e():
+        # the call a user makes: host buffers in, host buffer out (tracer.irradiance on freshly copied inputs)
+        p = h_pos.to(dev, non_blocking=True)
+        n = h_nrm.to(dev, non_blocking=True)
+        s = h_shift.to(dev, non_blocking=True)
+        e = tracer.irradiance(p, n, s)
+        h_out.copy_(e, non_blocking=True)
+
+    # ---- device-resident timing (value) ------------------------------------------------------------
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    n_launch0 = launch_count()
+    kernel_ms = []
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for a, b in ev:
+        a.record(stream)
+        step_resident()
+        b.record(stream)
+    e1.record(stream)
+    barrier()
+    launches = launch_count() - n_launch0
+    clocks = sampler.stop() if rank == 0 else {}
+    elapsed_ms = e0.elapsed_time(e1)
+    kernel_ms = [a.elapsed_time(b) for a, b in ev]
+    t = torch.tensor([elapsed_ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    value = world * P * SPP * args.steps / (elapsed_ms * 1e-3)
+
+    # ---- end-to-end timing through the public API with host buffers --------------------------------
+    for _ in range(max(1, min(args.warmup, 2))):
+        step_e2e()
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_e2e()
+    e1.record(stream)
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    e2e_value = world * P * SPP * args.steps / (e2e_ms * 1e-3)
+    h2d = (h_pos.numel() + h_nrm.numel() + h_shift.numel()) * 4
+    d2h = h_out.numel() * 4
+    checksum = float(h_out.double().sum().item())
+
+    # ---- material stage (C3 shape: 98 304 pixels, 256 spp importance, forward + backward) ----------
+    mat = None
+    if rank == 0 and not args.no_mat:
+        mat = bench_material_stage(tracer.scene, sc, dev, args)
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only) ------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        threads = os.cpu_count() or 1
+        rate, sec = cpu_reference_rate(sc, tex, 512, SPP, 3, 1, threads)
+        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": "3 steps of 512 texels x 2048 spp (%.1f s each); reference Python restated in torch (1 torch "
+                         "thread) + C BVH closest hit on %d threads; NOT Embree" % (sec, threads)}
+
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        balg = b_alg(NUM_TRIS)
+        k_ms = statistics.mean(kernel_ms)
+        achieved = balg * P * SPP / (k_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {
+                "workload": "IrT generation (BASELINE configs[1]): synthetic closed room, T=2^20 triangles, 4096^2 "
+                            "fp32 radiance texture, P=%d texels per GPU x 2048 spp uniform, forward only (the "
+                            "reference's IrT stage has no backward; the Mat-stage fwd+bwd is under 'mat_stage')" % P,
+                "points_per_gpu": P, "spp": SPP, "triangles": NUM_TRIS, "texture": [TEX_RES, TEX_RES],
+                "bvh": "BVH%d" % info["bvh_kind"], "scene_bytes": info["device_bytes"],
+                "l2": "no flush: BVH + triangles + UVs + texture = %.0f MB resident, larger than the 126 MB L2"
+                      % (info["device_bytes"] / 1e6),
+                "bvh_build_s": round(t_build, 2),
+            },
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": ncu_traffic_bytes_per_launch(P, SPP), "peak_source": peak_src,
+                         "kernel": "k_irradiance", "kernel_ms": k_ms, "alg_bytes_per_ray_sample": balg},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms / args.steps, "checksum": checksum},
+            "gpu_launches": launches,
+            "clocks": clocks,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        if mat is not None:
+            line["mat_stage"] = mat
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def bench_material_stage(scene, sc, dev, args):
+    """BASELINE configs[2] shape: 6x128^2 cube-map pixels, 256 importance samples, forward + backward"""
+    import numpy as np
+    import torch
+    from texir_code_b200 import ops, synth
+    rays = synth.cube_map_rays(128)
+    hit = scene.cast_rays(torch.from_numpy(rays).to(dev))
+    pos, nrm = synth.gbuffer_from_hits(sc, rays, hit["t_hit"].cpu().numpy(),
+                                       hit["primitive_ids"].cpu().numpy().view(np.uint32))
+    P, N = pos.shape[0], 256
+    rough, albedo, irr, g_rgb = synth.make_materials(P, seed=8)
+    torch.manual_seed(666)
+    sh = torch.rand(P, 1, 2).to(dev)
+    t = lambda x: torch.from_numpy(x).to(dev)
+    nrm_d, pos_d, irr_d, g_d, cam = t(nrm), t(pos), t(irr), t(g_rgb), torch.zeros(3, device=dev)
+    out = {"pixels": P, "spp": N}
+    for mode in ("stash", "recompute"):
+        a = t(albedo).requires_grad_(True)
+        r = t(rough).requires_grad_(True)
+
+        def step():
+            a.grad = None
+            r.grad = None
+            rgb = ops.shade(scene, nrm_d, a, r, pos_d, cam, irr_d, sh, num_spec=N, backward=mode)
+            rgb.backward(g_d)
+
+        for _ in range(2):
+            step()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 5
+        e0.record()
+        for _ in range(reps):
+            step()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / reps
+        out["fwd_bwd_%s_ms" % mode] = ms
+        out["fwd_bwd_%s_ray_samples_per_s" % mode] = P * N / (ms * 1e-3)
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--points", type=int, default=1 << 20, help="texels per GPU (default: the full 1024^2 IrT)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-mat", action="store_true", help="skip the material-stage fwd+bwd leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

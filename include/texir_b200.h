@@ -90,6 +90,10 @@ TEXIR_API int texir_cast_rays_stats(const texir_scene* scene, const float* rays,
  * Cranley-Patterson shift drawn by the caller; out [P,N,3]. */
 TEXIR_API int texir_generate_dir(const float* nrm, const float* rough, const float* shift, int64_t P, int N,
                                  int mode, float* out, void* stream);
+/* same with caller-drawn i.i.d. samples [P,N,2] (pre_mode != 'Hammersley', utils/sample_util.py:109-111:
+ * `samples = torch.rand((b, N, 2))`, used as drawn -- no shift, wrap or clamp). */
+TEXIR_API int texir_generate_dir_samples(const float* nrm, const float* rough, const float* samples, int64_t P,
+                                         int N, int mode, float* out, void* stream);
 /* gradient of generate_dir w.r.t. roughness (importance mode): g_out [P,N,3] -> g_rough [P] */
 TEXIR_API int texir_generate_dir_bwd(const float* nrm, const float* rough, const float* shift, int64_t P, int N,
                                      const float* g_out, float* g_rough, void* stream);

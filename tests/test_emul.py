@@ -1,0 +1,152 @@
+"""CPU: the kernels' host/device headers (texir_math.h, texir_bvh.h, texir_point.h) and the host BVH builder,
+compiled with g++ (tests/cpu_emul), against the oracle and the reference goldens.  This catches arithmetic bugs
+in the device code on a box without a GPU; the GPU tests (test_gpu_*.py) then check the real kernels."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from conftest import load_golden, rel_l2
+
+
+class EmulScene:
+    def __init__(self, lib, verts, tris, uvs=None, tex=None):
+        self.lib = lib
+        self.v = np.ascontiguousarray(verts, np.float32)
+        self.t = np.ascontiguousarray(tris, np.int32)
+        self.uv = None if uvs is None else np.ascontiguousarray(uvs, np.float64)
+        self.h = lib.emul_scene_create(self.v.ctypes.data, len(self.v), self.t.ctypes.data, len(self.t),
+                                       None if self.uv is None else self.uv.ctypes.data, 2)
+        assert self.h
+        if tex is not None:
+            self.tex = np.ascontiguousarray(tex, np.float32).reshape(3, tex.shape[-2], tex.shape[-1])
+            lib.emul_set_texture(self.h, self.tex.ctypes.data, self.tex.shape[1], self.tex.shape[2])
+
+    def __del__(self):
+        self.lib.emul_scene_destroy(self.h)
+
+    def stats(self):
+        out = np.zeros(7)
+        self.lib.emul_scene_stats(self.h, out.ctypes.data)
+        return out
+
+    def cast(self, kind, rays):
+        rays = np.ascontiguousarray(rays, np.float32)
+        R = len(rays)
+        t, i, uv = np.empty(R, np.float32), np.empty(R, np.uint32), np.empty((R, 2), np.float32)
+        nv, nt = np.empty(R, np.uint32), np.empty(R, np.uint32)
+        self.lib.emul_cast_rays(self.h, kind, rays.ctypes.data, R, t.ctypes.data, i.ctypes.data, uv.ctypes.data,
+                                nv.ctypes.data, nt.ctypes.data)
+        return t, i, uv, nv, nt
+
+
+def _rays(R, seed):
+    rng = np.random.default_rng(seed)
+    o = rng.uniform([-3.5, -1.2, -2.5], [3.5, 1.2, 2.5], size=(R, 3)).astype(np.float32)
+    d = rng.normal(size=(R, 3)).astype(np.float32)
+    d[:4] = 0.0
+    d[4:8] = [[1, 0, 0], [0, -1, 0], [0, 0, 1], [-1, 0, 0]]  # axis-aligned: zero components in the slab test
+    return np.concatenate([o, d], 1)
+
+
+@pytest.mark.parametrize("kind", [2, 8])
+def test_cast_rays_bit_exact_vs_oracle(emul, oracle, kind):
+    g = load_golden("scene_atlas")
+    rays = _rays(6000, 5)
+    t0, i0, u0 = oracle.OracleScene(g["vertices"], g["triangles"], brute=True).cast_rays_np(rays)
+    t, i, uv, nv, nt = EmulScene(emul, g["vertices"], g["triangles"]).cast(kind, rays)
+    assert np.array_equal(i, i0) and np.array_equal(t, t0) and np.array_equal(uv, u0)
+    assert nv.mean() < 60 and nt.mean() < 40  # a traversal, not a scan
+
+
+def test_bvh_build_stats(emul):
+    from texir_code_b200 import synth
+    sc = synth.make_room_scene(20000, clutter=8, tex_res=256)
+    es = EmulScene(emul, sc.vertices, sc.triangles)
+    n2, n8, d2, d8, sah2, sah8, secs = es.stats()
+    assert n2 > 20000 / 3 - 1 and n8 < n2 / 2 and d8 < d2 <= 60
+
+
+@pytest.mark.parametrize("N", [16, 64])
+@pytest.mark.parametrize("mode", ["uniform", "cosine", "importance"])
+def test_generate_dir_vs_reference(emul, N, mode):
+    g = load_golden("generate_dir")
+    nrm, rough, shift = g["normals"], np.ascontiguousarray(g["roughness"].reshape(-1)), np.ascontiguousarray(g["shift"].reshape(-1, 2))
+    out = np.empty((len(nrm), N, 3), np.float32)
+    emul.emul_generate_dir(nrm.ctypes.data, rough.ctypes.data, shift.ctypes.data, len(nrm), N,
+                           {"uniform": 0, "cosine": 1, "importance": 2}[mode], out.ctypes.data)
+    want = g["L_%s_%d" % (mode, N)]
+    # identical up to libm sin/cos ulps.  importance mode: torch's vectorised CPU sqrt is not correctly rounded
+    # (0.6 % of inputs differ from IEEE sqrt by 1 ulp; CUDA's sqrtf -- what the reference really runs -- is IEEE
+    # like ours), and a 1-ulp change of cos(theta) near 1 is amplified in sin(theta) = sqrt(1 - cos^2)
+    assert np.abs(out - want).max() <= (2e-6 if mode == "importance" else 2.5e-7)
+    assert (out == want).mean() > 0.9
+    assert np.all(out[3] == 0)
+
+
+@pytest.mark.parametrize("kind", [2, 8])
+def test_query_irf_vs_reference(emul, scene_golden, kind):
+    name, g = scene_golden
+    es = EmulScene(emul, g["vertices"], g["triangles"], g["triangle_uvs"], g["texture"])
+    for k in ("render_e14_16_", "render_e6_64_"):
+        l, want = np.ascontiguousarray(g[k + "l"]), g[k + "lighting"]
+        P, N = l.shape[:2]
+        rad = np.empty((P, N, 3), np.float32)
+        emul.emul_query_irf(es.h, kind, g["pos"].ctypes.data, l.ctypes.data, P, N, rad.ctypes.data)
+        assert np.array_equal(rad, want)
+    q = load_golden("query_irf_quad")
+    eq = EmulScene(emul, q["vertices"], q["triangles"], q["triangle_uvs"], q["texture"])
+    rad = np.empty((6, 1, 3), np.float32)
+    emul.emul_query_irf(eq.h, kind, q["org"].ctypes.data, q["dir"].ctypes.data, 6, 1, rad.ctypes.data)
+    assert np.array_equal(rad, q["rad"])
+
+
+@pytest.mark.parametrize("kind", [2, 8])
+def test_irradiance_vs_reference(emul, scene_golden, kind):
+    name, g = scene_golden
+    es = EmulScene(emul, g["vertices"], g["triangles"], g["triangle_uvs"], g["texture"])
+    P, N = len(g["irt_pos"]), int(g["irt_N"])
+    sh = np.ascontiguousarray(g["irt_shift"].reshape(P, 2))
+    E = np.empty((P, 3), np.float32)
+    emul.emul_irradiance(es.h, kind, g["irt_pos"].ctypes.data, g["irt_nrm"].ctypes.data, sh.ctypes.data, P, N, 0,
+                         E.ctypes.data)
+    # the atlas scene has a discontinuous texture: a 1-ulp sin/cos difference can move a hit to another
+    # atlas cell, so its bound is the north-star's 1e-4; the smooth scene must be much tighter
+    assert rel_l2(E, g["irt_E"]) < (1e-4 if name == "atlas" else 2e-6)
+    seam = np.all(g["irt_nrm"] == 0, axis=1)
+    assert np.all(E[seam] == 0)
+
+
+@pytest.mark.parametrize("kind", [2, 8])
+@pytest.mark.parametrize("tag,N,eps", [("e14", 16, 1e-14), ("e6", 64, 1e-6)])
+def test_shade_vs_reference(emul, scene_golden, kind, tag, N, eps):
+    name, g = scene_golden
+    es = EmulScene(emul, g["vertices"], g["triangles"], g["triangle_uvs"], g["texture"])
+    k = "render_%s_%d_" % (tag, N)
+    P = len(g["pos"])
+    rough = np.ascontiguousarray(g["rough"].reshape(-1))
+    sh = np.ascontiguousarray(g[k + "shift"].reshape(P, 2))
+    rgb, drgb, ediff = (np.empty((P, 3), np.float32) for _ in range(3))
+    emul.emul_shade(es.h, kind, g["nrm"].ctypes.data, g["albedo"].ctypes.data, rough.ctypes.data, g["pos"].ctypes.data,
+                    g["cam"].ctypes.data, g["irr"].ctypes.data, sh.ctypes.data, None, P, N, 0, 2, 0,
+                    ctypes.c_float(eps), rgb.ctypes.data, drgb.ctypes.data, ediff.ctypes.data)
+    assert rel_l2(rgb, g[k + "rgb"]) < 1e-4
+    g_rough = (g["g_rgb"] * drgb).sum(1)
+    assert rel_l2(g_rough, g[k + "g_rough"]) < 1e-3
+    assert rel_l2(g["g_rgb"] * g["irr"] / np.float32(np.pi), g[k + "g_albedo"]) < 1e-6
+
+
+@pytest.mark.parametrize("dmode", ["uniform", "cosine"])
+def test_relighting_vs_reference(emul, scene_golden, dmode):
+    name, g = scene_golden
+    es = EmulScene(emul, g["vertices"], g["triangles"], g["triangle_uvs"], g["texture"])
+    P = len(g["pos"])
+    rough = np.ascontiguousarray(g["rough"].reshape(-1))
+    shs = np.ascontiguousarray(g["relight_%s_shift_spec" % dmode].reshape(P, 2))
+    shd = np.ascontiguousarray(g["relight_%s_shift_diff" % dmode].reshape(P, 2))
+    rgb, drgb, ediff = (np.empty((P, 3), np.float32) for _ in range(3))
+    emul.emul_shade(es.h, 8, g["nrm"].ctypes.data, g["albedo"].ctypes.data, rough.ctypes.data, g["pos"].ctypes.data,
+                    g["cam"].ctypes.data, None, shs.ctypes.data, shd.ctypes.data, P, 16, 32, 2,
+                    1 if dmode == "cosine" else 0, ctypes.c_float(1e-6), rgb.ctypes.data, drgb.ctypes.data,
+                    ediff.ctypes.data)
+    assert rel_l2(rgb, g["relight_%s_rgb" % dmode]) < 1e-4

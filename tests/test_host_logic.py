@@ -1,0 +1,111 @@
+"""CPU: host-side logic of the package that needs no GPU -- Hammersley helpers, the synthetic scene
+generator, point sharding, and the multi-process (gloo, world_size 2) gather / gradient all-reduce."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+
+
+def test_hammersley_helpers_match_reference_goldens():
+    from texir_code_b200 import sample_util as su
+    g = load_golden("hammersley")
+    for i, want in zip(g["ri_in"], g["ri_out"]):
+        assert su.RadicalInverse(int(i)) == want
+    assert np.array_equal(np.array([su.Hammersley(i, 16) for i in range(16)]), g["ham16"])
+    assert np.array_equal(su.hammersley_table(16), g["ham16"].astype(np.float32))
+    t = su.hammersley_table(2048)
+    assert t.shape == (2048, 2) and len(np.unique(t[:, 1])) == 2048 and t.min() >= 0 and t.max() < 1
+
+
+def test_synthetic_scene_is_a_closed_room_with_exact_counts():
+    from texir_code_b200 import synth
+    for T in (3000, 20000):
+        sc = synth.make_room_scene(T, clutter=6, tex_res=256)
+        assert sc.triangles.shape == (T, 3) and sc.triangle_uvs.shape == (3 * T, 2)
+        assert sc.triangle_uvs.dtype == np.float64 and sc.vertices.dtype == np.float32
+        assert sc.triangles.min() >= 0 and sc.triangles.max() < len(sc.vertices)
+        assert 0 <= sc.triangle_uvs.min() and sc.triangle_uvs.max() <= 1
+        assert np.all(sc.tri_areas > 0)
+    a = synth.make_room_scene(3000, clutter=6, tex_res=256)
+    b = synth.make_room_scene(3000, clutter=6, tex_res=256)
+    assert np.array_equal(a.vertices, b.vertices) and np.array_equal(a.triangles, b.triangles)
+    tex = synth.make_radiance_texture(64)
+    assert tex.shape == (1, 3, 64, 64) and tex.dtype == np.float32 and tex.min() > 0
+    pos, nrm = synth.sample_surface_points(a, 2048, seam_fraction=0.05)
+    seam = np.all(nrm == 0, axis=1)
+    assert 0 < seam.sum() < 300 and np.all(pos[seam] == 0)
+    assert np.allclose(np.linalg.norm(nrm[~seam], axis=1), 1, atol=1e-5)
+    rays = synth.cube_map_rays(8)
+    assert rays.shape == (6 * 64, 6) and np.allclose(np.linalg.norm(rays[:, 3:], axis=1), 1, atol=1e-6)
+
+
+def test_shard_bounds_cover_and_align():
+    from texir_code_b200.parallel import shard_bounds, shard_sizes
+    for P, W, al in ((1048576, 8, 512), (98304, 4, 1), (1000, 3, 512), (7, 8, 1), (0, 2, 1), (513, 2, 512)):
+        spans = [shard_bounds(P, r, W, al) for r in range(W)]
+        assert spans[0][0] == 0 and spans[-1][1] == P
+        for (b0, e0), (b1, e1) in zip(spans, spans[1:]):
+            assert e0 == b1 and b0 <= e0
+        assert all(b % al == 0 or b == P for b, _ in spans)
+        assert sum(shard_sizes(P, W, al)) == P
+    with pytest.raises(ValueError):
+        shard_bounds(10, 2, 2)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    from texir_code_b200.parallel import allreduce_gradients, gather_points, shard_bounds
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        P = 1536 + 200  # ragged: rank 0 gets 1024, rank 1 gets 712
+        full = torch.arange(P * 3, dtype=torch.float32).reshape(P, 3)
+        b, e = shard_bounds(P, rank, world, 512)
+        out = gather_points(full[b:e].clone(), P, 512)
+        ok_gather = torch.equal(out, full)
+        # texture-gradient all-reduce: two "textures", one flat buffer
+        a = torch.nn.Parameter(torch.zeros(8, 8, 3))
+        r = torch.nn.Parameter(torch.zeros(16, 16, 1))
+        a.grad = torch.full_like(a, float(rank + 1))
+        r.grad = torch.full_like(r, 10.0 * (rank + 1))
+        nbytes = allreduce_gradients([a, r])
+        ok_red = bool((a.grad == 3).all() and (r.grad == 30).all() and nbytes == (8 * 8 * 3 + 16 * 16) * 4)
+        q.put((rank, ok_gather, ok_red))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gather_and_gradient_allreduce_world2_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(60)
+    assert res == [(0, True, True), (1, True, True)]
+
+
+def test_single_process_parallel_helpers_are_noops():
+    from texir_code_b200.parallel import allreduce_gradients, gather_points
+    x = torch.ones(5, 3)
+    assert gather_points(x, 5) is x
+    p = torch.nn.Parameter(torch.zeros(2))
+    p.grad = torch.ones(2)
+    assert allreduce_gradients([p]) == 0

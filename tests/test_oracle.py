@@ -1,0 +1,134 @@
+"""CPU: the oracle (oracle/texir_oracle.py + oracle/cast_rays_oracle.c) against the golden vectors written by
+executing the REFERENCE's own Python (oracle/make_golden.py).  The reference has no tests / KATs of its own
+(SURVEY.md section 4), so these goldens are the pin."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, rel_l2
+
+
+def test_hammersley_known_answers(oracle):
+    g = load_golden("hammersley")
+    tab = oracle.hammersley_table(16)
+    assert np.array_equal(tab, g["ham16"].astype(np.float32))
+    for i, want in zip(g["ri_in"], g["ri_out"]):
+        assert oracle.radical_inverse(int(i)) == want
+    # SURVEY section 4 probes
+    assert oracle.radical_inverse(1) == 0.5 and oracle.radical_inverse(3) == 0.75
+    assert list(tab[5]) == [0.3125, 0.625]
+
+
+@pytest.mark.parametrize("N", [16, 64])
+@pytest.mark.parametrize("mode", ["uniform", "cosine", "importance"])
+def test_generate_dir_matches_reference(oracle, N, mode):
+    g = load_golden("generate_dir")
+    nrm = torch.tensor(g["normals"])
+    rough = torch.tensor(g["roughness"], requires_grad=True)
+    L = oracle.generate_dir(nrm, N, None, mode, rough if mode == "importance" else None, shift=torch.tensor(g["shift"]))
+    assert np.array_equal(L.detach().numpy(), g["L_%s_%d" % (mode, N)])
+    assert np.all(L.detach().numpy()[3] == 0.0)  # zero normal -> zero directions, no NaN
+    if mode == "importance":
+        (L * torch.tensor(g["gL_%d" % N])).sum().backward()
+        assert rel_l2(rough.grad.numpy(), g["grough_%d" % N]) < 1e-6
+
+
+def test_generate_dir_draws_reference_shift_stream(oracle):
+    g = load_golden("generate_dir")
+    torch.manual_seed(666)
+    L = oracle.generate_dir(torch.tensor(g["normals"]), 16, None, "uniform")
+    assert np.array_equal(L.numpy(), g["L_uniform_16"])
+    # consecutive 512-row draws == one big draw (TracerO3d relies on it)
+    torch.manual_seed(1)
+    a = torch.cat([torch.rand(512, 1, 2) for _ in range(3)])
+    torch.manual_seed(1)
+    assert torch.equal(a, torch.rand(1536, 1, 2))
+
+
+def test_query_irf_quad_known_answers(oracle):
+    g = load_golden("query_irf_quad")
+    for brute in (True, False):
+        sc = oracle.OracleScene(g["vertices"], g["triangles"], brute=brute)
+        rad = oracle.query_irf(sc, g["triangle_uvs"], torch.tensor(g["texture"]), torch.tensor(g["org"]).unsqueeze(1),
+                               torch.tensor(g["dir"]).reshape(6, 1, 1, 3), 1)
+        assert np.array_equal(rad.numpy(), g["rad"])
+    # SURVEY appendix C probes
+    np.testing.assert_allclose(g["rad"][0, 0], [22.5, 23.5, 24.5], rtol=1e-6)
+    np.testing.assert_allclose(g["rad"][1, 0], [29.7, 30.7, 31.7], rtol=1e-6)
+    np.testing.assert_allclose(g["rad"][2, 0], [37.5, 38.5, 39.5], rtol=1e-6)
+    assert np.all(g["rad"][3] == 0) and np.all(g["rad"][4] == 0)
+
+
+def test_cast_rays_contract_and_bvh_equals_brute(oracle):
+    g = load_golden("scene_atlas")
+    rng = np.random.default_rng(3)
+    R = 4000
+    o = rng.uniform([-3.5, -1.2, -2.5], [3.5, 1.2, 2.5], size=(R, 3)).astype(np.float32)
+    d = rng.normal(size=(R, 3)).astype(np.float32)
+    d[:5] = 0.0  # zero directions never hit
+    rays = np.concatenate([o, d], 1)
+    tb, ib, ub = oracle.OracleScene(g["vertices"], g["triangles"], brute=True).cast_rays_np(rays)
+    tv, iv, uv = oracle.OracleScene(g["vertices"], g["triangles"], brute=False).cast_rays_np(rays)
+    assert np.array_equal(tb, tv) and np.array_equal(ib, iv) and np.array_equal(ub, uv)
+    miss = ib == 0xFFFFFFFF
+    assert miss[:5].all() and np.isinf(tb[miss]).all() and (ub[miss] == 0).all()
+    hit = ~miss
+    assert hit.mean() > 0.9  # closed room
+    # hit point = (1-u-v) v0 + u v1 + v v2  (Open3D's primitive_uvs convention)
+    tri = g["vertices"][g["triangles"][ib[hit].astype(np.int64)]].astype(np.float64)
+    u, v = ub[hit, 0:1].astype(np.float64), ub[hit, 1:2].astype(np.float64)
+    x = tri[:, 0] * (1 - u - v) + tri[:, 1] * u + tri[:, 2] * v
+    y = o[hit].astype(np.float64) + d[hit].astype(np.float64) * tb[hit, None]
+    assert np.abs(x - y).max() < 5e-4
+    # Open3D-style front end
+    res = oracle.OracleScene(g["vertices"], g["triangles"]).cast_rays(rays.reshape(40, 100, 6))
+    assert res["t_hit"].numpy().shape == (40, 100) and res["primitive_uvs"].numpy().shape == (40, 100, 2)
+    assert res["primitive_ids"].numpy().dtype == np.uint32
+
+
+@pytest.mark.parametrize("tag,N,eps", [("e14", 16, 1e-14), ("e6", 64, 1e-6)])
+def test_render_matches_reference(oracle, scene_golden, tag, N, eps):
+    name, g = scene_golden
+    sc = oracle.OracleScene(g["vertices"], g["triangles"])
+    k = "render_%s_%d_" % (tag, N)
+    a = torch.tensor(g["albedo"], requires_grad=True)
+    r = torch.tensor(g["rough"], requires_grad=True)
+    i = torch.tensor(g["irr"], requires_grad=True)
+    out = oracle.render(sc, g["triangle_uvs"], torch.tensor(g["texture"]), [N, N], ["uniform", "importance"],
+                        torch.tensor(g["nrm"]), a, r, torch.tensor(g["pos"]), torch.tensor(g["cam"]), i,
+                        shift_spec=torch.tensor(g[k + "shift"]), eps=eps)
+    (out["rgb"] * torch.tensor(g["g_rgb"])).sum().backward()
+    assert np.array_equal(out["rgb"].detach().numpy(), g[k + "rgb"])
+    assert rel_l2(a.grad.numpy(), g[k + "g_albedo"]) < 1e-6
+    assert rel_l2(r.grad.numpy().reshape(-1), g[k + "g_rough"]) < 1e-5
+    assert rel_l2(i.grad.numpy(), g[k + "g_irr"]) < 1e-6
+    # the stand-alone pieces
+    spec = oracle.specular_reflectance(torch.tensor(g[k + "lighting"]), torch.tensor(g[k + "h"]), torch.tensor(g["nrm"]),
+                                       torch.tensor(g[k + "view"]), torch.tensor(g[k + "l"]), torch.tensor(g["rough"]),
+                                       eps=eps)
+    assert rel_l2(spec.numpy(), g[k + "spec"]) < 1e-6  # summation order of a strided reduce differs by <= 1 ulp
+
+
+@pytest.mark.parametrize("dmode", ["uniform", "cosine"])
+def test_relighting_matches_reference(oracle, scene_golden, dmode):
+    name, g = scene_golden
+    sc = oracle.OracleScene(g["vertices"], g["triangles"])
+    out = oracle.render(sc, g["triangle_uvs"], torch.tensor(g["texture"]), [32, 16], [dmode, "importance"],
+                        torch.tensor(g["nrm"]), torch.tensor(g["albedo"]), torch.tensor(g["rough"]),
+                        torch.tensor(g["pos"]), torch.tensor(g["cam"]), torch.tensor(g["irr"]),
+                        shift_spec=torch.tensor(g["relight_%s_shift_spec" % dmode]),
+                        shift_diff=torch.tensor(g["relight_%s_shift_diff" % dmode]), relighting=True, eps=1e-6)
+    assert rel_l2(out["rgb"].numpy(), g["relight_%s_rgb" % dmode]) < 1e-6
+    d = oracle.diffuse_reflectance(torch.tensor(g["diffuse_%s_lighting" % dmode]), torch.tensor(g["diffuse_%s_l" % dmode]),
+                                   torch.tensor(g["nrm"]), torch.tensor(g["albedo"]), dmode)
+    assert rel_l2(d.numpy(), g["diffuse_%s_out" % dmode]) < 1e-6
+
+
+def test_irt_matches_reference(oracle, scene_golden):
+    name, g = scene_golden
+    sc = oracle.OracleScene(g["vertices"], g["triangles"])
+    E = oracle.irt_forward(sc, g["triangle_uvs"], torch.tensor(g["texture"]), torch.tensor(g["irt_pos"]),
+                           torch.tensor(g["irt_nrm"]), int(g["irt_N"]), "uniform", 512, torch.tensor(g["irt_shift"]))
+    assert np.array_equal(E.numpy(), g["irt_E"])
+    seam = np.all(g["irt_nrm"] == 0, axis=1)
+    assert seam.any() and np.all(E.numpy()[seam] == 0)

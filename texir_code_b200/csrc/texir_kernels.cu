@@ -151,6 +151,22 @@ __global__ void __launch_bounds__(256) k_generate_dir(const float* __restrict__ 
     out[3 * idx + 2] = ds.d.z;
 }
 
+// pre_mode != 'Hammersley': caller-drawn i.i.d. samples [P,N,2], used as drawn
+__global__ void __launch_bounds__(256) k_generate_dir_samples(const float* __restrict__ nrm,
+                                                              const float* __restrict__ rough,
+                                                              const float* __restrict__ samples, int64_t P, int N,
+                                                              int mode, float* __restrict__ out) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P * (int64_t)N) return;
+    int64_t p = idx / N;
+    Frame f = make_frame(load3(nrm, p));
+    float r = (mode == MODE_IMPORTANCE) ? __ldg(rough + p) : 0.f;
+    DirSample ds = sample_dir<false>(f, mode, __ldg(samples + 2 * idx + 0), __ldg(samples + 2 * idx + 1), r);
+    out[3 * idx + 0] = ds.d.x;
+    out[3 * idx + 1] = ds.d.y;
+    out[3 * idx + 2] = ds.d.z;
+}
+
 // one warp per point: g_rough[p] = sum_i g_out[p,i] . dL_i/dr
 __global__ void __launch_bounds__(128) k_generate_dir_bwd(const float* __restrict__ nrm, const float* __restrict__ rough,
                                                           const float* __restrict__ shift, int64_t P, int N,
@@ -842,6 +858,17 @@ int texir_generate_dir(const float* nrm, const float* rough, const float* shift,
     return finish_launch("k_generate_dir");
 }
 
+int texir_generate_dir_samples(const float* nrm, const float* rough, const float* samples, int64_t P, int N, int mode,
+                               float* out, void* stream) {
+    if (check_pn("texir_generate_dir_samples", P, N) || check_mode("texir_generate_dir_samples", mode)) return 1;
+    if (P == 0) return 0;
+    if (!nrm || !samples || !out) TX_FAIL("texir_generate_dir_samples: NULL argument");
+    if (mode == TEXIR_MODE_IMPORTANCE && !rough) TX_FAIL("texir_generate_dir_samples: importance mode needs roughness");
+    DeviceGuard guard(device_of(out));
+    k_generate_dir_samples<<<grid_for(P * N, 256), 256, 0, (cudaStream_t)stream>>>(nrm, rough, samples, P, N, mode, out);
+    return finish_launch("k_generate_dir_samples");
+}
+
 int texir_generate_dir_bwd(const float* nrm, const float* rough, const float* shift, int64_t P, int N,
                            const float* g_out, float* g_rough, void* stream) {
     if (check_pn("texir_generate_dir_bwd", P, N)) return 1;
@@ -970,8 +997,9 @@ int texir_shade_bwd(const texir_scene* sc, const float* nrm, const float* albedo
     if (P == 0) return 0;
     if (!g_rgb) TX_FAIL("texir_shade_bwd: g_rgb is NULL");
     DeviceGuard guard(sc->info.device);
-    const bool have_stash = drgb_drough && (N_diff == 0 || ediff);
-    if (have_stash) {
+    // rays are needed only for a gradient whose forward stash is missing
+    const bool need_rays = (g_rough && !drgb_drough) || (g_albedo && N_diff > 0 && !ediff);
+    if (!need_rays) {
         k_shade_bwd_stash<<<grid_for(P, 256), 256, 0, (cudaStream_t)stream>>>(a);
         return finish_launch("k_shade_bwd_stash");
     }

@@ -1,0 +1,298 @@
+"""Tensor-in / tensor-out operators of the hot path (CUDA float32, autograd-aware).
+
+Each one is a thin torch.autograd.Function over one entry point of libtexir_b200.so:
+
+    query_irf              models/mat_nvdiffrast.py:292-320, models/tracer_o3d_irt.py:240-269
+    specular_reflectance   models/mat_nvdiffrast.py:260-279 (eps 1e-14); models/test_nvdiffrast.py:318-338 (1e-6)
+    diffuse_reflectance    models/mat_nvdiffrast.py:252-258
+    shade                  MaterialModel.render, models/mat_nvdiffrast.py:201-249 -- ONE fused kernel
+                           (relighting branch models/test_nvdiffrast.py:275-295 when N_diff > 0)
+    irradiance             the IrT loop body, models/tracer_o3d_irt.py:165-173 -- ONE fused kernel
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _lib
+from .scene import Scene, _ptr, _stream_ptr
+
+TINY_NUMBER = 1e-6
+TINY_TINY_NUMBER = 1e-14
+
+
+def _f32c(t: torch.Tensor, dev=None) -> torch.Tensor:
+    t = t.detach()
+    if dev is not None and t.device != dev:
+        t = t.to(dev)
+    return t.to(torch.float32).contiguous()
+
+
+def _need_cuda(name: str, t: torch.Tensor):
+    if not t.is_cuda:
+        raise _lib.TexirError("%s: tensors must live on a CUDA device (there is no CPU path)" % name)
+
+
+# --------------------------------------------------------------------------------------------------
+# query_irf
+# --------------------------------------------------------------------------------------------------
+def query_irf(scene: Scene, points: torch.Tensor, directions: torch.Tensor, num_sample: Optional[int] = None
+              ) -> torch.Tensor:
+    """points [P,N,3] (the reference passes ``points.unsqueeze(1).expand_as(dirs)``; [P,3] also accepted),
+    directions [P,N,1,3] or [P,N,3] -> radiance [P,N,3].  Not differentiable (the reference's goes
+    through numpy)."""
+    _need_cuda("query_irf", directions)
+    dev = directions.device
+    d = directions
+    if d.dim() == 4:
+        d = d.reshape(d.shape[0], d.shape[1], 3)
+    P, N = int(d.shape[0]), int(d.shape[1])
+    if num_sample is not None and int(num_sample) != N:
+        raise ValueError("num_sample (%d) does not match directions (%d)" % (num_sample, N))
+    if points.dim() == 3:
+        if points.stride(1) == 0 or N == 1:
+            org = points[:, 0, :]
+        else:
+            org = points[:, 0, :]
+            if not torch.equal(points, org.unsqueeze(1).expand_as(points)):
+                # per-sample origins: trace them as N=1 "points"
+                return query_irf(scene, points.reshape(P * N, 3), d.reshape(P * N, 1, 3), 1).reshape(P, N, 3)
+    else:
+        org = points
+    org = _f32c(org, dev)
+    d = _f32c(d, dev)
+    rad = torch.empty(P, N, 3, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().texir_query_irf(scene.handle, _ptr(org), _ptr(d), P, N, _ptr(rad), _stream_ptr(dev)),
+                   "texir_query_irf")
+    return rad
+
+
+# --------------------------------------------------------------------------------------------------
+# stand-alone BRDF reductions
+# --------------------------------------------------------------------------------------------------
+class _Specular(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, lighting, h, n, v, l, roughness, eps):
+        dev = lighting.device
+        P, N = int(lighting.shape[0]), int(lighting.shape[1])
+        L, hh, ll = _f32c(lighting), _f32c(h), _f32c(l)
+        nn, vv = _f32c(n), _f32c(v)
+        rr = _f32c(roughness).reshape(-1)
+        out = torch.empty(P, 3, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().texir_specular_reflectance(_ptr(L), _ptr(hh), _ptr(nn), _ptr(vv), _ptr(ll), _ptr(rr),
+                                                              P, N, eps, _ptr(out), _stream_ptr(dev)),
+                       "texir_specular_reflectance")
+        ctx.save_for_backward(L, hh, nn, vv, ll, rr)
+        ctx.eps = eps
+        ctx.rshape = roughness.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        L, hh, nn, vv, ll, rr = ctx.saved_tensors
+        dev = L.device
+        P, N = int(L.shape[0]), int(L.shape[1])
+        need = ctx.needs_input_grad
+        gL = torch.empty_like(L) if need[0] else None
+        gh = torch.empty_like(hh) if need[1] else None
+        gl = torch.empty_like(ll) if need[4] else None
+        gr = torch.empty(P, dtype=torch.float32, device=dev) if need[5] else None
+        if need[2] or need[3]:
+            raise NotImplementedError("specular_reflectance: gradients w.r.t. n / v are not provided "
+                                      "(the reference detaches the G-buffer, mat_nvdiffrast.py:126,179)")
+        g = _f32c(g_out)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().texir_specular_reflectance_bwd(_ptr(L), _ptr(hh), _ptr(nn), _ptr(vv), _ptr(ll),
+                                                                  _ptr(rr), P, N, ctx.eps, _ptr(g), _ptr(gL), _ptr(gh),
+                                                                  _ptr(gl), _ptr(gr), _stream_ptr(dev)),
+                       "texir_specular_reflectance_bwd")
+        return gL, gh, None, None, gl, (gr.reshape(ctx.rshape) if gr is not None else None), None
+
+
+def specular_reflectance(lighting, h, n, v, l, roughness, albedo=None, eps: float = TINY_TINY_NUMBER):
+    """lighting, h, l [P,N,3]; n, v [P,3]; roughness [P,1] -> [P,3] (sum over samples, NOT divided by N).
+    ``albedo`` is accepted and ignored like in the reference (mat_nvdiffrast.py:260)."""
+    _need_cuda("specular_reflectance", lighting)
+    return _Specular.apply(lighting, h, n, v, l, roughness, float(eps))
+
+
+class _Diffuse(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, lighting, l, n, albedo, cosine):
+        dev = lighting.device
+        P, N = int(lighting.shape[0]), int(lighting.shape[1])
+        L, ll, nn, aa = _f32c(lighting), _f32c(l), _f32c(n), _f32c(albedo)
+        out = torch.empty(P, 3, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().texir_diffuse_reflectance(_ptr(L), _ptr(ll), _ptr(nn), _ptr(aa), P, N, cosine,
+                                                             _ptr(out), _stream_ptr(dev)), "texir_diffuse_reflectance")
+        ctx.save_for_backward(L, ll, nn, aa)
+        ctx.cosine = cosine
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        L, ll, nn, aa = ctx.saved_tensors
+        dev = L.device
+        P, N = int(L.shape[0]), int(L.shape[1])
+        need = ctx.needs_input_grad
+        if need[2]:
+            raise NotImplementedError("diffuse_reflectance: gradient w.r.t. n is not provided")
+        gL = torch.empty_like(L) if need[0] else None
+        gl = torch.empty_like(ll) if need[1] else None
+        ga = torch.empty_like(aa) if need[3] else None
+        g = _f32c(g_out)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().texir_diffuse_reflectance_bwd(_ptr(L), _ptr(ll), _ptr(nn), _ptr(aa), P, N, ctx.cosine,
+                                                                 _ptr(g), _ptr(gL), _ptr(gl), _ptr(ga),
+                                                                 _stream_ptr(dev)), "texir_diffuse_reflectance_bwd")
+        return gL, gl, None, ga, None
+
+
+def diffuse_reflectance(lighting, l, n, albedo, sample_type: str = "uniform"):
+    """lighting, l [P,N,3]; n, albedo [P,3] -> [P,3] (sum over samples; the caller divides by N)"""
+    _need_cuda("diffuse_reflectance", lighting)
+    return _Diffuse.apply(lighting, l, n, albedo, 1 if sample_type == "cosine" else 0)
+
+
+# --------------------------------------------------------------------------------------------------
+# fused render
+# --------------------------------------------------------------------------------------------------
+class _Shade(torch.autograd.Function):
+    """rgb = albedo * dfac + (1/N) sum_i L_i w_i(roughness).  backward='stash': the forward kernel also
+    emits d rgb / d roughness by forward-mode differentiation (roughness is the only non-trivial
+    input), so backward launches no rays; backward='recompute': nothing is stashed and the backward
+    kernel re-generates the samples and re-casts every ray (the north-star formulation)."""
+
+    @staticmethod
+    def forward(ctx, scene, normal, albedo, roughness, points, cam, irr, shift_spec, shift_diff, N_spec, N_diff,
+                mode_spec, mode_diff, eps, backward_mode):
+        dev = normal.device
+        P = int(normal.shape[0])
+        nrm, alb, pos = _f32c(normal), _f32c(albedo), _f32c(points)
+        rough = _f32c(roughness).reshape(-1)
+        camc = _f32c(cam, dev).reshape(3)
+        irrc = _f32c(irr) if irr is not None else None
+        shs = _f32c(shift_spec, dev).reshape(P, 2)
+        shd = _f32c(shift_diff, dev).reshape(P, 2) if N_diff > 0 else None
+        need_r = roughness.requires_grad
+        need_a = albedo.requires_grad
+        stash = backward_mode == "stash"
+        rgb = torch.empty(P, 3, dtype=torch.float32, device=dev)
+        drgb = torch.empty(P, 3, dtype=torch.float32, device=dev) if (stash and need_r) else None
+        ediff = torch.empty(P, 3, dtype=torch.float32, device=dev) if (stash and N_diff > 0 and need_a) else None
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().texir_shade_fwd(scene.handle, _ptr(nrm), _ptr(alb), _ptr(rough), _ptr(pos), _ptr(camc),
+                                                   _ptr(irrc), _ptr(shs), _ptr(shd), P, N_spec, N_diff, mode_spec,
+                                                   mode_diff, eps, _ptr(rgb), _ptr(drgb), _ptr(ediff),
+                                                   _stream_ptr(dev)), "texir_shade_fwd")
+        ctx.scene = scene
+        ctx.cfg = (P, N_spec, N_diff, mode_spec, mode_diff, eps)
+        ctx.shapes = (albedo.shape, roughness.shape, None if irr is None else irr.shape)
+        ctx.have = (drgb is not None, ediff is not None, irrc is not None, shd is not None)
+        saved = [nrm, alb, rough, pos, camc, shs]
+        for t in (irrc, shd, drgb, ediff):
+            if t is not None:
+                saved.append(t)
+        ctx.save_for_backward(*saved)
+        return rgb
+
+    @staticmethod
+    def backward(ctx, g_rgb):
+        saved = list(ctx.saved_tensors)
+        nrm, alb, rough, pos, camc, shs = saved[:6]
+        rest = saved[6:]
+        have_drgb, have_ediff, have_irr, have_shd = ctx.have
+        irrc = rest.pop(0) if have_irr else None
+        shd = rest.pop(0) if have_shd else None
+        drgb = rest.pop(0) if have_drgb else None
+        ediff = rest.pop(0) if have_ediff else None
+        P, N_spec, N_diff, mode_spec, mode_diff, eps = ctx.cfg
+        dev = nrm.device
+        need = ctx.needs_input_grad  # (scene, normal, albedo, roughness, points, cam, irr, ...)
+        g = _f32c(g_rgb).reshape(P, 3)
+        g_alb = torch.empty(P, 3, dtype=torch.float32, device=dev) if need[2] else None
+        g_rough = torch.empty(P, dtype=torch.float32, device=dev) if need[3] else None
+        g_irr = torch.empty(P, 3, dtype=torch.float32, device=dev) if (need[6] and have_irr) else None
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().texir_shade_bwd(
+                ctx.scene.handle, _ptr(nrm), _ptr(alb), _ptr(rough), _ptr(pos), _ptr(camc), _ptr(irrc), _ptr(shs),
+                _ptr(shd), P, N_spec, N_diff, mode_spec, mode_diff, eps, _ptr(g),
+                _ptr(drgb), _ptr(ediff),
+                _ptr(g_alb), _ptr(g_rough), _ptr(g_irr), _stream_ptr(dev)), "texir_shade_bwd")
+        a_shape, r_shape, i_shape = ctx.shapes
+        return (None, None, g_alb.reshape(a_shape) if g_alb is not None else None,
+                g_rough.reshape(r_shape) if g_rough is not None else None, None, None,
+                g_irr.reshape(i_shape) if g_irr is not None else None, None, None, None, None, None, None, None, None)
+
+
+def shade(scene: Scene, normal, albedo, roughness, points, cam_position, irr, shift_spec, *, num_spec: int,
+          shift_diff=None, num_diff: int = 0, mode_spec: str = "importance", mode_diff: str = "uniform",
+          eps: float = TINY_TINY_NUMBER, backward: str = "stash") -> torch.Tensor:
+    """Fused MaterialModel.render on flat per-point tensors: normal/albedo/points/irr [P,3], roughness [P,1],
+    cam_position [3], shift_spec [P,1,2] -> rgb [P,3].  num_diff > 0 selects the relighting variant
+    (Monte-Carlo diffuse with its own shift, models/test_nvdiffrast.py:275-281)."""
+    _need_cuda("shade", normal)
+    if backward not in ("stash", "recompute"):
+        raise ValueError("backward must be 'stash' or 'recompute'")
+    return _Shade.apply(scene, normal, albedo, roughness, points, cam_position, irr, shift_spec, shift_diff,
+                        int(num_spec), int(num_diff), _lib.MODES[mode_spec], _lib.MODES[mode_diff], float(eps), backward)
+
+
+# --------------------------------------------------------------------------------------------------
+# fused IrT batch
+# --------------------------------------------------------------------------------------------------
+def irradiance(scene: Scene, position: torch.Tensor, normal: torch.Tensor, shift: torch.Tensor, num_samples: int,
+               mode: str = "uniform", out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """E[p] = sum_i L_i clamp(n.l_i,0,1) 2 pi / N for P points in one launch (tracer_o3d_irt.py:168-171);
+    position, normal [P,3], shift [P,1,2] or [P,2] -> [P,3]."""
+    _need_cuda("irradiance", position)
+    dev = position.device
+    P = int(position.shape[0])
+    pos, nrm = _f32c(position), _f32c(normal)
+    sh = _f32c(shift, dev).reshape(P, 2)
+    E = out if out is not None else torch.empty(P, 3, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().texir_irradiance_fwd(scene.handle, _ptr(pos), _ptr(nrm), _ptr(sh), P, int(num_samples),
+                                                    _lib.MODES[mode], _ptr(E), _stream_ptr(dev)), "texir_irradiance_fwd")
+    return E
+
+
+# --------------------------------------------------------------------------------------------------
+# material-texture fetch / gradient scatter (dr.texture 'linear', models/mat_nvdiffrast.py:131-139)
+# --------------------------------------------------------------------------------------------------
+class _TextureFetch(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, tex, uv):
+        dev = tex.device
+        H, W, C = (int(x) for x in tex.shape)
+        P = int(uv.shape[0])
+        t, u = _f32c(tex), _f32c(uv)
+        out = torch.empty(P, C, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().texir_texture_fetch(_ptr(t), H, W, C, _ptr(u), P, _ptr(out), _stream_ptr(dev)),
+                       "texir_texture_fetch")
+        ctx.save_for_backward(u)
+        ctx.shape = (H, W, C)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        (u,) = ctx.saved_tensors
+        dev = u.device
+        H, W, C = ctx.shape
+        g = _f32c(g_out)
+        g_tex = torch.zeros(H, W, C, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().texir_texture_scatter(_ptr(g), H, W, C, _ptr(u), int(u.shape[0]), _ptr(g_tex),
+                                                         _stream_ptr(dev)), "texir_texture_scatter")
+        return g_tex, None
+
+
+def texture_fetch(tex: torch.Tensor, uv: torch.Tensor) -> torch.Tensor:
+    """bilinear fetch of a [H,W,C] material texture at uv [P,2]; backward scatters with atomics"""
+    _need_cuda("texture_fetch", tex)
+    return _TextureFetch.apply(tex, uv)
