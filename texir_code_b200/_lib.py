@@ -10,7 +10,8 @@ import os
 from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, "libtexir_b200.so")
+# TEXIR_LIB: tuning aid -- load another build of the same library (e.g. compiled with different launch bounds)
+SO_PATH = os.environ.get("TEXIR_LIB") or os.path.join(HERE, "libtexir_b200.so")
 
 MODE_UNIFORM, MODE_COSINE, MODE_IMPORTANCE = 0, 1, 2
 MODES = {"uniform": MODE_UNIFORM, "cosine": MODE_COSINE, "importance": MODE_IMPORTANCE}

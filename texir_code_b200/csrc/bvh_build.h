@@ -14,6 +14,9 @@ struct HostBVH {
     std::vector<float4> nodes2;
     std::vector<float4> tris2;  // 3 per slot
     std::vector<uint32_t> prim2;
+    // the same BVH2 with 32-byte nodes: child boxes on a global 16-bit grid (layout: texir_bvh.h)
+    std::vector<uint4> qnodes2;  // 2 per node
+    float qmin[3], qstep[3];
     // BVH8 compressed wide (layout: texir_bvh.h)
     std::vector<uint4> nodes8;  // 5 per node
     std::vector<float4> tris8;

@@ -12,6 +12,11 @@
 //          n2 = (c0.lo.z, c0.hi.z, c1.lo.z, c1.hi.z)   n3 = (child0, child1, -, -) as int bits
 //        child >= 0: inner node index; child < 0: leaf, ~child = (first_slot << 3) | (count-1).
 //
+//  QBVH2 the same tree with 32-byte nodes (2 x uint4): the six planes of each child box as 16-bit indices
+//        on a global grid  x = qmin + q * qstep  (per axis), low half = lo plane, high half = hi plane:
+//          q0 = (c0.x, c0.y, c0.z, c1.x)   q1 = (c1.y, c1.z, child0, child1)
+//        Half the L1 / L2 traffic per node visit of the float layout; this is the layout the kernels walk.
+//
 //  BVH8  80-byte compressed wide nodes (5 x uint4), 8 children with 8-bit quantised boxes on a
 //        per-node power-of-two grid (Ylitie, Karras, Laine: "Efficient Incoherent Ray Traversal
 //        on GPUs Through Compressed Wide BVHs", HPG 2017).  See BVH8 section below.
@@ -49,6 +54,8 @@ struct SceneView {
     const float4* __restrict__ nodes2;     // BVH2 nodes, 4 float4 each
     const float4* __restrict__ tris2;      // BVH2-ordered triangle slots, 3 float4 each
     const uint32_t* __restrict__ prim2;    // slot -> original primitive id
+    const uint4* __restrict__ qnodes2;     // QBVH2 nodes, 2 uint4 each (same indices as nodes2)
+    float qmin[3], qstep[3];               // the global 16-bit grid of qnodes2
     const uint4* __restrict__ nodes8;      // BVH8 nodes, 5 uint4 each
     const float4* __restrict__ tris8;      // BVH8-ordered triangle slots
     const uint32_t* __restrict__ prim8;
@@ -323,9 +330,13 @@ TX_HD V3 fetch_radiance(const SceneView& s, const Hit& h) {
               bilerp_apply(b4, nw.z, ne.z, sw.z, se.z));
 }
 
+TX_HD Hit trace_bvh2_fast(const SceneView& s, V3 o, V3 d);  // texir_stream.h
+TX_HD Hit trace_qbvh2(const SceneView& s, V3 o, V3 d);      // texir_stream.h
 template <int KIND>
 TX_HD Hit trace(const SceneView& s, V3 o, V3 d) {
     if (KIND == 8) return trace_bvh8(s, o, d);
+    if (KIND == 4) return trace_qbvh2(s, o, d);      // 32-byte quantised BVH2 nodes
+    if (KIND == 3) return trace_bvh2_fast(s, o, d);  // BVH2 layout, cheaper node step
     return trace_bvh2(s, o, d);
 }
 

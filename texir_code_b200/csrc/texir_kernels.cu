@@ -8,6 +8,7 @@
 
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -30,6 +31,7 @@ struct texir_scene {
     void* d_nodes2 = nullptr;
     void* d_tris2 = nullptr;
     void* d_prim2 = nullptr;
+    void* d_qnodes2 = nullptr;
     void* d_nodes8 = nullptr;
     void* d_tris8 = nullptr;
     void* d_prim8 = nullptr;
@@ -74,6 +76,27 @@ static int device_of(const void* p) {
         return d;
     }
     return a.device;
+}
+
+// tuning knobs (environment, read once): TEXIR_STREAM=0 selects the lock-step kernels, TEXIR_REFILL=n the
+// number of still-traversing lanes below which a warp refills its idle lanes
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+static int stream_mode() {  // 0: first lock-step kernels, 1: ray-stream kernels, 2: lock-step + cheaper node step,
+                            // 3 (default): 2 + the occupancy-tuned IrT kernel
+    static const int m = env_int("TEXIR_STREAM", 3);
+    return m;
+}
+static bool use_stream() { return stream_mode() == 1; }
+static bool use_qnodes() {  // TEXIR_QNODES=0: walk the 64-byte float nodes instead of the 32-byte quantised ones
+    static const bool on = env_int("TEXIR_QNODES", 1) != 0;
+    return on;
+}
+static int refill_threshold() {
+    static const int r = env_int("TEXIR_REFILL", 20);
+    return r < 1 ? 1 : (r > 33 ? 33 : r);
 }
 
 static int finish_launch(const char* what) {
@@ -214,8 +237,11 @@ __global__ void __launch_bounds__(128) k_query_irf(SceneView s, const float* __r
 // ------------------------------------------------------------------------------------------------
 // fused IrT: E = sum_i L_i clamp(n.l_i) * 2 pi / N       (models/tracer_o3d_irt.py:168-171)
 // ------------------------------------------------------------------------------------------------
+#ifndef TX_IRR_MINB
+#define TX_IRR_MINB 8
+#endif
 template <int KIND>
-__global__ void __launch_bounds__(128) k_irradiance(SceneView s, const float* __restrict__ pos,
+__global__ void __launch_bounds__(128, TX_IRR_MINB) k_irradiance(SceneView s, const float* __restrict__ pos,
                                                     const float* __restrict__ nrm, const float* __restrict__ shift,
                                                     int64_t P, int N, int mode, int G, int abits,
                                                     float* __restrict__ E) {
@@ -229,6 +255,102 @@ __global__ void __launch_bounds__(128) k_irradiance(SceneView s, const float* __
     irradiance_lane<KIND>(s, load3(nrm, p), load3(pos, p), __ldg(shift + 2 * p + 0), __ldg(shift + 2 * p + 1), N, mode,
                           gl, G, abits, acc);
     float ax = group_sum(acc[0], G), ay = group_sum(acc[1], G), az = group_sum(acc[2], G);
+    if (live && gl == 0) {
+        E[3 * p + 0] = irradiance_finish(ax, N);
+        E[3 * p + 1] = irradiance_finish(ay, N);
+        E[3 * p + 2] = irradiance_finish(az, N);
+    }
+}
+
+// Occupancy-tuned IrT kernel for G == 32 (N >= 32): measured on B200 the traversal is latency bound (ncu:
+// long-scoreboard stalls, 1.2 eligible warps per scheduler at 8 warps), so the kernel is written to fit 40
+// registers = 12 CTAs x 4 warps per SM: the per-point constants (tangent frame, normal, shift) live in shared
+// memory and are read back (broadcast) only while a direction is generated, the per-lane sums live in shared
+// memory too.  Same sample order and accumulation order as k_irradiance -> bit-identical results.
+struct IrtPointSmem {
+    float nx, ny, nz;     // raw normal
+    float fn[3], fu[3], fv[3];
+    float sh0, sh1;
+};
+#ifndef TX_LEAN_MINB
+#define TX_LEAN_MINB 12
+#endif
+template <int KIND>
+__global__ void __launch_bounds__(128, TX_LEAN_MINB) k_irradiance_lean(SceneView s, const float* __restrict__ pos,
+                                                             const float* __restrict__ nrm,
+                                                             const float* __restrict__ shift, int64_t P, int N, int mode,
+                                                             int abits, float* __restrict__ E) {
+    __shared__ IrtPointSmem sm_pt[4];
+    __shared__ float sm_acc[3][128];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int64_t p = (int64_t)blockIdx.x * 4 + wid;
+    const bool live = p < P;
+    if (!live) p = P - 1;
+    if (lane == 0) {
+        V3 n = load3(nrm, p);
+        Frame f = make_frame(n);
+        IrtPointSmem& q = sm_pt[wid];
+        q.nx = n.x; q.ny = n.y; q.nz = n.z;
+        q.fn[0] = f.n.x; q.fn[1] = f.n.y; q.fn[2] = f.n.z;
+        q.fu[0] = f.u.x; q.fu[1] = f.u.y; q.fu[2] = f.u.z;
+        q.fv[0] = f.v.x; q.fv[1] = f.v.y; q.fv[2] = f.v.z;
+        q.sh0 = __ldg(shift + 2 * p + 0);
+        q.sh1 = __ldg(shift + 2 * p + 1);
+    }
+    sm_acc[0][threadIdx.x] = 0.f;
+    sm_acc[1][threadIdx.x] = 0.f;
+    sm_acc[2][threadIdx.x] = 0.f;
+    __syncwarp();
+    const V3 o = load3(pos, p);
+    const volatile IrtPointSmem* q = &sm_pt[wid];
+    const int M = (N + (1 << abits) - 1) >> abits;
+    for (int c = 0; c < (1 << abits); ++c) {
+        for (int j = lane; j < M; j += 32) {
+            const uint32_t i = ((uint32_t)j << abits) + (uint32_t)c;
+            if (i >= (uint32_t)N) continue;
+            V3 d;
+            {
+                Frame f;
+                f.n = v3(q->fn[0], q->fn[1], q->fn[2]);
+                f.u = v3(q->fu[0], q->fu[1], q->fu[2]);
+                f.v = v3(q->fv[0], q->fv[1], q->fv[2]);
+                float s0 = shift_wrap_clamp(hammersley0(i, (uint32_t)N), q->sh0);
+                float s1 = shift_wrap_clamp(radical_inverse(i), q->sh1);
+                d = sample_dir<false>(f, mode, s0, s1, 0.f).d;
+            }
+            Hit h = trace<KIND>(s, o, d);
+            V3 L = fetch_radiance(s, h);
+            float ndl = clamp01(rn_dot(v3(q->nx, q->ny, q->nz), d));
+            sm_acc[0][threadIdx.x] += L.x * ndl;
+            sm_acc[1][threadIdx.x] += L.y * ndl;
+            sm_acc[2][threadIdx.x] += L.z * ndl;
+        }
+    }
+    float ax = group_sum(sm_acc[0][threadIdx.x], 32), ay = group_sum(sm_acc[1][threadIdx.x], 32),
+          az = group_sum(sm_acc[2][threadIdx.x], 32);
+    if (live && lane == 0) {
+        E[3 * p + 0] = irradiance_finish(ax, N);
+        E[3 * p + 1] = irradiance_finish(ay, N);
+        E[3 * p + 2] = irradiance_finish(az, N);
+    }
+}
+
+// ray-stream variant (texir_stream.h): same sums, lanes do not wait for each other between rays
+__global__ void __launch_bounds__(128) k_irradiance_stream(SceneView s, const float* __restrict__ pos,
+                                                           const float* __restrict__ nrm,
+                                                           const float* __restrict__ shift, int64_t P, int N, int mode,
+                                                           int G, int abits, int refill, float* __restrict__ E) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int gl = lane & (G - 1);
+    int64_t p = warp * (32 / G) + lane / G;
+    const bool live = p < P;
+    if (!live) p = P - 1;
+    IrtWork w;
+    w.init(&s, load3(nrm, p), load3(pos, p), __ldg(shift + 2 * p + 0), __ldg(shift + 2 * p + 1), N, mode, gl, G, abits,
+           live);
+    trace_stream_bvh2(s, w, refill);
+    float ax = group_sum(w.ax, G), ay = group_sum(w.ay, G), az = group_sum(w.az, G);
     if (live && gl == 0) {
         E[3 * p + 0] = irradiance_finish(ax, N);
         E[3 * p + 1] = irradiance_finish(ay, N);
@@ -263,39 +385,10 @@ struct ShadeArgs {
     float* g_irr;
 };
 
-template <int KIND, bool TANGENT>
-__global__ void __launch_bounds__(128) k_shade(SceneView s, ShadeArgs a) {
-    const int G = a.G;
-    const int lane = threadIdx.x & 31;
-    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int gl = lane & (G - 1);
-    int64_t p = warp * (32 / G) + lane / G;
-    const bool live = p < a.P;
-    if (!live) p = a.P - 1;
-    const V3 cam = v3(__ldg(a.cam + 0), __ldg(a.cam + 1), __ldg(a.cam + 2));
-    float shd0 = 0.f, shd1 = 0.f;
-    if (a.N_diff > 0) {
-        shd0 = __ldg(a.shift_diff + 2 * p + 0);
-        shd1 = __ldg(a.shift_diff + 2 * p + 1);
-    }
-    ShadeLaneOut lo;
-    shade_lane<KIND, TANGENT>(s, load3(a.nrm, p), load3(a.pos, p), cam, __ldg(a.rough + p), a.eps,
-                              __ldg(a.shift_spec + 2 * p + 0), __ldg(a.shift_spec + 2 * p + 1), a.N_spec, a.mode_spec,
-                              a.a_spec, shd0, shd1, a.N_diff, a.mode_diff, a.a_diff, gl, G, lo);
-    float sx = group_sum(lo.spec[0], G), sy = group_sum(lo.spec[1], G), sz = group_sum(lo.spec[2], G);
-    float dx = 0.f, dy = 0.f, dz = 0.f;
-    if (TANGENT) {
-        dx = group_sum(lo.dspec[0], G);
-        dy = group_sum(lo.dspec[1], G);
-        dz = group_sum(lo.dspec[2], G);
-    }
-    float dsum[3] = {0.f, 0.f, 0.f};
-    if (a.N_diff > 0) {
-        dsum[0] = group_sum(lo.diff[0], G);
-        dsum[1] = group_sum(lo.diff[1], G);
-        dsum[2] = group_sum(lo.diff[2], G);
-    }
-    if (!live || gl != 0) return;
+// per-point epilogue of k_shade / k_shade_stream (lane gl == 0 of a live point)
+template <bool TANGENT>
+__device__ __forceinline__ void shade_epilogue(const ShadeArgs& a, int64_t p, float sx, float sy, float sz, float dx,
+                                               float dy, float dz, const float dsum[3]) {
     const float inv_ns = 1.0f / (float)a.N_spec;
     float irr[3] = {0.f, 0.f, 0.f}, dfac[3];
     if (a.N_diff == 0) {
@@ -335,6 +428,70 @@ __global__ void __launch_bounds__(128) k_shade(SceneView s, ShadeArgs a) {
             a.g_irr[3 * p + 2] = lit ? g.z * al.z / kPi : 0.f;
         }
     }
+}
+
+template <bool TANGENT>
+__device__ __forceinline__ void shade_reduce_store(const ShadeArgs& a, const ShadeLaneOut& lo, int64_t p, bool live,
+                                                   int gl, int G) {
+    float sx = group_sum(lo.spec[0], G), sy = group_sum(lo.spec[1], G), sz = group_sum(lo.spec[2], G);
+    float dx = 0.f, dy = 0.f, dz = 0.f;
+    if (TANGENT) {
+        dx = group_sum(lo.dspec[0], G);
+        dy = group_sum(lo.dspec[1], G);
+        dz = group_sum(lo.dspec[2], G);
+    }
+    float dsum[3] = {0.f, 0.f, 0.f};
+    if (a.N_diff > 0) {
+        dsum[0] = group_sum(lo.diff[0], G);
+        dsum[1] = group_sum(lo.diff[1], G);
+        dsum[2] = group_sum(lo.diff[2], G);
+    }
+    if (live && gl == 0) shade_epilogue<TANGENT>(a, p, sx, sy, sz, dx, dy, dz, dsum);
+}
+
+template <int KIND, bool TANGENT>
+__global__ void __launch_bounds__(128) k_shade(SceneView s, ShadeArgs a) {
+    const int G = a.G;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int gl = lane & (G - 1);
+    int64_t p = warp * (32 / G) + lane / G;
+    const bool live = p < a.P;
+    if (!live) p = a.P - 1;
+    const V3 cam = v3(__ldg(a.cam + 0), __ldg(a.cam + 1), __ldg(a.cam + 2));
+    float shd0 = 0.f, shd1 = 0.f;
+    if (a.N_diff > 0) {
+        shd0 = __ldg(a.shift_diff + 2 * p + 0);
+        shd1 = __ldg(a.shift_diff + 2 * p + 1);
+    }
+    ShadeLaneOut lo;
+    shade_lane<KIND, TANGENT>(s, load3(a.nrm, p), load3(a.pos, p), cam, __ldg(a.rough + p), a.eps,
+                              __ldg(a.shift_spec + 2 * p + 0), __ldg(a.shift_spec + 2 * p + 1), a.N_spec, a.mode_spec,
+                              a.a_spec, shd0, shd1, a.N_diff, a.mode_diff, a.a_diff, gl, G, lo);
+    shade_reduce_store<TANGENT>(a, lo, p, live, gl, G);
+}
+
+template <bool TANGENT>
+__global__ void __launch_bounds__(128) k_shade_stream(SceneView s, ShadeArgs a, int refill) {
+    const int G = a.G;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int gl = lane & (G - 1);
+    int64_t p = warp * (32 / G) + lane / G;
+    const bool live = p < a.P;
+    if (!live) p = a.P - 1;
+    const V3 cam = v3(__ldg(a.cam + 0), __ldg(a.cam + 1), __ldg(a.cam + 2));
+    float shd0 = 0.f, shd1 = 0.f;
+    if (a.N_diff > 0) {
+        shd0 = __ldg(a.shift_diff + 2 * p + 0);
+        shd1 = __ldg(a.shift_diff + 2 * p + 1);
+    }
+    ShadeWork<TANGENT> w;
+    w.init(&s, load3(a.nrm, p), load3(a.pos, p), cam, __ldg(a.rough + p), a.eps, __ldg(a.shift_spec + 2 * p + 0),
+           __ldg(a.shift_spec + 2 * p + 1), a.N_spec, a.mode_spec, a.a_spec, shd0, shd1, a.N_diff, a.mode_diff, a.a_diff,
+           gl, G, live);
+    trace_stream_bvh2(s, w, refill);
+    shade_reduce_store<TANGENT>(a, w.out, p, live, gl, G);
 }
 
 // backward from the forward-mode stash: no rays
@@ -669,7 +826,7 @@ int64_t texir_launch_count(void) { return g_launches.load(); }
 int texir_scene_destroy(texir_scene* sc) {
     if (!sc) return 0;
     DeviceGuard guard(sc->info.device);
-    void* ptrs[] = {sc->d_nodes2, sc->d_tris2, sc->d_prim2, sc->d_nodes8, sc->d_tris8,
+    void* ptrs[] = {sc->d_nodes2, sc->d_tris2, sc->d_prim2, sc->d_qnodes2, sc->d_nodes8, sc->d_tris8,
                     sc->d_prim8,  sc->d_uvs,   sc->d_slot_of_prim, sc->d_tex};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -702,7 +859,8 @@ int texir_scene_create(const float* verts_host, int64_t nv, const int32_t* tris_
     std::vector<double> uvs;
     if (tri_uvs_host) uvs.assign(tri_uvs_host, tri_uvs_host + 6 * (size_t)nt);
     if ((rc = upload(bvh.nodes2, &sc->d_nodes2, &bytes)) || (rc = upload(bvh.tris2, &sc->d_tris2, &bytes)) ||
-        (rc = upload(bvh.prim2, &sc->d_prim2, &bytes)) || (rc = upload(bvh.nodes8, &sc->d_nodes8, &bytes)) ||
+        (rc = upload(bvh.prim2, &sc->d_prim2, &bytes)) || (rc = upload(bvh.qnodes2, &sc->d_qnodes2, &bytes)) ||
+        (rc = upload(bvh.nodes8, &sc->d_nodes8, &bytes)) ||
         (rc = upload(bvh.tris8, &sc->d_tris8, &bytes)) || (rc = upload(bvh.prim8, &sc->d_prim8, &bytes)) ||
         (rc = upload(slot_of_prim, &sc->d_slot_of_prim, &bytes)) || (rc = upload(uvs, &sc->d_uvs, &bytes))) {
         std::string keep = g_err;
@@ -714,6 +872,11 @@ int texir_scene_create(const float* verts_host, int64_t nv, const int32_t* tris_
     sc->view.nodes2 = (const float4*)sc->d_nodes2;
     sc->view.tris2 = (const float4*)sc->d_tris2;
     sc->view.prim2 = (const uint32_t*)sc->d_prim2;
+    sc->view.qnodes2 = (const uint4*)sc->d_qnodes2;
+    for (int a = 0; a < 3; ++a) {
+        sc->view.qmin[a] = bvh.qmin[a];
+        sc->view.qstep[a] = bvh.qstep[a];
+    }
     sc->view.nodes8 = (const uint4*)sc->d_nodes8;
     sc->view.tris8 = (const float4*)sc->d_tris8;
     sc->view.prim8 = (const uint32_t*)sc->d_prim8;
@@ -805,6 +968,8 @@ static int cast_impl(const texir_scene* sc, const float* rays, int64_t R, float*
     } else {
         if (stats)
             k_cast_rays<2, true><<<g, 128, 0, st>>>(sc->view, rays, R, t_hit, prim_id, prim_uv, nvis, ntri);
+        else if (stream_mode() >= 2 && use_qnodes())
+            k_cast_rays<4, false><<<g, 128, 0, st>>>(sc->view, rays, R, t_hit, prim_id, prim_uv, nullptr, nullptr);
         else
             k_cast_rays<2, false><<<g, 128, 0, st>>>(sc->view, rays, R, t_hit, prim_id, prim_uv, nullptr, nullptr);
     }
@@ -901,6 +1066,8 @@ int texir_query_irf(const texir_scene* sc, const float* org, const float* dir, i
     unsigned g = grid_for(P * N, 128);
     if (sc->info.bvh_kind == TEXIR_BVH8)
         k_query_irf<8><<<g, 128, 0, (cudaStream_t)stream>>>(sc->view, org, dir, P, N, rad);
+    else if (stream_mode() >= 2 && use_qnodes())
+        k_query_irf<4><<<g, 128, 0, (cudaStream_t)stream>>>(sc->view, org, dir, P, N, rad);
     else
         k_query_irf<2><<<g, 128, 0, (cudaStream_t)stream>>>(sc->view, org, dir, P, N, rad);
     return finish_launch("k_query_irf");
@@ -920,6 +1087,17 @@ int texir_irradiance_fwd(const texir_scene* sc, const float* pos, const float* n
     unsigned g = grid_for(warps * 32, 128);
     if (sc->info.bvh_kind == TEXIR_BVH8)
         k_irradiance<8><<<g, 128, 0, (cudaStream_t)stream>>>(sc->view, pos, nrm, shift, P, N, mode, G, ab, E);
+    else if (use_stream())
+        k_irradiance_stream<<<g, 128, 0, (cudaStream_t)stream>>>(sc->view, pos, nrm, shift, P, N, mode, G, ab,
+                                                                  refill_threshold(), E);
+    else if (stream_mode() == 3 && G == 32 && use_qnodes())
+        k_irradiance_lean<4><<<g, 128, 0, (cudaStream_t)stream>>>(sc->view, pos, nrm, shift, P, N, mode, ab, E);
+    else if (stream_mode() == 3 && G == 32)
+        k_irradiance_lean<3><<<g, 128, 0, (cudaStream_t)stream>>>(sc->view, pos, nrm, shift, P, N, mode, ab, E);
+    else if (stream_mode() >= 2 && use_qnodes())
+        k_irradiance<4><<<g, 128, 0, (cudaStream_t)stream>>>(sc->view, pos, nrm, shift, P, N, mode, G, ab, E);
+    else if (stream_mode() >= 2)
+        k_irradiance<3><<<g, 128, 0, (cudaStream_t)stream>>>(sc->view, pos, nrm, shift, P, N, mode, G, ab, E);
     else
         k_irradiance<2><<<g, 128, 0, (cudaStream_t)stream>>>(sc->view, pos, nrm, shift, P, N, mode, G, ab, E);
     return finish_launch("k_irradiance");
@@ -958,6 +1136,12 @@ static int launch_shade(const texir_scene* sc, const ShadeArgs& a, void* stream)
     unsigned g = grid_for(warps * 32, 128);
     if (sc->info.bvh_kind == TEXIR_BVH8)
         k_shade<8, TANGENT><<<g, 128, 0, (cudaStream_t)stream>>>(sc->view, a);
+    else if (use_stream())
+        k_shade_stream<TANGENT><<<g, 128, 0, (cudaStream_t)stream>>>(sc->view, a, refill_threshold());
+    else if (stream_mode() >= 2 && use_qnodes())
+        k_shade<4, TANGENT><<<g, 128, 0, (cudaStream_t)stream>>>(sc->view, a);
+    else if (stream_mode() >= 2)
+        k_shade<3, TANGENT><<<g, 128, 0, (cudaStream_t)stream>>>(sc->view, a);
     else
         k_shade<2, TANGENT><<<g, 128, 0, (cudaStream_t)stream>>>(sc->view, a);
     return finish_launch("k_shade");

@@ -1,0 +1,262 @@
+// texir_stream.h -- ray-stream BVH2 traversal: each lane pulls rays from a per-lane work source, walks
+// them through the BVH and hands the hit back, WITHOUT waiting for the other lanes of its warp between rays.
+//
+// The first kernels ran "generate -> trace -> shade" per sample in lock step, so every ray cost the warp
+// the length of its longest ray (measured on B200: 13.3 of 32 lanes active, ncu
+// smsp__thread_inst_executed_per_inst_executed).  Here the traversal loop is the outer loop; a lane whose ray
+// has terminated idles only until the number of still-traversing lanes falls below `refill`, then all idle
+// lanes consume their hits and fetch new rays together (dynamic fetch after Aila & Laine, HPG 2009).  Lanes
+// that restart together share the node fetches of the upper tree levels (same origin, neighbouring
+// directions), which keeps the L1 wavefront count per ray low.
+//
+// The per-node arithmetic is also cheaper than texir_bvh.h's first version: t = fma(plane, 1/d, -o/d), no
+// ulp widening (the builder's padding, 1e-5 of the scene diagonal + 4 ulp of the largest coordinate, already
+// covers every rounding in the slab test -- see DESIGN.md), all four node loads issued up front.
+//
+// Host + device: tests/cpu_emul runs the same code one lane at a time (the refill heuristic is a no-op there;
+// it changes the order in which lanes make progress, never a result).
+#pragma once
+#include "texir_bvh.h"
+
+namespace texir {
+
+struct RayState {
+    V3 o, d;     // origin, direction (the triangle test needs both)
+    V3 id, nood; // 1/d and -o/d for the slab test
+};
+
+TX_HD void ray_setup(RayState& r, V3 o, V3 d) {
+    r.o = o;
+    r.d = d;
+    r.id = safe_rcp_dir(d);
+    r.nood = v3(-(o.x * r.id.x), -(o.y * r.id.y), -(o.z * r.id.z));
+}
+
+#ifdef __CUDA_ARCH__
+// volatile asm pins the issue order: the child references are requested together with the boxes instead of
+// after the box test (the compiler sinks a plain load below the branch and serialises two round trips)
+TX_D float4 ld_nc_f4(const float4* p) {
+    float4 v;
+    asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+TX_D void ld_nc_i2(const float4* p, int* a, int* b) {
+    asm volatile("ld.global.nc.v2.s32 {%0,%1}, [%2];" : "=r"(*a), "=r"(*b) : "l"(p));
+}
+#define TX_ACTIVE_LANES() __popc(__activemask())
+#define TX_ANY(pred) __any_sync(0xFFFFFFFFu, (pred))
+#else
+inline float4 ld_nc_f4(const float4* p) { return *p; }
+inline void ld_nc_i2(const float4* p, int* a, int* b) {
+    *a = float_as_int_(p->x);
+    *b = float_as_int_(p->y);
+}
+#define TX_ACTIVE_LANES() 32
+#define TX_ANY(pred) (pred)
+#endif
+
+// one inner-node step: returns the next node (inner index, leaf reference < 0, or kSentinel)
+TX_HD int bvh2_step(const SceneView& s, const RayState& r, float tbest, int node, int* stack, int& sp) {
+    const float4* np = s.nodes2 + 4 * (size_t)node;
+    const float4 n0 = ld_nc_f4(np + 0), n1 = ld_nc_f4(np + 1), n2 = ld_nc_f4(np + 2);
+    int c0, c1;
+    ld_nc_i2(np + 3, &c0, &c1);
+    // child 0: x = n0.xy, y = n0.zw, z = n2.xy ; child 1: x = n1.xy, y = n1.zw, z = n2.zw
+    const float a0x = tx_fma(n0.x, r.id.x, r.nood.x), b0x = tx_fma(n0.y, r.id.x, r.nood.x);
+    const float a0y = tx_fma(n0.z, r.id.y, r.nood.y), b0y = tx_fma(n0.w, r.id.y, r.nood.y);
+    const float a0z = tx_fma(n2.x, r.id.z, r.nood.z), b0z = tx_fma(n2.y, r.id.z, r.nood.z);
+    const float a1x = tx_fma(n1.x, r.id.x, r.nood.x), b1x = tx_fma(n1.y, r.id.x, r.nood.x);
+    const float a1y = tx_fma(n1.z, r.id.y, r.nood.y), b1y = tx_fma(n1.w, r.id.y, r.nood.y);
+    const float a1z = tx_fma(n2.z, r.id.z, r.nood.z), b1z = tx_fma(n2.w, r.id.z, r.nood.z);
+    const float t0n = fmaxf(fmaxf(fminf(a0x, b0x), fminf(a0y, b0y)), fmaxf(fminf(a0z, b0z), 0.0f));
+    const float t0f = fminf(fminf(fmaxf(a0x, b0x), fmaxf(a0y, b0y)), fminf(fmaxf(a0z, b0z), tbest));
+    const float t1n = fmaxf(fmaxf(fminf(a1x, b1x), fminf(a1y, b1y)), fmaxf(fminf(a1z, b1z), 0.0f));
+    const float t1f = fminf(fminf(fmaxf(a1x, b1x), fmaxf(a1y, b1y)), fminf(fmaxf(a1z, b1z), tbest));
+    const bool h0 = t0n <= t0f, h1 = t1n <= t1f;
+    if (h0 && h1) {
+        const bool swap = t1n < t0n;
+        stack[sp++] = swap ? c0 : c1;
+        return swap ? c1 : c0;
+    }
+    if (h0) return c0;
+    if (h1) return c1;
+    return stack[--sp];
+}
+
+TX_HD void bvh2_leaf(const SceneView& s, const RayState& r, int node, Hit& hit) {
+    const int ref = ~node;
+    const int first = ref >> 3, cnt = (ref & 7) + 1;
+    for (int i = 0; i < cnt; ++i) test_slot(s.tris2, s.prim2, first + i, r.o, r.d, hit);
+}
+
+TX_HD void hit_reset(Hit& hit) {
+    hit.t = INFINITY;
+    hit.u = 0.f;
+    hit.v = 0.f;
+    hit.prim = kInvalidId;
+}
+
+// plain closest hit with the cheaper node step (one ray, run to completion)
+TX_HD Hit trace_bvh2_fast(const SceneView& s, V3 o, V3 d) {
+    RayState r;
+    ray_setup(r, o, d);
+    Hit hit;
+    hit_reset(hit);
+    int stack[kStackSize];
+    int sp = 0;
+    stack[sp++] = kSentinel;
+    int node = 0;
+    while (node != kSentinel) {
+        while (node >= 0 && node != kSentinel) node = bvh2_step(s, r, hit.t, node, stack, sp);
+        if (node < 0) {
+            bvh2_leaf(s, r, node, hit);
+            node = stack[--sp];
+        }
+    }
+    return hit;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// QBVH2: 32-byte nodes on a global 16-bit grid (layout in texir_bvh.h, encoder in bvh_build.cpp).
+// A plane index q becomes the float 2^23 + q with ONE byte permute (0x4B00'qqqq), and the ray parameter of
+// the plane is one FMA:  t = (2^23 + q) * S + O,  S = step/d,  O = (gmin - o)/d - 2^23 * S.  The permute
+// selector also picks the NEAR or the FAR plane of the slab from the sign of d, so no per-axis min/max is left:
+// per child 6 permutes + 6 FMAs + 2 three-input min/max.
+// ---------------------------------------------------------------------------------------------------
+struct RayQ {
+    V3 o, d;   // for the triangle test
+    V3 S, O;   // slab decode
+    uint32_t selx, sely, selz;  // permute selectors of the near plane; far = sel ^ 0x0022
+};
+
+TX_HD uint32_t byte_perm_(uint32_t x, uint32_t y, uint32_t sel) {
+#ifdef __CUDA_ARCH__
+    return __byte_perm(x, y, sel);
+#else
+    uint64_t both = ((uint64_t)y << 32) | x;
+    uint32_t r = 0;
+    for (int k = 0; k < 4; ++k) r |= (uint32_t)((both >> (8 * ((sel >> (4 * k)) & 7))) & 0xFF) << (8 * k);
+    return r;
+#endif
+}
+
+TX_HD void rayq_setup(const SceneView& s, RayQ& r, V3 o, V3 d) {
+    r.o = o;
+    r.d = d;
+    const V3 id = safe_rcp_dir(d);
+    r.S = v3(s.qstep[0] * id.x, s.qstep[1] * id.y, s.qstep[2] * id.z);
+    r.O = v3((s.qmin[0] - o.x) * id.x - 8388608.0f * r.S.x, (s.qmin[1] - o.y) * id.y - 8388608.0f * r.S.y,
+             (s.qmin[2] - o.z) * id.z - 8388608.0f * r.S.z);
+    // low half (0x7610) = lo plane is the near plane when the ray travels in +axis
+    r.selx = id.x >= 0.f ? 0x7610u : 0x7632u;
+    r.sely = id.y >= 0.f ? 0x7610u : 0x7632u;
+    r.selz = id.z >= 0.f ? 0x7610u : 0x7632u;
+}
+
+#ifdef __CUDA_ARCH__
+TX_D uint4 ld_nc_u4(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+#else
+inline uint4 ld_nc_u4(const uint4* p) { return *p; }
+#endif
+
+TX_HD float qplane_(uint32_t w, uint32_t sel, float S, float O) {
+    return tx_fma(int_as_float_((int)byte_perm_(w, 0x4B000000u, sel)), S, O);
+}
+
+TX_HD int qbvh2_step(const SceneView& s, const RayQ& r, float tbest, int node, int* stack, int& sp) {
+    const uint4* np = s.qnodes2 + 2 * (size_t)node;
+    const uint4 q0 = ld_nc_u4(np + 0), q1 = ld_nc_u4(np + 1);
+    const uint32_t fx = r.selx ^ 0x0022u, fy = r.sely ^ 0x0022u, fz = r.selz ^ 0x0022u;
+    const float t0n = fmaxf(fmaxf(qplane_(q0.x, r.selx, r.S.x, r.O.x), qplane_(q0.y, r.sely, r.S.y, r.O.y)),
+                            fmaxf(qplane_(q0.z, r.selz, r.S.z, r.O.z), 0.0f));
+    const float t0f = fminf(fminf(qplane_(q0.x, fx, r.S.x, r.O.x), qplane_(q0.y, fy, r.S.y, r.O.y)),
+                            fminf(qplane_(q0.z, fz, r.S.z, r.O.z), tbest));
+    const float t1n = fmaxf(fmaxf(qplane_(q0.w, r.selx, r.S.x, r.O.x), qplane_(q1.x, r.sely, r.S.y, r.O.y)),
+                            fmaxf(qplane_(q1.y, r.selz, r.S.z, r.O.z), 0.0f));
+    const float t1f = fminf(fminf(qplane_(q0.w, fx, r.S.x, r.O.x), qplane_(q1.x, fy, r.S.y, r.O.y)),
+                            fminf(qplane_(q1.y, fz, r.S.z, r.O.z), tbest));
+    const int c0 = (int)q1.z, c1 = (int)q1.w;
+    const bool h0 = t0n <= t0f, h1 = t1n <= t1f;
+    if (h0 && h1) {
+        const bool swap = t1n < t0n;
+        stack[sp++] = swap ? c0 : c1;
+        return swap ? c1 : c0;
+    }
+    if (h0) return c0;
+    if (h1) return c1;
+    return stack[--sp];
+}
+
+TX_HD Hit trace_qbvh2(const SceneView& s, V3 o, V3 d) {
+    RayQ r;
+    rayq_setup(s, r, o, d);
+    Hit hit;
+    hit_reset(hit);
+    int stack[kStackSize];
+    int sp = 0;
+    stack[sp++] = kSentinel;
+    int node = 0;
+    while (node != kSentinel) {
+        while (node >= 0 && node != kSentinel) node = qbvh2_step(s, r, hit.t, node, stack, sp);
+        if (node < 0) {
+            const int ref = ~node;
+            const int first = ref >> 3, cnt = (ref & 7) + 1;
+            for (int i = 0; i < cnt; ++i) test_slot(s.tris2, s.prim2, first + i, r.o, r.d, hit);
+            node = stack[--sp];
+        }
+    }
+    return hit;
+}
+
+// Work concept:
+//   bool next(V3* o, V3* d)     produce this lane's next ray; false when the lane has no more rays
+//   void done(const Hit& h, V3 d) consume the finished ray (d = its direction)
+// `refill`: leave the traversal loop to refill idle lanes once fewer than `refill` lanes are still traversing
+// (32 = wait for nobody ... 1 = classic lock step).
+template <class Work>
+TX_HD void trace_stream_bvh2(const SceneView& s, Work& w, int refill) {
+    int stack[kStackSize];
+    RayState r;
+    Hit hit;
+    hit_reset(hit);
+    r.o = r.d = r.id = r.nood = v3(0.f, 0.f, 0.f);
+    int sp = 0;
+    int node = kSentinel;
+    bool live = false;  // this lane owns a ray in flight
+    bool more = true;   // this lane's source may have more rays
+    for (;;) {
+        if (node == kSentinel) {  // idle lane: hand back the finished ray, fetch the next one
+            if (live) {
+                w.done(hit, r.d);
+                live = false;
+            }
+            if (more) {
+                V3 o, d;
+                more = w.next(&o, &d);
+                if (more) {
+                    ray_setup(r, o, d);
+                    hit_reset(hit);
+                    sp = 0;
+                    stack[sp++] = kSentinel;
+                    node = 0;
+                    live = true;
+                }
+            }
+        }
+        if (!TX_ANY(live)) break;
+        while (node != kSentinel) {
+            while (node >= 0 && node != kSentinel) node = bvh2_step(s, r, hit.t, node, stack, sp);
+            if (node < 0) {
+                bvh2_leaf(s, r, node, hit);
+                node = stack[--sp];
+            }
+            if (TX_ACTIVE_LANES() < refill) break;
+        }
+    }
+}
+
+}  // namespace texir
