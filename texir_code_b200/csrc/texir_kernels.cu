@@ -449,8 +449,11 @@ __device__ __forceinline__ void shade_reduce_store(const ShadeArgs& a, const Sha
     if (live && gl == 0) shade_epilogue<TANGENT>(a, p, sx, sy, sz, dx, dy, dz, dsum);
 }
 
+#ifndef TX_SHADE_MINB
+#define TX_SHADE_MINB 5
+#endif
 template <int KIND, bool TANGENT>
-__global__ void __launch_bounds__(128) k_shade(SceneView s, ShadeArgs a) {
+__global__ void __launch_bounds__(128, TX_SHADE_MINB) k_shade(SceneView s, ShadeArgs a) {
     const int G = a.G;
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -469,6 +472,116 @@ __global__ void __launch_bounds__(128) k_shade(SceneView s, ShadeArgs a) {
                               __ldg(a.shift_spec + 2 * p + 0), __ldg(a.shift_spec + 2 * p + 1), a.N_spec, a.mode_spec,
                               a.a_spec, shd0, shd1, a.N_diff, a.mode_diff, a.a_diff, gl, G, lo);
     shade_reduce_store<TANGENT>(a, lo, p, live, gl, G);
+}
+
+// Occupancy-tuned render kernel for G == 32 (same idea as k_irradiance_lean): the per-point constants (frame,
+// view, Smith/Fresnel terms, shifts) sit in shared memory and are read back while a sample is generated; the
+// nine per-lane sums sit in shared memory as well.  Bit-identical to k_shade (same sample and summation order).
+struct ShadePointSmem {
+    Frame f;
+    SpecPoint sp;
+    float rough, shs0, shs1, shd0, shd1;
+};
+#ifndef TX_SHADE_LEAN_MINB
+#define TX_SHADE_LEAN_MINB 10
+#endif
+template <int KIND, bool TANGENT>
+__global__ void __launch_bounds__(128, TX_SHADE_LEAN_MINB) k_shade_lean(SceneView s, ShadeArgs a) {
+    __shared__ ShadePointSmem sm_pt[4];
+    __shared__ float sm_acc[TANGENT ? 9 : 6][128];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, tid = threadIdx.x;
+    int64_t p = (int64_t)blockIdx.x * 4 + wid;
+    const bool live = p < a.P;
+    if (!live) p = a.P - 1;
+    const V3 o = load3(a.pos, p);
+    if (lane == 0) {
+        ShadePointSmem& q = sm_pt[wid];
+        const V3 n = load3(a.nrm, p);
+        const V3 cam = v3(__ldg(a.cam + 0), __ldg(a.cam + 1), __ldg(a.cam + 2));
+        const V3 view = view_dir(cam, o);
+        q.rough = __ldg(a.rough + p);
+        q.f = make_frame(n);
+        q.sp = spec_point(n, view, q.rough, a.eps);
+        q.shs0 = __ldg(a.shift_spec + 2 * p + 0);
+        q.shs1 = __ldg(a.shift_spec + 2 * p + 1);
+        q.shd0 = a.N_diff > 0 ? __ldg(a.shift_diff + 2 * p + 0) : 0.f;
+        q.shd1 = a.N_diff > 0 ? __ldg(a.shift_diff + 2 * p + 1) : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < (TANGENT ? 9 : 6); ++k) sm_acc[k][tid] = 0.f;
+    __syncwarp();
+    const volatile ShadePointSmem* q = &sm_pt[wid];
+    auto load_frame = [&]() {
+        Frame f;
+        f.n = v3(q->f.n.x, q->f.n.y, q->f.n.z);
+        f.u = v3(q->f.u.x, q->f.u.y, q->f.u.z);
+        f.v = v3(q->f.v.x, q->f.v.y, q->f.v.z);
+        return f;
+    };
+    {  // specular samples
+        const int ab = a.a_spec, N = a.N_spec, M = (N + (1 << ab) - 1) >> ab;
+        for (int c = 0; c < (1 << ab); ++c)
+            for (int j = lane; j < M; j += 32) {
+                const uint32_t i = ((uint32_t)j << ab) + (uint32_t)c;
+                if (i >= (uint32_t)N) continue;
+                V3 l;
+                float w, dw = 0.f;
+                {
+                    const Frame f = load_frame();
+                    SpecPoint sp;
+                    sp.n = v3(q->sp.n.x, q->sp.n.y, q->sp.n.z);
+                    sp.v = v3(q->sp.v.x, q->sp.v.y, q->sp.v.z);
+                    sp.ndv = q->sp.ndv; sp.k = q->sp.k; sp.dk = q->sp.dk; sp.g1v = q->sp.g1v; sp.dg1v = q->sp.dg1v;
+                    sp.eps = q->sp.eps;
+                    float s0 = shift_wrap_clamp(hammersley0(i, (uint32_t)N), q->shs0);
+                    float s1 = shift_wrap_clamp(radical_inverse(i), q->shs1);
+                    DirSample ds = sample_dir<TANGENT>(f, a.mode_spec, s0, s1, q->rough);
+                    float vdh_raw;
+                    l = reflect_dir(ds.d, sp.v, &vdh_raw);
+                    w = spec_weight<TANGENT>(sp, f, ds, l, vdh_raw, &dw);
+                }
+                Hit h = trace<KIND>(s, o, l);
+                V3 L = fetch_radiance(s, h);
+                sm_acc[0][tid] += L.x * w;
+                sm_acc[1][tid] += L.y * w;
+                sm_acc[2][tid] += L.z * w;
+                if (TANGENT) {
+                    sm_acc[6][tid] += L.x * dw;
+                    sm_acc[7][tid] += L.y * dw;
+                    sm_acc[8][tid] += L.z * dw;
+                }
+            }
+    }
+    if (a.N_diff > 0) {  // Monte-Carlo diffuse (relighting)
+        const int ab = a.a_diff, N = a.N_diff, M = (N + (1 << ab) - 1) >> ab;
+        for (int c = 0; c < (1 << ab); ++c)
+            for (int j = lane; j < M; j += 32) {
+                const uint32_t i = ((uint32_t)j << ab) + (uint32_t)c;
+                if (i >= (uint32_t)N) continue;
+                V3 d;
+                float wgt;
+                {
+                    const Frame f = load_frame();
+                    float s0 = shift_wrap_clamp(hammersley0(i, (uint32_t)N), q->shd0);
+                    float s1 = shift_wrap_clamp(radical_inverse(i), q->shd1);
+                    d = sample_dir<false>(f, a.mode_diff, s0, s1, 0.f).d;
+                    wgt = (a.mode_diff == MODE_COSINE) ? 1.0f
+                                                       : clamp01(rn_dot(v3(q->sp.n.x, q->sp.n.y, q->sp.n.z), d));
+                }
+                Hit h = trace<KIND>(s, o, d);
+                V3 L = fetch_radiance(s, h);
+                sm_acc[3][tid] += L.x * wgt;
+                sm_acc[4][tid] += L.y * wgt;
+                sm_acc[5][tid] += L.z * wgt;
+            }
+    }
+    ShadeLaneOut lo;
+    for (int k = 0; k < 3; ++k) {
+        lo.spec[k] = sm_acc[k][tid];
+        lo.diff[k] = sm_acc[3 + k][tid];
+        lo.dspec[k] = TANGENT ? sm_acc[TANGENT ? 6 + k : 0][tid] : 0.f;
+    }
+    shade_reduce_store<TANGENT>(a, lo, p, live, lane, 32);
 }
 
 template <bool TANGENT>
@@ -1138,6 +1251,8 @@ static int launch_shade(const texir_scene* sc, const ShadeArgs& a, void* stream)
         k_shade<8, TANGENT><<<g, 128, 0, (cudaStream_t)stream>>>(sc->view, a);
     else if (use_stream())
         k_shade_stream<TANGENT><<<g, 128, 0, (cudaStream_t)stream>>>(sc->view, a, refill_threshold());
+    else if (stream_mode() == 3 && a.G == 32 && use_qnodes())
+        k_shade_lean<4, TANGENT><<<g, 128, 0, (cudaStream_t)stream>>>(sc->view, a);
     else if (stream_mode() >= 2 && use_qnodes())
         k_shade<4, TANGENT><<<g, 128, 0, (cudaStream_t)stream>>>(sc->view, a);
     else if (stream_mode() >= 2)
