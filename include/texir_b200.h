@@ -104,9 +104,15 @@ TEXIR_API int texir_query_irf(const texir_scene* scene, const float* org, const 
                               float* rad, void* stream);
 
 /* ---- fused IrT batch: models/tracer_o3d_irt.py:165-173 for P points at once.
- * E[p] = sum_i L_i * clamp(n.l_i, 0, 1) * 2*pi / N  with l_i = generate_dir(nrm, N, mode). */
+ * E[p] = sum_i L_i * clamp(n.l_i, 0, 1) * 2*pi / N  with l_i = generate_dir(nrm, N, mode).
+ * order (nullable): a permutation of [0,P) from texir_point_order; warp w then works on point order[w].  The
+ * result is independent of it (every point is computed by one warp from its own inputs); it only makes
+ * neighbouring warps walk neighbouring parts of the BVH (measured +7 % on scattered points). */
 TEXIR_API int texir_irradiance_fwd(const texir_scene* scene, const float* pos, const float* nrm,
-                                   const float* shift, int64_t P, int N, int mode, float* E, void* stream);
+                                   const float* shift, const int32_t* order, int64_t P, int N, int mode, float* E,
+                                   void* stream);
+/* order [P] (int32, device): the points sorted along a 30-bit Morton curve over the scene box */
+TEXIR_API int texir_point_order(const texir_scene* scene, const float* pos, int64_t P, int32_t* order, void* stream);
 
 /* ---- fused render: MaterialModel.render, models/mat_nvdiffrast.py:201-249 (and the relighting
  *      variant models/test_nvdiffrast.py:256-303 when N_diff > 0).

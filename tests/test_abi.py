@@ -57,7 +57,8 @@ def test_argument_validation_without_gpu(lib):
     assert lib.texir_generate_dir(z, z, z, -1, 16, 0, z, z) != 0      # negative P
     assert lib.texir_query_irf(z, z, z, 1, 1, z, z) != 0              # NULL scene
     assert b"NULL scene" in lib.texir_last_error()
-    assert lib.texir_irradiance_fwd(z, z, z, z, 1, 1, 0, z, z) != 0
+    assert lib.texir_irradiance_fwd(z, z, z, z, z, 1, 1, 0, z, z) != 0
+    assert lib.texir_point_order(z, z, 4, z, z) != 0
     assert lib.texir_scene_set_bvh(z, 8) != 0
     h = ctypes.c_void_p()
     assert lib.texir_scene_create(z, 0, z, 0, z, 0, 1, ctypes.byref(h)) != 0   # empty mesh, fails before CUDA

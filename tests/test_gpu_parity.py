@@ -348,6 +348,26 @@ def test_irradiance_edge_cases(tx, gscene, cuda_device):
         tx.irradiance(sc, pos[:4], nrm[:4], sh[:4], 8, "importance")
 
 
+def test_point_order_is_a_morton_permutation_and_changes_no_value(tx, big, cuda_device):
+    from texir_code_b200 import ops, synth
+    sc, tex, scene = big
+    P = 20000
+    pos, nrm = synth.sample_surface_points(sc, P, seed=12)
+    posd, nrmd = T(pos, cuda_device), T(nrm, cuda_device)
+    order = ops.point_order(scene, posd).cpu().numpy()
+    assert order.dtype == np.int32 and np.array_equal(np.sort(order), np.arange(P))
+    # consecutive points of the order are spatial neighbours: mean step far below the random-order step
+    live = ~np.all(nrm == 0, axis=1)
+    step_sorted = np.linalg.norm(np.diff(pos[order][live[order]], axis=0), axis=1).mean()
+    step_random = np.linalg.norm(np.diff(pos[live], axis=0), axis=1).mean()
+    assert step_sorted < 0.1 * step_random
+    torch.manual_seed(3)
+    sh = torch.rand(P, 1, 2).to(cuda_device)
+    a = tx.irradiance(scene, posd, nrmd, sh, 64, coherent=True)
+    b = tx.irradiance(scene, posd, nrmd, sh, 64, coherent=False)
+    assert torch.equal(a, b)
+
+
 # ---------------------------------------------------------------------------------------------------
 # material texture fetch / scatter
 # ---------------------------------------------------------------------------------------------------

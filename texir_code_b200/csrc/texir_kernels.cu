@@ -5,6 +5,7 @@
 // coherent 32-sample patches per warp iteration, see coherent_bits) and the per-point Monte-Carlo
 // sum is a warp-shuffle reduction.  No [P,N,.] tensor ever exists in the fused kernels.
 #include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
 
 #include <atomic>
 #include <cstdio>
@@ -39,6 +40,7 @@ struct texir_scene {
     void* d_slot_of_prim = nullptr;  // original primitive id -> BVH2 slot
     void* d_tex = nullptr;
     int64_t geom_bytes = 0, tex_bytes = 0;
+    float lo[3] = {0, 0, 0}, hi[3] = {1, 1, 1};  // scene box
 };
 
 #define TX_FAIL(msg)                 \
@@ -243,14 +245,15 @@ __global__ void __launch_bounds__(128) k_query_irf(SceneView s, const float* __r
 template <int KIND>
 __global__ void __launch_bounds__(128, TX_IRR_MINB) k_irradiance(SceneView s, const float* __restrict__ pos,
                                                     const float* __restrict__ nrm, const float* __restrict__ shift,
-                                                    int64_t P, int N, int mode, int G, int abits,
-                                                    float* __restrict__ E) {
+                                                    const int32_t* __restrict__ order, int64_t P, int N, int mode,
+                                                    int G, int abits, float* __restrict__ E) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int gl = lane & (G - 1);
     int64_t p = warp * (32 / G) + lane / G;
     const bool live = p < P;
     if (!live) p = P - 1;
+    if (order) p = __ldg(order + p);
     float acc[3];
     irradiance_lane<KIND>(s, load3(nrm, p), load3(pos, p), __ldg(shift + 2 * p + 0), __ldg(shift + 2 * p + 1), N, mode,
                           gl, G, abits, acc);
@@ -278,14 +281,16 @@ struct IrtPointSmem {
 template <int KIND>
 __global__ void __launch_bounds__(128, TX_LEAN_MINB) k_irradiance_lean(SceneView s, const float* __restrict__ pos,
                                                              const float* __restrict__ nrm,
-                                                             const float* __restrict__ shift, int64_t P, int N, int mode,
-                                                             int abits, float* __restrict__ E) {
+                                                             const float* __restrict__ shift,
+                                                             const int32_t* __restrict__ order, int64_t P, int N,
+                                                             int mode, int abits, float* __restrict__ E) {
     __shared__ IrtPointSmem sm_pt[4];
     __shared__ float sm_acc[3][128];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     int64_t p = (int64_t)blockIdx.x * 4 + wid;
     const bool live = p < P;
     if (!live) p = P - 1;
+    if (order) p = __ldg(order + p);
     if (lane == 0) {
         V3 n = load3(nrm, p);
         Frame f = make_frame(n);
@@ -338,7 +343,8 @@ __global__ void __launch_bounds__(128, TX_LEAN_MINB) k_irradiance_lean(SceneView
 // ray-stream variant (texir_stream.h): same sums, lanes do not wait for each other between rays
 __global__ void __launch_bounds__(128) k_irradiance_stream(SceneView s, const float* __restrict__ pos,
                                                            const float* __restrict__ nrm,
-                                                           const float* __restrict__ shift, int64_t P, int N, int mode,
+                                                           const float* __restrict__ shift,
+                                                           const int32_t* __restrict__ order, int64_t P, int N, int mode,
                                                            int G, int abits, int refill, float* __restrict__ E) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -346,6 +352,7 @@ __global__ void __launch_bounds__(128) k_irradiance_stream(SceneView s, const fl
     int64_t p = warp * (32 / G) + lane / G;
     const bool live = p < P;
     if (!live) p = P - 1;
+    if (order) p = __ldg(order + p);
     IrtWork w;
     w.init(&s, load3(nrm, p), load3(pos, p), __ldg(shift + 2 * p + 0), __ldg(shift + 2 * p + 1), N, mode, gl, G, abits,
            live);
@@ -982,6 +989,10 @@ int texir_scene_create(const float* verts_host, int64_t nv, const int32_t* tris_
         return rc;
     }
     sc->geom_bytes = bytes;
+    for (int a = 0; a < 3; ++a) {
+        sc->lo[a] = bvh.scene_lo[a];
+        sc->hi[a] = bvh.scene_hi[a];
+    }
     sc->view.nodes2 = (const float4*)sc->d_nodes2;
     sc->view.tris2 = (const float4*)sc->d_tris2;
     sc->view.prim2 = (const uint32_t*)sc->d_prim2;
@@ -1186,8 +1197,68 @@ int texir_query_irf(const texir_scene* sc, const float* org, const float* dir, i
     return finish_launch("k_query_irf");
 }
 
-int texir_irradiance_fwd(const texir_scene* sc, const float* pos, const float* nrm, const float* shift, int64_t P,
-                         int N, int mode, float* E, void* stream) {
+// 30-bit Morton key of a point in the scene box
+__global__ void __launch_bounds__(256) k_morton_keys(const float* __restrict__ pos, int64_t P, float lx, float ly, float lz,
+                                                     float sx, float sy, float sz, uint32_t* __restrict__ keys,
+                                                     int32_t* __restrict__ idx) {
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    auto spread = [](uint32_t v) {
+        v = (v | (v << 16)) & 0x030000FFu;
+        v = (v | (v << 8)) & 0x0300F00Fu;
+        v = (v | (v << 4)) & 0x030C30C3u;
+        v = (v | (v << 2)) & 0x09249249u;
+        return v;
+    };
+    auto cell = [](float x, float lo, float sc) {
+        float q = (x - lo) * sc;
+        return (uint32_t)fminf(fmaxf(q, 0.f), 1023.f);  // NaN -> 0
+    };
+    keys[p] = spread(cell(__ldg(pos + 3 * p + 0), lx, sx)) | (spread(cell(__ldg(pos + 3 * p + 1), ly, sy)) << 1) |
+              (spread(cell(__ldg(pos + 3 * p + 2), lz, sz)) << 2);
+    idx[p] = (int32_t)p;
+}
+
+int texir_point_order(const texir_scene* sc, const float* pos, int64_t P, int32_t* order, void* stream) {
+    if (!sc) TX_FAIL("texir_point_order: NULL scene");
+    if (P < 0 || P >= (1ll << 31)) TX_FAIL("texir_point_order: P out of range");
+    if (P == 0) return 0;
+    if (!pos || !order) TX_FAIL("texir_point_order: NULL argument");
+    DeviceGuard guard(sc->info.device);
+    cudaStream_t st = (cudaStream_t)stream;
+    size_t tmp_bytes = 0;
+    uint32_t* keys = nullptr;
+    TX_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys, order, order, (int)P, 0, 30, st));
+    const size_t key_bytes = ((size_t)P * 4 + 255) & ~(size_t)255;
+    char* ws = nullptr;
+    TX_CUDA(cudaMallocAsync((void**)&ws, 3 * key_bytes + tmp_bytes, st));
+    uint32_t* k_in = (uint32_t*)ws;
+    uint32_t* k_out = (uint32_t*)(ws + key_bytes);
+    int32_t* v_in = (int32_t*)(ws + 2 * key_bytes);
+    float sc3[3];
+    for (int a = 0; a < 3; ++a) {
+        float ext = sc->hi[a] - sc->lo[a];
+        sc3[a] = ext > 0.f ? 1023.999f / ext : 0.f;
+    }
+    k_morton_keys<<<grid_for(P, 256), 256, 0, st>>>(pos, P, sc->lo[0], sc->lo[1], sc->lo[2], sc3[0], sc3[1], sc3[2], k_in,
+                                                    v_in);
+    int rc = finish_launch("k_morton_keys");
+    if (!rc) {
+        cudaError_t e = cub::DeviceRadixSort::SortPairs(ws + 3 * key_bytes, tmp_bytes, k_in, k_out, v_in, order, (int)P, 0,
+                                                        30, st);
+        if (e != cudaSuccess) {
+            g_err = std::string("texir_point_order: sort: ") + cudaGetErrorString(e);
+            rc = 2;
+        } else {
+            g_launches.fetch_add(1);
+        }
+    }
+    cudaFreeAsync(ws, st);
+    return rc;
+}
+
+int texir_irradiance_fwd(const texir_scene* sc, const float* pos, const float* nrm, const float* shift,
+                         const int32_t* order, int64_t P, int N, int mode, float* E, void* stream) {
     if (check_scene_tex("texir_irradiance_fwd", sc) || check_pn("texir_irradiance_fwd", P, N) ||
         check_mode("texir_irradiance_fwd", mode))
         return 1;
@@ -1199,20 +1270,20 @@ int texir_irradiance_fwd(const texir_scene* sc, const float* pos, const float* n
     const int64_t warps = (P + (32 / G) - 1) / (32 / G);
     unsigned g = grid_for(warps * 32, 128);
     if (sc->info.bvh_kind == TEXIR_BVH8)
-        k_irradiance<8><<<g, 128, 0, (cudaStream_t)stream>>>(sc->view, pos, nrm, shift, P, N, mode, G, ab, E);
+        k_irradiance<8><<<g, 128, 0, (cudaStream_t)stream>>>(sc->view, pos, nrm, shift, order, P, N, mode, G, ab, E);
     else if (use_stream())
-        k_irradiance_stream<<<g, 128, 0, (cudaStream_t)stream>>>(sc->view, pos, nrm, shift, P, N, mode, G, ab,
+        k_irradiance_stream<<<g, 128, 0, (cudaStream_t)stream>>>(sc->view, pos, nrm, shift, order, P, N, mode, G, ab,
                                                                   refill_threshold(), E);
     else if (stream_mode() == 3 && G == 32 && use_qnodes())
-        k_irradiance_lean<4><<<g, 128, 0, (cudaStream_t)stream>>>(sc->view, pos, nrm, shift, P, N, mode, ab, E);
+        k_irradiance_lean<4><<<g, 128, 0, (cudaStream_t)stream>>>(sc->view, pos, nrm, shift, order, P, N, mode, ab, E);
     else if (stream_mode() == 3 && G == 32)
-        k_irradiance_lean<3><<<g, 128, 0, (cudaStream_t)stream>>>(sc->view, pos, nrm, shift, P, N, mode, ab, E);
+        k_irradiance_lean<3><<<g, 128, 0, (cudaStream_t)stream>>>(sc->view, pos, nrm, shift, order, P, N, mode, ab, E);
     else if (stream_mode() >= 2 && use_qnodes())
-        k_irradiance<4><<<g, 128, 0, (cudaStream_t)stream>>>(sc->view, pos, nrm, shift, P, N, mode, G, ab, E);
+        k_irradiance<4><<<g, 128, 0, (cudaStream_t)stream>>>(sc->view, pos, nrm, shift, order, P, N, mode, G, ab, E);
     else if (stream_mode() >= 2)
-        k_irradiance<3><<<g, 128, 0, (cudaStream_t)stream>>>(sc->view, pos, nrm, shift, P, N, mode, G, ab, E);
+        k_irradiance<3><<<g, 128, 0, (cudaStream_t)stream>>>(sc->view, pos, nrm, shift, order, P, N, mode, G, ab, E);
     else
-        k_irradiance<2><<<g, 128, 0, (cudaStream_t)stream>>>(sc->view, pos, nrm, shift, P, N, mode, G, ab, E);
+        k_irradiance<2><<<g, 128, 0, (cudaStream_t)stream>>>(sc->view, pos, nrm, shift, order, P, N, mode, G, ab, E);
     return finish_launch("k_irradiance");
 }
 

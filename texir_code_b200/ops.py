@@ -245,19 +245,35 @@ def shade(scene: Scene, normal, albedo, roughness, points, cam_position, irr, sh
 # --------------------------------------------------------------------------------------------------
 # fused IrT batch
 # --------------------------------------------------------------------------------------------------
+def point_order(scene: Scene, position: torch.Tensor) -> torch.Tensor:
+    """int32 [P] permutation that sorts the points along a Morton curve over the scene box"""
+    _need_cuda("point_order", position)
+    dev = position.device
+    P = int(position.shape[0])
+    pos = _f32c(position)
+    order = torch.empty(P, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().texir_point_order(scene.handle, _ptr(pos), P, _ptr(order), _stream_ptr(dev)),
+                   "texir_point_order")
+    return order
+
+
 def irradiance(scene: Scene, position: torch.Tensor, normal: torch.Tensor, shift: torch.Tensor, num_samples: int,
-               mode: str = "uniform", out: Optional[torch.Tensor] = None) -> torch.Tensor:
+               mode: str = "uniform", out: Optional[torch.Tensor] = None, coherent: bool = True) -> torch.Tensor:
     """E[p] = sum_i L_i clamp(n.l_i,0,1) 2 pi / N for P points in one launch (tracer_o3d_irt.py:168-171);
-    position, normal [P,3], shift [P,1,2] or [P,2] -> [P,3]."""
+    position, normal [P,3], shift [P,1,2] or [P,2] -> [P,3].  coherent=True lets warps take the points in Morton
+    order (texir_point_order); the values do not depend on it."""
     _need_cuda("irradiance", position)
     dev = position.device
     P = int(position.shape[0])
     pos, nrm = _f32c(position), _f32c(normal)
     sh = _f32c(shift, dev).reshape(P, 2)
     E = out if out is not None else torch.empty(P, 3, dtype=torch.float32, device=dev)
+    order = point_order(scene, pos) if (coherent and P > 4096) else None
     with torch.cuda.device(dev):
-        _lib.check(_lib.load().texir_irradiance_fwd(scene.handle, _ptr(pos), _ptr(nrm), _ptr(sh), P, int(num_samples),
-                                                    _lib.MODES[mode], _ptr(E), _stream_ptr(dev)), "texir_irradiance_fwd")
+        _lib.check(_lib.load().texir_irradiance_fwd(scene.handle, _ptr(pos), _ptr(nrm), _ptr(sh), _ptr(order), P,
+                                                    int(num_samples), _lib.MODES[mode], _ptr(E), _stream_ptr(dev)),
+                   "texir_irradiance_fwd")
     return E
 
 
