@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "texir_code_b200", "csrc")
 SO = os.path.join(HERE, "libtexir_emul.so")
 SOURCES = [os.path.join(HERE, "emul.cpp"), os.path.join(CSRC, "bvh_build.cpp")]
-DEPS = SOURCES + [os.path.join(CSRC, h) for h in ("texir_math.h", "texir_bvh.h", "texir_stream.h", "texir_point.h",
+DEPS = SOURCES + [os.path.join(CSRC, h) for h in ("texir_math.h", "texir_bvh.h", "texir_walk.h", "texir_point.h",
                                                    "bvh_build.h")]
 
 
@@ -36,8 +36,6 @@ def load():
     lib.emul_query_irf.argtypes = [vp, i32, vp, vp, i64, i32, vp]
     lib.emul_irradiance.argtypes = [vp, i32, vp, vp, vp, i64, i32, i32, vp]
     lib.emul_shade.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, f32, vp, vp, vp]
-    lib.emul_irradiance_stream.argtypes = [vp, vp, vp, vp, i64, i32, i32, vp]
-    lib.emul_shade_stream.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, f32, vp, vp, vp]
     lib.emul_cast_rays_fast.argtypes = [vp, i32, vp, i64, vp, vp, vp]
     return lib
 

@@ -136,61 +136,7 @@ void emul_irradiance(EmulScene* s, int kind, const float* pos, const float* nrm,
     }
 }
 
-// ray-stream variants (texir_stream.h work sources), one lane at a time
-void emul_irradiance_stream(EmulScene* s, const float* pos, const float* nrm, const float* shift, int64_t P, int N,
-                            int mode, float* E) {
-    const int G = group_lanes(N), ab = coherent_bits(N);
-    for (int64_t p = 0; p < P; ++p) {
-        float sum[3] = {0.f, 0.f, 0.f};
-        for (int gl = 0; gl < G; ++gl) {
-            IrtWork w;
-            w.init(&s->view, v3(nrm[3 * p], nrm[3 * p + 1], nrm[3 * p + 2]), v3(pos[3 * p], pos[3 * p + 1], pos[3 * p + 2]),
-                   shift[2 * p], shift[2 * p + 1], N, mode, gl, G, ab, true);
-            trace_stream_bvh2(s->view, w, 32);
-            sum[0] += w.ax;
-            sum[1] += w.ay;
-            sum[2] += w.az;
-        }
-        for (int c = 0; c < 3; ++c) E[3 * p + c] = irradiance_finish(sum[c], N);
-    }
-}
-
-void emul_shade_stream(EmulScene* s, const float* nrm, const float* albedo, const float* rough, const float* pos,
-                       const float* cam, const float* irr, const float* shift_spec, const float* shift_diff, int64_t P,
-                       int N_spec, int N_diff, int mode_spec, int mode_diff, float eps, float* rgb, float* drgb,
-                       float* ediff) {
-    int gs = group_lanes(N_spec), gd = N_diff > 0 ? group_lanes(N_diff) : gs;
-    const int G = gs > gd ? gs : gd;
-    const int abs_ = coherent_bits(N_spec), abd = N_diff > 0 ? coherent_bits(N_diff) : 0;
-    V3 c = v3(cam[0], cam[1], cam[2]);
-    for (int64_t p = 0; p < P; ++p) {
-        float sp[3] = {0, 0, 0}, dsp[3] = {0, 0, 0}, df[3] = {0, 0, 0};
-        V3 n = v3(nrm[3 * p], nrm[3 * p + 1], nrm[3 * p + 2]), o = v3(pos[3 * p], pos[3 * p + 1], pos[3 * p + 2]);
-        for (int gl = 0; gl < G; ++gl) {
-            float d0 = N_diff > 0 ? shift_diff[2 * p] : 0.f, d1 = N_diff > 0 ? shift_diff[2 * p + 1] : 0.f;
-            ShadeWork<true> w;
-            w.init(&s->view, n, o, c, rough[p], eps, shift_spec[2 * p], shift_spec[2 * p + 1], N_spec, mode_spec, abs_, d0,
-                   d1, N_diff, mode_diff, abd, gl, G, true);
-            trace_stream_bvh2(s->view, w, 32);
-            for (int k = 0; k < 3; ++k) {
-                sp[k] += w.out.spec[k];
-                dsp[k] += w.out.dspec[k];
-                df[k] += w.out.diff[k];
-            }
-        }
-        float ir[3] = {0, 0, 0}, dfac[3];
-        if (N_diff == 0)
-            for (int k = 0; k < 3; ++k) ir[k] = irr[3 * p + k];
-        diffuse_factor(ir, df, N_diff, mode_diff, dfac);
-        for (int k = 0; k < 3; ++k) {
-            rgb[3 * p + k] = albedo[3 * p + k] * dfac[k] + sp[k] / (float)N_spec;
-            drgb[3 * p + k] = dsp[k] / (float)N_spec;
-            ediff[3 * p + k] = dfac[k];
-        }
-    }
-}
-
-// kind 3 = BVH2 with the cheaper node step of texir_stream.h
+// kind 3 = BVH2 with the cheaper node step of texir_walk.h
 void emul_cast_rays_fast(EmulScene* s, int quantised, const float* rays, int64_t R, float* t, uint32_t* id, float* uv) {
     for (int64_t r = 0; r < R; ++r) {
         V3 o = v3(rays[6 * r], rays[6 * r + 1], rays[6 * r + 2]), d = v3(rays[6 * r + 3], rays[6 * r + 4], rays[6 * r + 5]);

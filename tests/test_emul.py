@@ -153,7 +153,7 @@ def test_relighting_vs_reference(emul, scene_golden, dmode):
 
 
 # ---------------------------------------------------------------------------------------------------
-# ray-stream traversal (texir_stream.h): cheaper node step, per-lane work sources
+# the walks the kernels use (texir_walk.h): cheaper float node step, 32-byte quantised nodes
 # ---------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("quantised", [0, 1])
 def test_fast_node_step_bit_exact_vs_oracle(emul, oracle, quantised):
@@ -181,29 +181,3 @@ def test_quantised_nodes_on_degenerate_scenes(emul, oracle):
         t, i, uv = np.empty(len(rays), np.float32), np.empty(len(rays), np.uint32), np.empty((len(rays), 2), np.float32)
         emul.emul_cast_rays_fast(es.h, 1, rays.ctypes.data, len(rays), t.ctypes.data, i.ctypes.data, uv.ctypes.data)
         assert np.array_equal(i, i0) and np.array_equal(t, t0) and np.array_equal(uv, u0)
-
-
-def test_stream_work_sources_equal_the_lockstep_loops(emul, scene_golden):
-    name, g = scene_golden
-    es = EmulScene(emul, g["vertices"], g["triangles"], g["triangle_uvs"], g["texture"])
-    P = 200
-    sh = np.ascontiguousarray(g["irt_shift"].reshape(-1, 2)[:P])
-    for N in (5, 48, 128):
-        a, b = np.empty((P, 3), np.float32), np.empty((P, 3), np.float32)
-        emul.emul_irradiance(es.h, 2, g["irt_pos"].ctypes.data, g["irt_nrm"].ctypes.data, sh.ctypes.data, P, N, 0, a.ctypes.data)
-        emul.emul_irradiance_stream(es.h, g["irt_pos"].ctypes.data, g["irt_nrm"].ctypes.data, sh.ctypes.data, P, N, 0, b.ctypes.data)
-        assert np.array_equal(a, b)
-    P = len(g["pos"])
-    rough = np.ascontiguousarray(g["rough"].reshape(-1))
-    shs = np.ascontiguousarray(g["relight_uniform_shift_spec"].reshape(P, 2))
-    shd = np.ascontiguousarray(g["relight_uniform_shift_diff"].reshape(P, 2))
-    for n_diff, md in ((0, 0), (32, 0), (24, 1)):
-        outs = []
-        for fn in (lambda *a: emul.emul_shade(es.h, 2, *a), lambda *a: emul.emul_shade_stream(es.h, *a)):
-            rgb, drgb, ediff = (np.empty((P, 3), np.float32) for _ in range(3))
-            fn(g["nrm"].ctypes.data, g["albedo"].ctypes.data, rough.ctypes.data, g["pos"].ctypes.data, g["cam"].ctypes.data,
-               g["irr"].ctypes.data, shs.ctypes.data, shd.ctypes.data, P, 16, n_diff, 2, md, ctypes.c_float(1e-6),
-               rgb.ctypes.data, drgb.ctypes.data, ediff.ctypes.data)
-            outs.append((rgb, drgb, ediff))
-        for x, y in zip(*outs):
-            assert np.array_equal(x, y)

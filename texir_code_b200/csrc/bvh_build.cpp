@@ -49,10 +49,16 @@ struct BNode {
     int depth = 0;
 };
 
-constexpr int kBins = 16;
+#ifndef TX_BINS
+#define TX_BINS 16
+#endif
+#ifndef TX_COST_NODE
+#define TX_COST_NODE 1.2
+#endif
+constexpr int kBins = TX_BINS;
 constexpr int kMaxLeaf = 3;       // triangles per leaf (BVH8 child slots hold at most 3)
 constexpr int kSahDepthLimit = 40;  // beyond this depth fall back to object-median splits
-constexpr double kCostNode = 1.2, kCostTri = 1.0;
+constexpr double kCostNode = TX_COST_NODE, kCostTri = 1.0;
 
 struct Builder {
     const float* verts;
@@ -354,7 +360,7 @@ void flatten2(const Builder& B, float pad, int top_depth, HostBVH& out) {
 // QBVH2: the flattened BVH2 re-encoded with 32-byte nodes.  Every (already padded) child box is snapped
 // outwards onto a global 16-bit grid over the scene box and widened by one more grid unit per side, which
 // covers the half-unit error of the traversal's folded decode  t = fma(2^23 + q, step/d, (gmin - o)/d -
-// 2^23 step/d)  (texir_stream.h).  At 65 531 steps per axis the widening is ~0.1 mm on a 10 m scene.
+// 2^23 step/d)  (texir_walk.h).  At 65 531 steps per axis the widening is ~0.1 mm on a 10 m scene.
 // ----------------------------------------------------------------------------------------------
 void quantise2(HostBVH& out) {
     const size_t n = out.nodes2.size() / 4;

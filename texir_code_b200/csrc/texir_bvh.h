@@ -330,8 +330,8 @@ TX_HD V3 fetch_radiance(const SceneView& s, const Hit& h) {
               bilerp_apply(b4, nw.z, ne.z, sw.z, se.z));
 }
 
-TX_HD Hit trace_bvh2_fast(const SceneView& s, V3 o, V3 d);  // texir_stream.h
-TX_HD Hit trace_qbvh2(const SceneView& s, V3 o, V3 d);      // texir_stream.h
+TX_HD Hit trace_bvh2_fast(const SceneView& s, V3 o, V3 d);  // texir_walk.h
+TX_HD Hit trace_qbvh2(const SceneView& s, V3 o, V3 d);      // texir_walk.h
 template <int KIND>
 TX_HD Hit trace(const SceneView& s, V3 o, V3 d) {
     if (KIND == 8) return trace_bvh8(s, o, d);

@@ -80,27 +80,20 @@ static int device_of(const void* p) {
     return a.device;
 }
 
-// tuning knobs (environment, read once): TEXIR_STREAM=0 selects the lock-step kernels, TEXIR_REFILL=n the
-// number of still-traversing lanes below which a warp refills its idle lanes
+// tuning knobs (environment, read once), kept so that the measurements in DESIGN.md can be repeated
 static int env_int(const char* name, int dflt) {
     const char* v = getenv(name);
     return (v && *v) ? atoi(v) : dflt;
 }
-static int stream_mode() {  // 0: first lock-step kernels, 1: ray-stream kernels, 2: lock-step + cheaper node step,
-                            // 3 (default): 2 + the occupancy-tuned IrT kernel
-    static const int m = env_int("TEXIR_STREAM", 3);
+static int stream_mode() {  // TEXIR_KERNELS = 0: first kernels, 2: cheaper node step, 3 (default): 2 + the
+                            // occupancy-tuned (lean) IrT / render kernels
+    static const int m = env_int("TEXIR_KERNELS", 3);
     return m;
 }
-static bool use_stream() { return stream_mode() == 1; }
 static bool use_qnodes() {  // TEXIR_QNODES=0: walk the 64-byte float nodes instead of the 32-byte quantised ones
     static const bool on = env_int("TEXIR_QNODES", 1) != 0;
     return on;
 }
-static int refill_threshold() {
-    static const int r = env_int("TEXIR_REFILL", 20);
-    return r < 1 ? 1 : (r > 33 ? 33 : r);
-}
-
 static int finish_launch(const char* what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
@@ -340,31 +333,6 @@ __global__ void __launch_bounds__(128, TX_LEAN_MINB) k_irradiance_lean(SceneView
     }
 }
 
-// ray-stream variant (texir_stream.h): same sums, lanes do not wait for each other between rays
-__global__ void __launch_bounds__(128) k_irradiance_stream(SceneView s, const float* __restrict__ pos,
-                                                           const float* __restrict__ nrm,
-                                                           const float* __restrict__ shift,
-                                                           const int32_t* __restrict__ order, int64_t P, int N, int mode,
-                                                           int G, int abits, int refill, float* __restrict__ E) {
-    const int lane = threadIdx.x & 31;
-    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int gl = lane & (G - 1);
-    int64_t p = warp * (32 / G) + lane / G;
-    const bool live = p < P;
-    if (!live) p = P - 1;
-    if (order) p = __ldg(order + p);
-    IrtWork w;
-    w.init(&s, load3(nrm, p), load3(pos, p), __ldg(shift + 2 * p + 0), __ldg(shift + 2 * p + 1), N, mode, gl, G, abits,
-           live);
-    trace_stream_bvh2(s, w, refill);
-    float ax = group_sum(w.ax, G), ay = group_sum(w.ay, G), az = group_sum(w.az, G);
-    if (live && gl == 0) {
-        E[3 * p + 0] = irradiance_finish(ax, N);
-        E[3 * p + 1] = irradiance_finish(ay, N);
-        E[3 * p + 2] = irradiance_finish(az, N);
-    }
-}
-
 // ------------------------------------------------------------------------------------------------
 // fused render / its backward with ray recomputation   (models/mat_nvdiffrast.py:201-249)
 // ------------------------------------------------------------------------------------------------
@@ -392,7 +360,7 @@ struct ShadeArgs {
     float* g_irr;
 };
 
-// per-point epilogue of k_shade / k_shade_stream (lane gl == 0 of a live point)
+// per-point epilogue of k_shade / k_shade_lean (lane gl == 0 of a live point)
 template <bool TANGENT>
 __device__ __forceinline__ void shade_epilogue(const ShadeArgs& a, int64_t p, float sx, float sy, float sz, float dx,
                                                float dy, float dz, const float dsum[3]) {
@@ -589,29 +557,6 @@ __global__ void __launch_bounds__(128, TX_SHADE_LEAN_MINB) k_shade_lean(SceneVie
         lo.dspec[k] = TANGENT ? sm_acc[TANGENT ? 6 + k : 0][tid] : 0.f;
     }
     shade_reduce_store<TANGENT>(a, lo, p, live, lane, 32);
-}
-
-template <bool TANGENT>
-__global__ void __launch_bounds__(128) k_shade_stream(SceneView s, ShadeArgs a, int refill) {
-    const int G = a.G;
-    const int lane = threadIdx.x & 31;
-    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int gl = lane & (G - 1);
-    int64_t p = warp * (32 / G) + lane / G;
-    const bool live = p < a.P;
-    if (!live) p = a.P - 1;
-    const V3 cam = v3(__ldg(a.cam + 0), __ldg(a.cam + 1), __ldg(a.cam + 2));
-    float shd0 = 0.f, shd1 = 0.f;
-    if (a.N_diff > 0) {
-        shd0 = __ldg(a.shift_diff + 2 * p + 0);
-        shd1 = __ldg(a.shift_diff + 2 * p + 1);
-    }
-    ShadeWork<TANGENT> w;
-    w.init(&s, load3(a.nrm, p), load3(a.pos, p), cam, __ldg(a.rough + p), a.eps, __ldg(a.shift_spec + 2 * p + 0),
-           __ldg(a.shift_spec + 2 * p + 1), a.N_spec, a.mode_spec, a.a_spec, shd0, shd1, a.N_diff, a.mode_diff, a.a_diff,
-           gl, G, live);
-    trace_stream_bvh2(s, w, refill);
-    shade_reduce_store<TANGENT>(a, w.out, p, live, gl, G);
 }
 
 // backward from the forward-mode stash: no rays
@@ -1271,9 +1216,6 @@ int texir_irradiance_fwd(const texir_scene* sc, const float* pos, const float* n
     unsigned g = grid_for(warps * 32, 128);
     if (sc->info.bvh_kind == TEXIR_BVH8)
         k_irradiance<8><<<g, 128, 0, (cudaStream_t)stream>>>(sc->view, pos, nrm, shift, order, P, N, mode, G, ab, E);
-    else if (use_stream())
-        k_irradiance_stream<<<g, 128, 0, (cudaStream_t)stream>>>(sc->view, pos, nrm, shift, order, P, N, mode, G, ab,
-                                                                  refill_threshold(), E);
     else if (stream_mode() == 3 && G == 32 && use_qnodes())
         k_irradiance_lean<4><<<g, 128, 0, (cudaStream_t)stream>>>(sc->view, pos, nrm, shift, order, P, N, mode, ab, E);
     else if (stream_mode() == 3 && G == 32)
@@ -1320,8 +1262,6 @@ static int launch_shade(const texir_scene* sc, const ShadeArgs& a, void* stream)
     unsigned g = grid_for(warps * 32, 128);
     if (sc->info.bvh_kind == TEXIR_BVH8)
         k_shade<8, TANGENT><<<g, 128, 0, (cudaStream_t)stream>>>(sc->view, a);
-    else if (use_stream())
-        k_shade_stream<TANGENT><<<g, 128, 0, (cudaStream_t)stream>>>(sc->view, a, refill_threshold());
     else if (stream_mode() == 3 && a.G == 32 && use_qnodes())
         k_shade_lean<4, TANGENT><<<g, 128, 0, (cudaStream_t)stream>>>(sc->view, a);
     else if (stream_mode() >= 2 && use_qnodes())

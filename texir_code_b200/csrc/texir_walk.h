@@ -1,20 +1,14 @@
-// texir_stream.h -- ray-stream BVH2 traversal: each lane pulls rays from a per-lane work source, walks
-// them through the BVH and hands the hit back, WITHOUT waiting for the other lanes of its warp between rays.
+// texir_walk.h -- the BVH2 walks the kernels use (texir_bvh.h holds the first versions and the BVH8 walk).
 //
-// The first kernels ran "generate -> trace -> shade" per sample in lock step, so every ray cost the warp
-// the length of its longest ray (measured on B200: 13.3 of 32 lanes active, ncu
-// smsp__thread_inst_executed_per_inst_executed).  Here the traversal loop is the outer loop; a lane whose ray
-// has terminated idles only until the number of still-traversing lanes falls below `refill`, then all idle
-// lanes consume their hits and fetch new rays together (dynamic fetch after Aila & Laine, HPG 2009).  Lanes
-// that restart together share the node fetches of the upper tree levels (same origin, neighbouring
-// directions), which keeps the L1 wavefront count per ray low.
+//   trace_bvh2_fast   float nodes, t = fma(plane, 1/d, -o/d), no ulp widening (the builder's padding -- 1e-5 of the
+//                     scene diagonal + 4 ulp of the largest coordinate -- already covers every rounding of the slab
+//                     test), all node loads issued up front
+//   trace_qbvh2       the same tree with 32-byte nodes on a global 16-bit grid: half the L1/L2 traffic per visit
 //
-// The per-node arithmetic is also cheaper than texir_bvh.h's first version: t = fma(plane, 1/d, -o/d), no
-// ulp widening (the builder's padding, 1e-5 of the scene diagonal + 4 ulp of the largest coordinate, already
-// covers every rounding in the slab test -- see DESIGN.md), all four node loads issued up front.
+// Measured on B200 and dropped: a ray-stream variant in which idle lanes refill
+// independently (better lane use, worse L1 locality) and a speculative while-while loop.
 //
-// Host + device: tests/cpu_emul runs the same code one lane at a time (the refill heuristic is a no-op there;
-// it changes the order in which lanes make progress, never a result).
+// Host + device: tests/cpu_emul compiles the same code with g++.
 #pragma once
 #include "texir_bvh.h"
 
@@ -43,16 +37,12 @@ TX_D float4 ld_nc_f4(const float4* p) {
 TX_D void ld_nc_i2(const float4* p, int* a, int* b) {
     asm volatile("ld.global.nc.v2.s32 {%0,%1}, [%2];" : "=r"(*a), "=r"(*b) : "l"(p));
 }
-#define TX_ACTIVE_LANES() __popc(__activemask())
-#define TX_ANY(pred) __any_sync(0xFFFFFFFFu, (pred))
 #else
 inline float4 ld_nc_f4(const float4* p) { return *p; }
 inline void ld_nc_i2(const float4* p, int* a, int* b) {
     *a = float_as_int_(p->x);
     *b = float_as_int_(p->y);
 }
-#define TX_ACTIVE_LANES() 32
-#define TX_ANY(pred) (pred)
 #endif
 
 // one inner-node step: returns the next node (inner index, leaf reference < 0, or kSentinel)
@@ -210,53 +200,6 @@ TX_HD Hit trace_qbvh2(const SceneView& s, V3 o, V3 d) {
         }
     }
     return hit;
-}
-
-// Work concept:
-//   bool next(V3* o, V3* d)     produce this lane's next ray; false when the lane has no more rays
-//   void done(const Hit& h, V3 d) consume the finished ray (d = its direction)
-// `refill`: leave the traversal loop to refill idle lanes once fewer than `refill` lanes are still traversing
-// (32 = wait for nobody ... 1 = classic lock step).
-template <class Work>
-TX_HD void trace_stream_bvh2(const SceneView& s, Work& w, int refill) {
-    int stack[kStackSize];
-    RayState r;
-    Hit hit;
-    hit_reset(hit);
-    r.o = r.d = r.id = r.nood = v3(0.f, 0.f, 0.f);
-    int sp = 0;
-    int node = kSentinel;
-    bool live = false;  // this lane owns a ray in flight
-    bool more = true;   // this lane's source may have more rays
-    for (;;) {
-        if (node == kSentinel) {  // idle lane: hand back the finished ray, fetch the next one
-            if (live) {
-                w.done(hit, r.d);
-                live = false;
-            }
-            if (more) {
-                V3 o, d;
-                more = w.next(&o, &d);
-                if (more) {
-                    ray_setup(r, o, d);
-                    hit_reset(hit);
-                    sp = 0;
-                    stack[sp++] = kSentinel;
-                    node = 0;
-                    live = true;
-                }
-            }
-        }
-        if (!TX_ANY(live)) break;
-        while (node != kSentinel) {
-            while (node >= 0 && node != kSentinel) node = bvh2_step(s, r, hit.t, node, stack, sp);
-            if (node < 0) {
-                bvh2_leaf(s, r, node, hit);
-                node = stack[--sp];
-            }
-            if (TX_ACTIVE_LANES() < refill) break;
-        }
-    }
 }
 
 }  // namespace texir
