@@ -114,6 +114,21 @@ TEXIR_API int texir_irradiance_fwd(const texir_scene* scene, const float* pos, c
 /* order [P] (int32, device): the points sorted along a 30-bit Morton curve over the scene box */
 TEXIR_API int texir_point_order(const texir_scene* scene, const float* pos, int64_t P, int32_t* order, void* stream);
 
+/* ---- fused radiance-field samples: the target generator of the NIrF / irradiance-field stages,
+ *      models/tracer_o3d.py:73-116 and models/tracer_o3d_irrf.py:72-122: for every point the N
+ *      shifted-Hammersley directions of generate_dir(nrm, N, mode) are traced and the hit radiance returned
+ *      un-reduced.  rad [P,N,3]; dir [P,N,3] (nullable) receives the directions. */
+TEXIR_API int texir_radiance_samples(const texir_scene* scene, const float* pos, const float* nrm, const float* shift,
+                                     int64_t P, int N, int mode, float* rad, float* dir, void* stream);
+
+/* ---- G-buffer from primary rays (replaces dr.rasterize + dr.interpolate of position / normal / uv,
+ *      models/mat_nvdiffrast.py:119-126, models/tracer_o3d_irt.py:99-112).
+ * rays [R,6].  Outputs (each nullable): pos [R,3] hit point, nrm [R,3] unit geometric normal turned against the
+ * ray, uv [R,2] interpolated per-corner UVs (the reference's texc), prim [R] u32, bary [R,2], mask [R] f32
+ * (1 = covered).  Uncovered pixels get pos = nrm = (1,0,0) like mat_nvdiffrast.py:125, uv = 0. */
+TEXIR_API int texir_gbuffer(const texir_scene* scene, const float* rays, int64_t R, float* pos, float* nrm, float* uv,
+                            uint32_t* prim, float* bary, float* mask, void* stream);
+
 /* ---- fused render: MaterialModel.render, models/mat_nvdiffrast.py:201-249 (and the relighting
  *      variant models/test_nvdiffrast.py:256-303 when N_diff > 0).
  * nrm, albedo, pos, irr [P,3]; rough [P]; cam [3]; shift_spec [P,2]; shift_diff [P,2] (N_diff > 0).

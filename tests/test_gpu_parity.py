@@ -348,6 +348,86 @@ def test_irradiance_edge_cases(tx, gscene, cuda_device):
         tx.irradiance(sc, pos[:4], nrm[:4], sh[:4], 8, "importance")
 
 
+def test_radiance_samples_is_the_nirf_target_generator(tx, gscene, oracle, cuda_device):
+    """models/tracer_o3d.py:73-116: generate_dir(uniform, h*w Hammersley + shift) -> cast -> texture, un-reduced"""
+    name, g, sc = gscene
+    P, N = 64, 8 * 16  # resolution [8,16] like train.env_res
+    pos, nrm, sh = T(g["irt_pos"][:P], cuda_device), T(g["irt_nrm"][:P], cuda_device), T(g["irt_shift"][:P], cuda_device)
+    n0 = tx.launch_count()
+    rad, dirs = tx.radiance_samples(sc, pos, nrm, sh, N, return_dirs=True)
+    assert tx.launch_count() - n0 == 1 and rad.shape == (P, N, 3)
+    l = tx.generate_dir(nrm, N, None, "uniform", shift=sh)
+    assert torch.equal(dirs, l) and torch.equal(rad, tx.query_irf(sc, pos, l))
+    lo = oracle.generate_dir(torch.from_numpy(g["irt_nrm"][:P]), N, None, "uniform", shift=torch.from_numpy(g["irt_shift"][:P]))
+    ro = oracle.query_irf(oracle.OracleScene(g["vertices"], g["triangles"]), g["triangle_uvs"], torch.from_numpy(g["texture"]),
+                          torch.from_numpy(g["irt_pos"][:P]).unsqueeze(1).expand_as(lo), lo.unsqueeze(-2), N)
+    assert rel_l2(rad.cpu().numpy(), ro.numpy()) < FWD_TOL
+
+
+def test_gbuffer_from_primary_rays(tx, gscene, oracle, cuda_device):
+    from texir_code_b200 import synth
+    name, g, sc = gscene
+    rays = synth.cube_map_rays(16, cam=(0.2, -0.1, 0.3))
+    gb = tx.gbuffer(sc, T(rays, cuda_device).reshape(6, 16, 16, 6))
+    assert gb["position"].shape == (6, 16, 16, 3) and gb["texc"].shape == (6, 16, 16, 2) and gb["mask"].shape == (6, 16, 16, 1)
+    t0, i0, u0 = oracle.OracleScene(g["vertices"], g["triangles"], brute=True).cast_rays_np(rays)
+    assert np.array_equal(gb["primitive_ids"].cpu().numpy().reshape(-1).view(np.uint32), i0)
+    assert np.array_equal(gb["primitive_uvs"].cpu().numpy().reshape(-1, 2), u0)
+    hit = i0 != 0xFFFFFFFF
+    assert np.array_equal(gb["mask"].cpu().numpy().reshape(-1) > 0, hit) and hit.mean() > 0.95
+    x = rays[:, :3].astype(np.float64) + rays[:, 3:].astype(np.float64) * t0[:, None].astype(np.float64)
+    got = gb["position"].cpu().numpy().reshape(-1, 3)
+    assert np.abs(got[hit] - x[hit]).max() < 2e-6
+    tri = g["vertices"][g["triangles"][np.where(hit, i0, 0).astype(np.int64)]].astype(np.float64)
+    ng = np.cross(tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0])
+    ng /= np.linalg.norm(ng, axis=1, keepdims=True)
+    ng *= -np.sign((ng * rays[:, 3:]).sum(1, keepdims=True))  # facing the camera
+    assert np.abs(gb["normal"].cpu().numpy().reshape(-1, 3)[hit] - ng[hit]).max() < 1e-5
+    # texc = the reference's UV interpolation (mat_nvdiffrast.py:303-311)
+    uvc = g["triangle_uvs"].reshape(-1, 3, 2)[np.where(hit, i0, 0).astype(np.int64)]
+    b = np.clip(u0, 0, 1)
+    uv = uvc[:, 0] * (1 - b[:, 0:1] - b[:, 1:2]) + uvc[:, 1] * b[:, 0:1] + uvc[:, 2] * b[:, 1:2]
+    assert np.abs(gb["texc"].cpu().numpy().reshape(-1, 2)[hit] - uv[hit].astype(np.float32)).max() <= 1e-7
+    if (~hit).any():
+        assert np.all(got[~hit] == [1, 0, 0])
+    off = tx.gbuffer(sc, T(rays, cuda_device), offset=1e-2)["position"].cpu().numpy()
+    assert np.abs(off[hit] - (got[hit] + 1e-2 * gb["normal"].cpu().numpy().reshape(-1, 3)[hit])).max() < 1e-6
+
+
+def test_material_textures_receive_scattered_gradients(tx, gscene, oracle, cuda_device):
+    """G-buffer -> bilinear material fetch -> fused render -> backward: the gradients land in the trainable
+    textures materials_a / materials_r through the atomic scatter, compared with the same chain in
+    torch (grid_sample) on top of the oracle's render"""
+    name, g, _ = gscene
+    mm = tx.MaterialModel(g["vertices"], g["triangles"], g["triangle_uvs"], torch.from_numpy(g["texture"]),
+                          sample_l=[16, 16], device=cuda_device, materials_a_res=32, materials_r_res=64)
+    rng = np.random.default_rng(7)
+    with torch.no_grad():
+        mm.materials_a.copy_(T(rng.uniform(0.1, 0.9, size=(32, 32, 3)).astype(np.float32), cuda_device))
+        mm.materials_r.copy_(T(rng.uniform(0.05, 0.7, size=(64, 64, 1)).astype(np.float32), cuda_device))
+    P = len(g["pos"])
+    texc = rng.uniform(0.05, 0.95, size=(P, 2)).astype(np.float32)
+    torch.manual_seed(666)
+    out = mm(T(g["nrm"], cuda_device), T(g["pos"], cuda_device), T(g["cam"], cuda_device), T(g["irr"], cuda_device),
+             texc=T(texc, cuda_device))
+    (out["rgb"] * T(g["g_rgb"], cuda_device)).sum().backward()
+    # torch / oracle chain on the CPU
+    ta = mm.materials_a.detach().cpu().clone().requires_grad_(True)
+    tr = mm.materials_r.detach().cpu().clone().requires_grad_(True)
+    grid = (torch.from_numpy(texc) * 2 - 1).reshape(1, P, 1, 2)
+    fetch = lambda t: torch.nn.functional.grid_sample(t.permute(2, 0, 1).unsqueeze(0), grid, mode="bilinear",
+                                                      padding_mode="border", align_corners=False)[0, :, :, 0].t()
+    ref = oracle.render(oracle.OracleScene(g["vertices"], g["triangles"]), g["triangle_uvs"], torch.from_numpy(g["texture"]),
+                        [16, 16], ["uniform", "importance"], torch.from_numpy(g["nrm"]), fetch(ta), fetch(tr),
+                        torch.from_numpy(g["pos"]), torch.from_numpy(g["cam"]), torch.from_numpy(g["irr"]),
+                        shift_spec=torch.from_numpy(g["render_e14_16_shift"]))
+    (ref["rgb"] * torch.from_numpy(g["g_rgb"])).sum().backward()
+    assert rel_l2(out["rgb"].detach().cpu().numpy(), ref["rgb"].detach().numpy()) < FWD_TOL
+    assert rel_l2(mm.materials_a.grad.cpu().numpy(), ta.grad.numpy()) < GRAD_TOL
+    assert rel_l2(mm.materials_r.grad.cpu().numpy(), tr.grad.numpy()) < GRAD_TOL
+    assert (mm.materials_a.grad != 0).any() and (mm.materials_r.grad != 0).any()
+
+
 def test_point_order_is_a_morton_permutation_and_changes_no_value(tx, big, cuda_device):
     from texir_code_b200 import ops, synth
     sc, tex, scene = big

@@ -24,6 +24,8 @@ def __getattr__(name):  # lazy: importing the package must not require torch.cud
         "specular_reflectance": ("ops", "specular_reflectance"),
         "diffuse_reflectance": ("ops", "diffuse_reflectance"),
         "shade": ("ops", "shade"), "irradiance": ("ops", "irradiance"), "texture_fetch": ("ops", "texture_fetch"),
+        "radiance_samples": ("ops", "radiance_samples"), "gbuffer": ("ops", "gbuffer"),
+        "point_order": ("ops", "point_order"),
         "HotPathMixin": ("models", "HotPathMixin"), "MaterialModel": ("models", "MaterialModel"),
         "TracerO3d": ("models", "TracerO3d"),
     }
@@ -36,5 +38,5 @@ def __getattr__(name):  # lazy: importing the package must not require torch.cud
 
 
 __all__ = ["TexirError", "launch_count", "Scene", "RaycastingScene", "generate_dir", "sample_hemisphere", "query_irf",
-           "trace", "specular_reflectance", "diffuse_reflectance", "shade", "irradiance", "texture_fetch",
+           "trace", "specular_reflectance", "diffuse_reflectance", "shade", "irradiance", "texture_fetch", "radiance_samples", "gbuffer", "point_order",
            "HotPathMixin", "MaterialModel", "TracerO3d"]

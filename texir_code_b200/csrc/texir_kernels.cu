@@ -230,6 +230,73 @@ __global__ void __launch_bounds__(128) k_query_irf(SceneView s, const float* __r
 }
 
 // ------------------------------------------------------------------------------------------------
+// fused radiance-field samples (generate_dir + query_irf, un-reduced) and the primary-ray G-buffer
+// ------------------------------------------------------------------------------------------------
+template <int KIND>
+__global__ void __launch_bounds__(128) k_radiance_samples(SceneView s, const float* __restrict__ pos,
+                                                          const float* __restrict__ nrm, const float* __restrict__ shift,
+                                                          int64_t P, int N, int mode, float* __restrict__ rad,
+                                                          float* __restrict__ dir) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P * (int64_t)N) return;
+    int64_t p = idx / N;
+    uint32_t i = (uint32_t)(idx - p * N);
+    Frame f = make_frame(load3(nrm, p));
+    float s0 = shift_wrap_clamp(hammersley0(i, (uint32_t)N), __ldg(shift + 2 * p + 0));
+    float s1 = shift_wrap_clamp(radical_inverse(i), __ldg(shift + 2 * p + 1));
+    V3 d = sample_dir<false>(f, mode, s0, s1, 0.f).d;
+    Hit h = trace<KIND>(s, load3(pos, p), d);
+    V3 L = fetch_radiance(s, h);
+    rad[3 * idx + 0] = L.x;
+    rad[3 * idx + 1] = L.y;
+    rad[3 * idx + 2] = L.z;
+    if (dir) {
+        dir[3 * idx + 0] = d.x;
+        dir[3 * idx + 1] = d.y;
+        dir[3 * idx + 2] = d.z;
+    }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(128) k_gbuffer(SceneView s, const float* __restrict__ rays, int64_t R,
+                                                 const uint32_t* __restrict__ slot_of_prim, float* __restrict__ pos,
+                                                 float* __restrict__ nrm, float* __restrict__ uv,
+                                                 uint32_t* __restrict__ prim, float* __restrict__ bary,
+                                                 float* __restrict__ mask) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    V3 o = v3(__ldg(rays + 6 * r + 0), __ldg(rays + 6 * r + 1), __ldg(rays + 6 * r + 2));
+    V3 d = v3(__ldg(rays + 6 * r + 3), __ldg(rays + 6 * r + 4), __ldg(rays + 6 * r + 5));
+    Hit h = trace<KIND>(s, o, d);
+    const bool hit = h.prim != kInvalidId;
+    V3 x = v3(1.f, 0.f, 0.f), n = v3(1.f, 0.f, 0.f);
+    float tu = 0.f, tv = 0.f;
+    if (hit) {
+        x = v3(o.x + h.t * d.x, o.y + h.t * d.y, o.z + h.t * d.z);
+        const float4 c = __ldg(s.tris2 + 3 * (size_t)__ldg(slot_of_prim + h.prim) + 2);
+        // stored Ng = e2 x e1 = -(v1-v0) x (v2-v0); Open3D's primitive_normals follow (v1-v0) x (v2-v0)
+        float gx = -c.y, gy = -c.z, gz = -c.w;
+        float len = sqrtf(gx * gx + gy * gy + gz * gz);
+        if (len > 0.f) {
+            float sgn = (gx * d.x + gy * d.y + gz * d.z) > 0.f ? -1.0f : 1.0f;  // face the viewer
+            n = v3(sgn * gx / len, sgn * gy / len, sgn * gz / len);
+        }
+        if (s.tri_uvs) {
+            const double* t = s.tri_uvs + 6 * (size_t)h.prim;
+            double tuv[6];
+            for (int k = 0; k < 6; ++k) tuv[k] = t[k];
+            interp_uv(tuv, h.u, h.v, &tu, &tv);
+        }
+    }
+    if (pos) { pos[3 * r + 0] = x.x; pos[3 * r + 1] = x.y; pos[3 * r + 2] = x.z; }
+    if (nrm) { nrm[3 * r + 0] = n.x; nrm[3 * r + 1] = n.y; nrm[3 * r + 2] = n.z; }
+    if (uv) { uv[2 * r + 0] = tu; uv[2 * r + 1] = tv; }
+    if (prim) prim[r] = h.prim;
+    if (bary) { bary[2 * r + 0] = h.u; bary[2 * r + 1] = h.v; }
+    if (mask) mask[r] = hit ? 1.0f : 0.0f;
+}
+
+// ------------------------------------------------------------------------------------------------
 // fused IrT: E = sum_i L_i clamp(n.l_i) * 2 pi / N       (models/tracer_o3d_irt.py:168-171)
 // ------------------------------------------------------------------------------------------------
 #ifndef TX_IRR_MINB
@@ -1200,6 +1267,36 @@ int texir_point_order(const texir_scene* sc, const float* pos, int64_t P, int32_
     }
     cudaFreeAsync(ws, st);
     return rc;
+}
+
+int texir_radiance_samples(const texir_scene* sc, const float* pos, const float* nrm, const float* shift, int64_t P,
+                           int N, int mode, float* rad, float* dir, void* stream) {
+    if (check_scene_tex("texir_radiance_samples", sc) || check_pn("texir_radiance_samples", P, N) ||
+        check_mode("texir_radiance_samples", mode))
+        return 1;
+    if (mode == TEXIR_MODE_IMPORTANCE) TX_FAIL("texir_radiance_samples: sampling must be uniform or cosine");
+    if (P == 0) return 0;
+    if (!pos || !nrm || !shift || !rad) TX_FAIL("texir_radiance_samples: NULL argument");
+    DeviceGuard guard(sc->info.device);
+    unsigned g = grid_for(P * N, 128);
+    if (sc->info.bvh_kind == TEXIR_BVH8)
+        k_radiance_samples<8><<<g, 128, 0, (cudaStream_t)stream>>>(sc->view, pos, nrm, shift, P, N, mode, rad, dir);
+    else
+        k_radiance_samples<4><<<g, 128, 0, (cudaStream_t)stream>>>(sc->view, pos, nrm, shift, P, N, mode, rad, dir);
+    return finish_launch("k_radiance_samples");
+}
+
+int texir_gbuffer(const texir_scene* sc, const float* rays, int64_t R, float* pos, float* nrm, float* uv,
+                  uint32_t* prim, float* bary, float* mask, void* stream) {
+    if (!sc) TX_FAIL("texir_gbuffer: NULL scene");
+    if (R < 0) TX_FAIL("texir_gbuffer: negative ray count");
+    if (R == 0) return 0;
+    if (!rays) TX_FAIL("texir_gbuffer: NULL rays");
+    if (uv && !sc->view.tri_uvs) TX_FAIL("texir_gbuffer: uv requested but the scene has no triangle uvs");
+    DeviceGuard guard(sc->info.device);
+    k_gbuffer<4><<<grid_for(R, 128), 128, 0, (cudaStream_t)stream>>>(sc->view, rays, R, (const uint32_t*)sc->d_slot_of_prim,
+                                                                      pos, nrm, uv, prim, bary, mask);
+    return finish_launch("k_gbuffer");
 }
 
 int texir_irradiance_fwd(const texir_scene* sc, const float* pos, const float* nrm, const float* shift,

@@ -277,6 +277,54 @@ def irradiance(scene: Scene, position: torch.Tensor, normal: torch.Tensor, shift
     return E
 
 
+def radiance_samples(scene: Scene, position: torch.Tensor, normal: torch.Tensor, shift: torch.Tensor,
+                     num_samples: int, mode: str = "uniform", return_dirs: bool = False):
+    """Target generator of the NIrF / irradiance-field stages (models/tracer_o3d.py:73-116): the N
+    shifted-Hammersley directions of every point are traced and the hit radiance returned un-reduced.
+    position, normal [P,3]; shift [P,1,2]; -> rad [P,N,3] (and the directions [P,N,3])."""
+    _need_cuda("radiance_samples", position)
+    dev = position.device
+    P, N = int(position.shape[0]), int(num_samples)
+    pos, nrm = _f32c(position), _f32c(normal)
+    sh = _f32c(shift, dev).reshape(P, 2)
+    rad = torch.empty(P, N, 3, dtype=torch.float32, device=dev)
+    dirs = torch.empty(P, N, 3, dtype=torch.float32, device=dev) if return_dirs else None
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().texir_radiance_samples(scene.handle, _ptr(pos), _ptr(nrm), _ptr(sh), P, N,
+                                                      _lib.MODES[mode], _ptr(rad), _ptr(dirs), _stream_ptr(dev)),
+                   "texir_radiance_samples")
+    return (rad, dirs) if return_dirs else rad
+
+
+def gbuffer(scene: Scene, rays: torch.Tensor, offset: float = 0.0) -> dict:
+    """G-buffer from primary rays [...,6] (replaces dr.rasterize + dr.interpolate, mat_nvdiffrast.py:119-126):
+    dict(position, normal [...,3], texc [...,2] when the scene has UVs, primitive_ids, primitive_uvs, mask).
+    position = hit + offset * normal (the reference shifts by 1e-2, :179); uncovered pixels get position =
+    normal = (1,0,0)."""
+    _need_cuda("gbuffer", rays)
+    dev = rays.device
+    r = _f32c(rays).reshape(-1, 6)
+    shape = tuple(rays.shape[:-1])
+    R = int(r.shape[0])
+    pos = torch.empty(R, 3, dtype=torch.float32, device=dev)
+    nrm = torch.empty(R, 3, dtype=torch.float32, device=dev)
+    uv = torch.empty(R, 2, dtype=torch.float32, device=dev) if scene.has_uvs else None
+    prim = torch.empty(R, dtype=torch.int32, device=dev)
+    bary = torch.empty(R, 2, dtype=torch.float32, device=dev)
+    mask = torch.empty(R, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().texir_gbuffer(scene.handle, _ptr(r), R, _ptr(pos), _ptr(nrm), _ptr(uv), _ptr(prim),
+                                             _ptr(bary), _ptr(mask), _stream_ptr(dev)), "texir_gbuffer")
+    if offset:
+        pos = torch.where(mask.unsqueeze(-1) > 0, pos + offset * nrm, pos)
+    out = {"position": pos.reshape(shape + (3,)), "normal": nrm.reshape(shape + (3,)),
+           "primitive_ids": prim.reshape(shape), "primitive_uvs": bary.reshape(shape + (2,)),
+           "mask": mask.reshape(shape + (1,))}
+    if uv is not None:
+        out["texc"] = uv.reshape(shape + (2,))
+    return out
+
+
 # --------------------------------------------------------------------------------------------------
 # material-texture fetch / gradient scatter (dr.texture 'linear', models/mat_nvdiffrast.py:131-139)
 # --------------------------------------------------------------------------------------------------
