@@ -119,7 +119,7 @@ class ClockSampler:
 
 def make_workload(seed_offset: int = 0):
     from texir_code_b200 import synth
-    sc = synth.make_room_scene(NUM_TRIS, seed=666)
+    sc = synth.make_room_scene(NUM_TRIS, seed=666, tex_res=TEX_RES)
     tex = synth.make_radiance_texture(TEX_RES, seed=666)
     return sc, tex
 
@@ -313,9 +313,10 @@ def run_ours(args):
             "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {
-                "workload": "IrT generation (BASELINE configs[1]): synthetic closed room, T=2^20 triangles, 4096^2 "
+                "workload": "IrT generation (BASELINE configs[1]): synthetic closed room, T=%d triangles, %d^2 "
                             "fp32 radiance texture, P=%d texels per GPU x 2048 spp uniform, forward only (the "
-                            "reference's IrT stage has no backward; the Mat-stage fwd+bwd is under 'mat_stage')" % P,
+                            "reference's IrT stage has no backward; the Mat-stage fwd+bwd is under 'mat_stage')"
+                            % (NUM_TRIS, TEX_RES, P),
                 "points_per_gpu": P, "spp": SPP, "triangles": NUM_TRIS, "texture": [TEX_RES, TEX_RES],
                 "bvh": "BVH%d" % info["bvh_kind"], "scene_bytes": info["device_bytes"],
                 "l2": "no flush: BVH + triangles + UVs + texture = %.0f MB resident, larger than the 126 MB L2"
@@ -394,7 +395,10 @@ def main():
     ap.add_argument("--bvh", type=int, default=2, choices=[2, 8], help="BVH layout the kernels traverse")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-mat", action="store_true", help="skip the material-stage fwd+bwd leg")
+    ap.add_argument("--tris", type=int, default=NUM_TRIS, help="triangles of the synthetic scene (configs[3]: 4194304)")
+    ap.add_argument("--tex", type=int, default=TEX_RES, help="radiance texture resolution (configs[3]: 8192)")
     args = ap.parse_args()
+    globals().update(NUM_TRIS=args.tris, TEX_RES=args.tex)
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)
