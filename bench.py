@@ -359,14 +359,14 @@ def bench_material_stage(scene, sc, dev, args):
     t = lambda x: torch.from_numpy(x).to(dev)
     nrm_d, pos_d, irr_d, g_d, cam = t(nrm), t(pos), t(irr), t(g_rgb), torch.zeros(3, device=dev)
     out = {"pixels": P, "spp": N}
-    for mode in ("stash", "recompute"):
+    for mode, N in (("stash", 256), ("recompute", 256), ("stash_16spp", 16)):  # 16 spp = configs/syn.conf training
         a = t(albedo).requires_grad_(True)
         r = t(rough).requires_grad_(True)
 
         def step():
             a.grad = None
             r.grad = None
-            rgb = ops.shade(scene, nrm_d, a, r, pos_d, cam, irr_d, sh, num_spec=N, backward=mode)
+            rgb = ops.shade(scene, nrm_d, a, r, pos_d, cam, irr_d, sh, num_spec=N, backward=mode.split("_")[0])
             rgb.backward(g_d)
 
         for _ in range(2):

@@ -38,7 +38,6 @@ EmulScene* emul_scene_create(const float* verts, int64_t nv, const int32_t* tris
     if (uvs) s->uvs.assign(uvs, uvs + 6 * (size_t)nt);
     s->view.nodes2 = s->bvh.nodes2.data();
     s->view.tris2 = s->bvh.tris2.data();
-    s->view.prim2 = s->bvh.prim2.data();
     s->view.qnodes2 = s->bvh.qnodes2.data();
     for (int a = 0; a < 3; ++a) {
         s->view.qmin[a] = s->bvh.qmin[a];
@@ -46,7 +45,6 @@ EmulScene* emul_scene_create(const float* verts, int64_t nv, const int32_t* tris
     }
     s->view.nodes8 = s->bvh.nodes8.data();
     s->view.tris8 = s->bvh.tris8.data();
-    s->view.prim8 = s->bvh.prim8.data();
     s->view.tri_uvs = s->uvs.empty() ? nullptr : s->uvs.data();
     s->view.num_tris = (uint32_t)nt;
     return s;

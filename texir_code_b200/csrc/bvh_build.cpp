@@ -233,16 +233,16 @@ struct Builder {
     }
 };
 
-void pack_triangle(const float* verts, const int32_t* tri, float4* out) {
+float as_float(int i);
+void pack_triangle(const float* verts, const int32_t* tri, int prim, float4* out) {
     V3 a = v3(verts[3 * (size_t)tri[0] + 0], verts[3 * (size_t)tri[0] + 1], verts[3 * (size_t)tri[0] + 2]);
     V3 b = v3(verts[3 * (size_t)tri[1] + 0], verts[3 * (size_t)tri[1] + 1], verts[3 * (size_t)tri[1] + 2]);
     V3 c = v3(verts[3 * (size_t)tri[2] + 0], verts[3 * (size_t)tri[2] + 1], verts[3 * (size_t)tri[2] + 2]);
     V3 e1 = rn_sub(a, b);
     V3 e2 = rn_sub(c, a);
-    V3 ng = fcross(e2, e1);
     out[0] = float4{a.x, a.y, a.z, e1.x};
     out[1] = float4{e1.y, e1.z, e2.x, e2.y};
-    out[2] = float4{e2.z, ng.x, ng.y, ng.z};
+    out[2] = float4{e2.z, as_float(prim), 0.f, 0.f};
 }
 
 float as_float(int i) {
@@ -282,7 +282,7 @@ void flatten2(const Builder& B, float pad, int top_depth, HostBVH& out) {
         for (int i = 0; i < n.count; ++i) {
             int p = B.idx[n.first + i];
             float4 t[3];
-            pack_triangle(B.verts, B.tris + 3 * (size_t)p, t);
+            pack_triangle(B.verts, B.tris + 3 * (size_t)p, p, t);
             out.tris2.push_back(t[0]);
             out.tris2.push_back(t[1]);
             out.tris2.push_back(t[2]);
@@ -524,7 +524,7 @@ void build8(const Builder& B, float pad, HostBVH& out) {
                 for (int i = 0; i < cn.count; ++i) {
                     int p = B.idx[cn.first + i];
                     float4 t[3];
-                    pack_triangle(B.verts, B.tris + 3 * (size_t)p, t);
+                    pack_triangle(B.verts, B.tris + 3 * (size_t)p, p, t);
                     out.tris8.push_back(t[0]);
                     out.tris8.push_back(t[1]);
                     out.tris8.push_back(t[2]);

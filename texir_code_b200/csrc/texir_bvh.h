@@ -22,8 +22,10 @@
 //        on GPUs Through Compressed Wide BVHs", HPG 2017).  See BVH8 section below.
 //
 //  Triangles (both): slot-ordered, 48 bytes = 3 x float4:
-//          (v0.x v0.y v0.z e1.x) (e1.y e1.z e2.x e2.y) (e2.z ng.x ng.y ng.z)
-//        with e1 = v0 - v1, e2 = v2 - v0, ng = e2 x e1; original primitive id in tri_prim[slot].
+//          (v0.x v0.y v0.z e1.x) (e1.y e1.z e2.x e2.y) (e2.z prim - -)
+//        with e1 = v0 - v1, e2 = v2 - v0 and the original primitive id as int bits in the same record, so that
+//        accepting a hit needs no second, dependent load; Ng = e2 x e1 is recomputed per test with the same
+//        fma chain the builder and the oracle use (three FMA-pipe instructions, the pipe with headroom).
 #pragma once
 #include "texir_math.h"
 
@@ -53,12 +55,10 @@ constexpr int kStack8 = 48;
 struct SceneView {
     const float4* __restrict__ nodes2;     // BVH2 nodes, 4 float4 each
     const float4* __restrict__ tris2;      // BVH2-ordered triangle slots, 3 float4 each
-    const uint32_t* __restrict__ prim2;    // slot -> original primitive id
     const uint4* __restrict__ qnodes2;     // QBVH2 nodes, 2 uint4 each (same indices as nodes2)
     float qmin[3], qstep[3];               // the global 16-bit grid of qnodes2
     const uint4* __restrict__ nodes8;      // BVH8 nodes, 5 uint4 each
     const float4* __restrict__ tris8;      // BVH8-ordered triangle slots
-    const uint32_t* __restrict__ prim8;
     const double* __restrict__ tri_uvs;    // [T][3][2] float64, original primitive order
     const float4* __restrict__ tex;        // radiance texture, RGBA float4 [H][W]
     int tex_w, tex_h;
@@ -104,15 +104,15 @@ TX_HD bool slab(float lox, float hix, float loy, float hiy, float loz, float hiz
     return tmin * 0.9999996f <= tmax * 1.0000004f;
 }
 
-TX_HD void test_slot(const float4* __restrict__ tris, const uint32_t* __restrict__ prims, int slot, V3 o, V3 d,
-                     Hit& hit) {
+TX_HD void test_slot(const float4* __restrict__ tris, int slot, V3 o, V3 d, Hit& hit) {
     float4 a = TX_LDG(&tris[3 * slot + 0]);
     float4 b = TX_LDG(&tris[3 * slot + 1]);
     float4 c = TX_LDG(&tris[3 * slot + 2]);
+    const V3 e1 = v3(a.w, b.x, b.y), e2 = v3(b.z, b.w, c.x);
     float t, u, v;
-    if (tri_test(v3(a.x, a.y, a.z), v3(a.w, b.x, b.y), v3(b.z, b.w, c.x), v3(c.y, c.z, c.w), o, d, &t, &u, &v)) {
+    if (tri_test(v3(a.x, a.y, a.z), e1, e2, fcross(e2, e1), o, d, &t, &u, &v)) {
         if (t <= hit.t) {
-            uint32_t p = TX_LDG(&prims[slot]);
+            uint32_t p = (uint32_t)float_as_int_(c.y);
             if (t < hit.t || p < hit.prim) {
                 hit.t = t;
                 hit.u = u;
@@ -162,7 +162,7 @@ TX_HD Hit trace_bvh2(const SceneView& s, V3 o, V3 d, uint32_t* nodes_visited = n
         if (node < 0) {
             int ref = ~node;
             int first = ref >> 3, cnt = (ref & 7) + 1;
-            for (int i = 0; i < cnt; ++i) test_slot(s.tris2, s.prim2, first + i, o, d, hit);
+            for (int i = 0; i < cnt; ++i) test_slot(s.tris2, first + i, o, d, hit);
             nt += cnt;
             node = stack[--sp];
         }
@@ -290,7 +290,7 @@ TX_HD Hit trace_bvh8(const SceneView& s, V3 o, V3 d, uint32_t* nodes_visited = n
         while (tg.mask != 0) {
             int bit = ffs_msb_(tg.mask);
             tg.mask &= ~(1u << bit);
-            test_slot(s.tris8, s.prim8, (int)(tg.base + (uint32_t)bit), o, d, hit);
+            test_slot(s.tris8, (int)(tg.base + (uint32_t)bit), o, d, hit);
             ++nt;
         }
         if (ng.mask <= 0x00FFFFFFu) {

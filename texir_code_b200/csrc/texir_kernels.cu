@@ -31,11 +31,9 @@ struct texir_scene {
     texir_scene_info info{};
     void* d_nodes2 = nullptr;
     void* d_tris2 = nullptr;
-    void* d_prim2 = nullptr;
     void* d_qnodes2 = nullptr;
     void* d_nodes8 = nullptr;
     void* d_tris8 = nullptr;
-    void* d_prim8 = nullptr;
     void* d_uvs = nullptr;
     void* d_slot_of_prim = nullptr;  // original primitive id -> BVH2 slot
     void* d_tex = nullptr;
@@ -273,9 +271,11 @@ __global__ void __launch_bounds__(128) k_gbuffer(SceneView s, const float* __res
     float tu = 0.f, tv = 0.f;
     if (hit) {
         x = v3(o.x + h.t * d.x, o.y + h.t * d.y, o.z + h.t * d.z);
-        const float4 c = __ldg(s.tris2 + 3 * (size_t)__ldg(slot_of_prim + h.prim) + 2);
-        // stored Ng = e2 x e1 = -(v1-v0) x (v2-v0); Open3D's primitive_normals follow (v1-v0) x (v2-v0)
-        float gx = -c.y, gy = -c.z, gz = -c.w;
+        const float4* tp = s.tris2 + 3 * (size_t)__ldg(slot_of_prim + h.prim);
+        const float4 ta = __ldg(tp), tb = __ldg(tp + 1), tc = __ldg(tp + 2);
+        // Ng = e2 x e1 = -(v1-v0) x (v2-v0); Open3D's primitive_normals follow (v1-v0) x (v2-v0)
+        const V3 ng = fcross(v3(tb.z, tb.w, tc.x), v3(ta.w, tb.x, tb.y));
+        float gx = -ng.x, gy = -ng.y, gz = -ng.z;
         float len = sqrtf(gx * gx + gy * gy + gz * gz);
         if (len > 0.f) {
             float sgn = (gx * d.x + gy * d.y + gz * d.z) > 0.f ? -1.0f : 1.0f;  // face the viewer
@@ -911,8 +911,7 @@ __global__ void __launch_bounds__(256) k_pack_texture(const float* __restrict__ 
 }
 
 // per-primitive unit geometric normal for cast_rays' primitive_normals output
-__global__ void __launch_bounds__(256) k_prim_normals(const float4* __restrict__ tris, const uint32_t* __restrict__ prim,
-                                                      int64_t T, const uint32_t* __restrict__ prim_id, int64_t R,
+__global__ void __launch_bounds__(256) k_prim_normals(const float4* __restrict__ tris, int64_t T, const uint32_t* __restrict__ prim_id, int64_t R,
                                                       const uint32_t* __restrict__ slot_of_prim,
                                                       float* __restrict__ out) {
     int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -921,12 +920,13 @@ __global__ void __launch_bounds__(256) k_prim_normals(const float4* __restrict__
     float x = 0.f, y = 0.f, z = 0.f;
     if (id != kInvalidId && id < (uint32_t)T) {
         uint32_t slot = slot_of_prim[id];
-        float4 c = tris[3 * (int64_t)slot + 2];
-        float len = sqrtf(c.y * c.y + c.z * c.z + c.w * c.w);
+        const float4 ta = tris[3 * (int64_t)slot], tb = tris[3 * (int64_t)slot + 1], tc = tris[3 * (int64_t)slot + 2];
+        const V3 ng = fcross(v3(tb.z, tb.w, tc.x), v3(ta.w, tb.x, tb.y));
+        float len = sqrtf(ng.x * ng.x + ng.y * ng.y + ng.z * ng.z);
         if (len > 0.f) {
-            x = c.y / len;
-            y = c.z / len;
-            z = c.w / len;
+            x = ng.x / len;
+            y = ng.y / len;
+            z = ng.z / len;
         }
     }
     out[3 * r + 0] = x;
@@ -958,8 +958,8 @@ int64_t texir_launch_count(void) { return g_launches.load(); }
 int texir_scene_destroy(texir_scene* sc) {
     if (!sc) return 0;
     DeviceGuard guard(sc->info.device);
-    void* ptrs[] = {sc->d_nodes2, sc->d_tris2, sc->d_prim2, sc->d_qnodes2, sc->d_nodes8, sc->d_tris8,
-                    sc->d_prim8,  sc->d_uvs,   sc->d_slot_of_prim, sc->d_tex};
+    void* ptrs[] = {sc->d_nodes2, sc->d_tris2, sc->d_qnodes2, sc->d_nodes8, sc->d_tris8,
+                    sc->d_uvs,    sc->d_slot_of_prim, sc->d_tex};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     delete sc;
@@ -991,9 +991,9 @@ int texir_scene_create(const float* verts_host, int64_t nv, const int32_t* tris_
     std::vector<double> uvs;
     if (tri_uvs_host) uvs.assign(tri_uvs_host, tri_uvs_host + 6 * (size_t)nt);
     if ((rc = upload(bvh.nodes2, &sc->d_nodes2, &bytes)) || (rc = upload(bvh.tris2, &sc->d_tris2, &bytes)) ||
-        (rc = upload(bvh.prim2, &sc->d_prim2, &bytes)) || (rc = upload(bvh.qnodes2, &sc->d_qnodes2, &bytes)) ||
+        (rc = upload(bvh.qnodes2, &sc->d_qnodes2, &bytes)) ||
         (rc = upload(bvh.nodes8, &sc->d_nodes8, &bytes)) ||
-        (rc = upload(bvh.tris8, &sc->d_tris8, &bytes)) || (rc = upload(bvh.prim8, &sc->d_prim8, &bytes)) ||
+        (rc = upload(bvh.tris8, &sc->d_tris8, &bytes)) ||
         (rc = upload(slot_of_prim, &sc->d_slot_of_prim, &bytes)) || (rc = upload(uvs, &sc->d_uvs, &bytes))) {
         std::string keep = g_err;
         texir_scene_destroy(sc);
@@ -1007,7 +1007,6 @@ int texir_scene_create(const float* verts_host, int64_t nv, const int32_t* tris_
     }
     sc->view.nodes2 = (const float4*)sc->d_nodes2;
     sc->view.tris2 = (const float4*)sc->d_tris2;
-    sc->view.prim2 = (const uint32_t*)sc->d_prim2;
     sc->view.qnodes2 = (const uint4*)sc->d_qnodes2;
     for (int a = 0; a < 3; ++a) {
         sc->view.qmin[a] = bvh.qmin[a];
@@ -1015,7 +1014,6 @@ int texir_scene_create(const float* verts_host, int64_t nv, const int32_t* tris_
     }
     sc->view.nodes8 = (const uint4*)sc->d_nodes8;
     sc->view.tris8 = (const float4*)sc->d_tris8;
-    sc->view.prim8 = (const uint32_t*)sc->d_prim8;
     sc->view.tri_uvs = tri_uvs_host ? (const double*)sc->d_uvs : nullptr;
     sc->view.tex = nullptr;
     sc->view.tex_w = sc->view.tex_h = 0;
@@ -1118,7 +1116,7 @@ int texir_cast_rays(const texir_scene* sc, const float* rays, int64_t R, float* 
     if (rc || !prim_normal || R == 0) return rc;
     DeviceGuard guard(sc->info.device);
     k_prim_normals<<<grid_for(R, 256), 256, 0, (cudaStream_t)stream>>>(
-        sc->view.tris2, sc->view.prim2, (int64_t)sc->view.num_tris, prim_id, R, (const uint32_t*)sc->d_slot_of_prim,
+        sc->view.tris2, (int64_t)sc->view.num_tris, prim_id, R, (const uint32_t*)sc->d_slot_of_prim,
         prim_normal);
     return finish_launch("k_prim_normals");
 }

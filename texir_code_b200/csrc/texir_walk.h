@@ -76,7 +76,7 @@ TX_HD int bvh2_step(const SceneView& s, const RayState& r, float tbest, int node
 TX_HD void bvh2_leaf(const SceneView& s, const RayState& r, int node, Hit& hit) {
     const int ref = ~node;
     const int first = ref >> 3, cnt = (ref & 7) + 1;
-    for (int i = 0; i < cnt; ++i) test_slot(s.tris2, s.prim2, first + i, r.o, r.d, hit);
+    for (int i = 0; i < cnt; ++i) test_slot(s.tris2, first + i, r.o, r.d, hit);
 }
 
 TX_HD void hit_reset(Hit& hit) {
@@ -195,7 +195,7 @@ TX_HD Hit trace_qbvh2(const SceneView& s, V3 o, V3 d) {
         if (node < 0) {
             const int ref = ~node;
             const int first = ref >> 3, cnt = (ref & 7) + 1;
-            for (int i = 0; i < cnt; ++i) test_slot(s.tris2, s.prim2, first + i, r.o, r.d, hit);
+            for (int i = 0; i < cnt; ++i) test_slot(s.tris2, first + i, r.o, r.d, hit);
             node = stack[--sp];
         }
     }
