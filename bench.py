@@ -204,7 +204,7 @@ def run_ours(args):
     sc, tex = make_workload()
     t_build = time.perf_counter()
     tracer = models.TracerO3d(sc.vertices, sc.triangles, sc.triangle_uvs, torch.from_numpy(tex), sample_l=[SPP, 64],
-                              device=dev)
+                              device=dev, build_threads=max(1, (os.cpu_count() or 1) // world))
     tracer.scene.set_texture(tracer.texture)
     t_build = time.perf_counter() - t_build
     if args.bvh != 2:

@@ -553,3 +553,49 @@ def test_full_size_material_step(tx, oracle, big, cuda_device):
     assert rel_l2(rgb[sl].detach().cpu().numpy(), ref["rgb"].detach().numpy()) < FWD_TOL
     assert rel_l2(a.grad[sl].cpu().numpy(), ac.grad.numpy()) < GRAD_TOL
     assert rel_l2(r.grad[sl].cpu().numpy(), rc.grad.numpy()) < GRAD_TOL
+
+
+# ---------------------------------------------------------------------------------------------------
+# system level: the optimisation loop of trainer/train_material.py (stage 2) on top of the ops
+# ---------------------------------------------------------------------------------------------------
+def test_material_optimisation_loop_recovers_textures(tx, gscene, cuda_device):
+    """Adam on materials_a / materials_r through G-buffer -> texture fetch -> fused render -> log-L1 loss
+    (models/loss.py:81-99), with the trainer's clamps (train_material.py:458,592-593): the loss must fall."""
+    from texir_code_b200 import synth
+    name, g, _ = gscene
+    if name != "smooth":
+        pytest.skip("the i.i.d.-noise atlas texture makes a 32-spp roughness landscape too rough for a 100-step test")
+    mm = tx.MaterialModel(g["vertices"], g["triangles"], g["triangle_uvs"], torch.from_numpy(g["texture"]),
+                          sample_l=[32, 32], device=cuda_device, materials_a_res=16, materials_r_res=16)
+    rays = synth.cube_map_rays(12, cam=(0.1, 0.0, 0.2))
+    gb = tx.gbuffer(mm.scene, T(rays, cuda_device), offset=1e-2)
+    keep = gb["mask"].reshape(-1) > 0
+    nrm, pos, texc = gb["normal"][keep], gb["position"][keep], gb["texc"][keep]
+    cam = torch.tensor([0.1, 0.0, 0.2], device=cuda_device)
+    irr = torch.full_like(pos, 3.0)
+    rng = np.random.default_rng(0)
+    gt_a = T(rng.uniform(0.2, 0.9, size=(16, 16, 3)).astype(np.float32), cuda_device)
+    gt_r = T(rng.uniform(0.1, 0.6, size=(16, 16, 1)).astype(np.float32), cuda_device)
+    shift = torch.rand(pos.shape[0], 1, 2, generator=torch.Generator().manual_seed(1)).to(cuda_device)
+
+    def render(a_tex, r_tex):
+        a = tx.texture_fetch(a_tex, texc)
+        r = tx.texture_fetch(r_tex, texc)
+        return tx.shade(mm.scene, nrm, a, r, pos, cam, irr, shift, num_spec=32)
+
+    mm.scene.set_texture(mm.texture)
+    with torch.no_grad():
+        target = render(gt_a, gt_r)
+    opt = torch.optim.Adam([mm.materials_a, mm.materials_r], lr=3e-2)
+    losses = []
+    for it in range(100):
+        opt.zero_grad()
+        loss = (torch.log1p(render(mm.materials_a, mm.materials_r)) - torch.log1p(target)).abs().mean()
+        loss.backward()
+        opt.step()
+        with torch.no_grad():
+            mm.materials_r.clamp_(0.01, 0.8)
+            mm.materials_a.clamp_(min=0.0)
+        losses.append(float(loss.detach()))
+    assert losses[-1] < 0.6 * losses[0], (losses[0], losses[-1])
+    assert set(mm.state_dict()) >= {"materials_a", "materials_r"}  # the reference's checkpoint keys

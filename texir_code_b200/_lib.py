@@ -70,10 +70,17 @@ def load() -> ctypes.CDLL:
     """dlopen libtexir_b200.so and type every entry point; raises TexirError if it is not built."""
     global _lib
     if _lib is None:
+        if not os.path.exists(SO_PATH) and "TEXIR_LIB" not in os.environ:
+            try:  # a fresh checkout (the .so is git-ignored): compile it once with nvcc
+                from . import build as _build
+                _build.build_library()
+            except Exception as exc:
+                raise TexirError(
+                    "libtexir_b200.so is not built (%s missing) and building it failed (%s): run "
+                    "`python -m texir_code_b200.build` or __graft_entry__.build(); there is no CPU fallback"
+                    % (SO_PATH, exc))
         if not os.path.exists(SO_PATH):
-            raise TexirError(
-                "libtexir_b200.so is not built (%s missing): run `python -m texir_code_b200.build` or "
-                "__graft_entry__.build(); there is no CPU fallback" % SO_PATH)
+            raise TexirError("libtexir_b200.so not found at %s; there is no CPU fallback" % SO_PATH)
         lib = ctypes.CDLL(SO_PATH)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)  # AttributeError if the library lacks a declared symbol

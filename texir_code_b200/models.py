@@ -142,9 +142,9 @@ class TracerO3d(nn.Module):
     batch = 512
 
     def __init__(self, vertices, triangles, triangle_uvs, texture, sample_l: Sequence[int] = (2048, 64),
-                 sample_type: Sequence[str] = ("uniform", "importance"), device=None):
+                 sample_type: Sequence[str] = ("uniform", "importance"), device=None, build_threads: int = 0):
         super().__init__()
-        self.scene = Scene(vertices, triangles, triangle_uvs, device=device)
+        self.scene = Scene(vertices, triangles, triangle_uvs, device=device, build_threads=build_threads)
         self.triangle_uvs = np.asarray(triangle_uvs)
         self.texture = texture if isinstance(texture, torch.Tensor) else torch.from_numpy(np.asarray(texture))
         self.sample_l = list(sample_l)
