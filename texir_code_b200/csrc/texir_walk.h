@@ -159,6 +159,8 @@ TX_HD float qplane_(uint32_t w, uint32_t sel, float S, float O) {
 
 TX_HD int qbvh2_step(const SceneView& s, const RayQ& r, float tbest, int node, int* stack, int& sp) {
     const uint4* np = s.qnodes2 + 2 * (size_t)node;
+    // two 128-bit loads: sm_100's 256-bit LDG (LDG.E.ENL2.256) was measured 23 % slower here -- it does not
+    // allocate in L1, and the upper tree lives there
     const uint4 q0 = ld_nc_u4(np + 0), q1 = ld_nc_u4(np + 1);
     const uint32_t fx = r.selx ^ 0x0022u, fy = r.sely ^ 0x0022u, fz = r.selz ^ 0x0022u;
     const float t0n = fmaxf(fmaxf(qplane_(q0.x, r.selx, r.S.x, r.O.x), qplane_(q0.y, r.sely, r.S.y, r.O.y)),
