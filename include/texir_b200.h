@@ -178,6 +178,25 @@ TEXIR_API int texir_texture_fetch(const float* tex, int H, int W, int C, const f
 TEXIR_API int texir_texture_scatter(const float* g_out, int H, int W, int C, const float* uv, int64_t P,
                                     float* g_tex, void* stream);
 
+/* ---- IrT post-processing ---------------------------------------------
+ * padding_texture (tools/padding_texture.py:49-80): every empty texel (channel sum == 0) takes the value of
+ * its nearest non-empty texel -- scipy.ndimage.distance_transform_edt(return_indices=True) followed by
+ * F.grid_sample(mode='nearest'), including both of their tie / rounding rules (csrc/texir_post.h).
+ * img, out [H,W,C] f32 (C <= 4, out != img); index [H,W,2] int32 (row, col of the nearest non-empty texel,
+ * scipy's `indices`; may be NULL); scratch [H,W] int32. */
+TEXIR_API int texir_pad_texture(const float* img, int H, int W, int C, float* out, int32_t* index, int32_t* scratch,
+                                void* stream);
+/* Radiance RGBE pixel codec of cv2.imwrite / cv2.imread for .hdr (trainer/generate_ir_texture.py:80-82,
+ * models/mat_nvdiffrast.py:73,89; OpenCV rgbe.cpp float2rgbe / rgbe2float).  img [n,3] f32 in RGB order, or in
+ * cv2's BGR order when bgr != 0; rgbe [n,4] bytes in file order (R, G, B mantissas, exponent). */
+TEXIR_API int texir_rgbe_encode(const float* img, int64_t n, int bgr, uint8_t* rgbe, void* stream);
+TEXIR_API int texir_rgbe_decode(const uint8_t* rgbe, int64_t n, int bgr, float* img, void* stream);
+/* the .hdr container around it, HOST memory and file I/O only (no GPU work): header "#?RADIANCE / FORMAT=32-bit_rle_rgbe /
+ * -Y H +X W" and OpenCV's per-scanline run-length coding; byte-identical to cv2.imwrite for the same pixels. */
+TEXIR_API int texir_hdr_write_host(const char* path, const uint8_t* rgbe_host /*[H,W,4]*/, int H, int W);
+TEXIR_API int texir_hdr_read_info(const char* path, int* H, int* W);
+TEXIR_API int texir_hdr_read_host(const char* path, uint8_t* rgbe_host /*[H,W,4]*/, int H, int W);
+
 #ifdef __cplusplus
 }
 #endif

@@ -305,3 +305,53 @@ def irt_forward(scene, triangle_uvs, texture, position, normal, num_samples: int
         ndl = torch.clamp(torch.sum(nrm.unsqueeze(1) * l.reshape(batch, -1, 3), dim=-1, keepdim=True), 0.0, 1.0)
         out[sl] = torch.sum(rad.reshape(batch, -1, 3).to(ndl.device) * ndl, dim=1) * 2 * np.pi / num_samples
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# IrT post-processing: tools/padding_texture.py:49-80 on arrays, and OpenCV's RGBE pixel codec
+# (cv2.imwrite / cv2.imread of .hdr; trainer/generate_ir_texture.py:80-82, models/mat_nvdiffrast.py:73,89).
+# Pinned by tests/golden/post_*.npz, which oracle/make_golden_post.py wrote by running the reference's own
+# padding_texture() and cv2 (tests/test_oracle.py).
+# ------------------------------------------------------------------------------------------------
+def padding_texture_array(img: np.ndarray):
+    """tools/padding_texture.py:50-77 without the file I/O: img float32 [H,W,3] -> (padded [H,W,3], indices [2,H,W])"""
+    from scipy import ndimage
+    img = np.asarray(img, np.float32)
+    h, w, c = img.shape
+    intensity = img[:, :, 0] + img[:, :, 1] + img[:, :, 2]
+    mask = np.asarray(intensity == 0.0, dtype=np.uint8)
+    _, indices_np = ndimage.distance_transform_edt(mask, return_indices=True)
+    indices = torch.from_numpy(indices_np).permute(1, 2, 0).reshape(-1, 2)
+    img_torch = torch.from_numpy(img).permute(2, 0, 1).unsqueeze(0)
+    uv_init = torch.zeros((h * w, 2), dtype=torch.float32)
+    sel = torch.from_numpy(mask.reshape(-1).astype(bool))   # the reference indexes with the uint8 mask (legacy bool)
+    uv_init[sel] = indices[sel][:, [1, 0]].float() / torch.tensor([w, h]).unsqueeze(0) * 2. - 1.
+    uv_init = uv_init.reshape(h, w, 2).unsqueeze(0)
+    res = F.grid_sample(img_torch, uv_init, mode="nearest", align_corners=False)[0].permute(1, 2, 0).numpy()
+    res = res * np.asarray(mask, np.float32)[:, :, np.newaxis] + img * np.asarray(1 - mask, np.float32)[:, :, np.newaxis]
+    return res, indices_np.astype(np.int32)
+
+
+def float2rgbe(img_bgr: np.ndarray) -> np.ndarray:
+    """OpenCV rgbe.cpp float2rgbe on a BGR float32 image -> bytes [..., 4] in file order (R, G, B, exponent)"""
+    img_bgr = np.asarray(img_bgr, np.float32)
+    r, g, b = img_bgr[..., 2], img_bgr[..., 1], img_bgr[..., 0]
+    v = np.maximum(np.maximum(r, g), b)
+    m, e = np.frexp(v.astype(np.float64))
+    ok = v.astype(np.float64) >= 1e-32
+    with np.errstate(divide="ignore", invalid="ignore"):
+        scale = np.where(ok, m * 256.0 / v.astype(np.float64), 0.0).astype(np.float32)
+    out = np.zeros(img_bgr.shape[:-1] + (4,), np.uint8)
+    for k, ch in enumerate((r, g, b)):
+        out[..., k] = np.where(ok, (ch * scale).astype(np.int32) & 255, 0)
+    out[..., 3] = np.where(ok, e + 128, 0)
+    return out
+
+
+def rgbe2float(rgbe: np.ndarray) -> np.ndarray:
+    """OpenCV rgbe.cpp rgbe2float: bytes [..., 4] -> BGR float32 image (what cv2.imread(path, -1) returns)"""
+    rgbe = np.asarray(rgbe, np.uint8)
+    f = np.ldexp(1.0, rgbe[..., 3].astype(np.int32) - 136).astype(np.float32)
+    out = np.stack([rgbe[..., 2] * f, rgbe[..., 1] * f, rgbe[..., 0] * f], -1).astype(np.float32)
+    out[rgbe[..., 3] == 0] = 0.0
+    return out

@@ -11,7 +11,7 @@ CSRC = os.path.join(ROOT, "texir_code_b200", "csrc")
 SO = os.path.join(HERE, "libtexir_emul.so")
 SOURCES = [os.path.join(HERE, "emul.cpp"), os.path.join(CSRC, "bvh_build.cpp")]
 DEPS = SOURCES + [os.path.join(CSRC, h) for h in ("texir_math.h", "texir_bvh.h", "texir_walk.h", "texir_point.h",
-                                                   "bvh_build.h")]
+                                                   "texir_post.h", "bvh_build.h")]
 
 
 def build(force: bool = False) -> str:
@@ -37,6 +37,9 @@ def load():
     lib.emul_irradiance.argtypes = [vp, i32, vp, vp, vp, i64, i32, i32, vp]
     lib.emul_shade.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, f32, vp, vp, vp]
     lib.emul_cast_rays_fast.argtypes = [vp, i32, vp, i64, vp, vp, vp]
+    lib.emul_pad_texture.argtypes = [vp, i32, i32, i32, vp, vp]
+    lib.emul_rgbe_encode.argtypes = [vp, i64, i32, vp]
+    lib.emul_rgbe_decode.argtypes = [vp, i64, i32, vp]
     return lib
 
 

@@ -9,6 +9,7 @@
 
 #include "../../texir_code_b200/csrc/bvh_build.h"
 #include "../../texir_code_b200/csrc/texir_point.h"
+#include "../../texir_code_b200/csrc/texir_post.h"
 
 using namespace texir;
 
@@ -183,6 +184,49 @@ void emul_shade(EmulScene* s, int kind, const float* nrm, const float* albedo, c
             ediff[3 * p + k] = dfac[k];
         }
     }
+}
+
+// ---- IrT post-processing (texir_post.h): the two passes of k_pad_columns / k_pad_rows, texel by texel ----
+void emul_pad_texture(const float* img, int H, int W, int C, float* out, int32_t* index) {
+    std::vector<int> near((size_t)H * W), g((size_t)W);
+    for (int j = 0; j < W; ++j) {
+        int last = -1;
+        for (int i = 0; i < H; ++i) {
+            if (!pad_texel_empty(img + ((size_t)i * W + j) * C, C)) last = i;
+            near[(size_t)i * W + j] = last;
+        }
+        int next = -1;
+        for (int i = H - 1; i >= 0; --i) {
+            const int up = near[(size_t)i * W + j];
+            if (up == i) next = i;
+            near[(size_t)i * W + j] = pad_pick_row(i, up, next);
+        }
+    }
+    for (int i = 0; i < H; ++i) {
+        const int* nr = near.data() + (size_t)i * W;
+        const int maxl = pad_build_envelope(nr, W, i, g.data());
+        for (int x = 0; x < W; ++x) {
+            int sr = i, sc = x, rr = i, rc = x;
+            if (nr[x] != i && maxl >= 0) {
+                sc = pad_query_envelope(nr, g.data(), maxl, i, x);
+                sr = nr[sc];
+                rr = pad_source_index(sr, H);
+                rc = pad_source_index(sc, W);
+            }
+            for (int c = 0; c < C; ++c)
+                out[((size_t)i * W + x) * C + c] = (rr >= 0 && rc >= 0) ? img[((size_t)rr * W + rc) * C + c] : 0.0f;
+            index[2 * ((size_t)i * W + x) + 0] = sr;
+            index[2 * ((size_t)i * W + x) + 1] = sc;
+        }
+    }
+}
+void emul_rgbe_encode(const float* img, int64_t n, int bgr, unsigned char* rgbe) {
+    for (int64_t i = 0; i < n; ++i)
+        rgbe_from_float(img[3 * i + (bgr ? 2 : 0)], img[3 * i + 1], img[3 * i + (bgr ? 0 : 2)], rgbe + 4 * i);
+}
+void emul_rgbe_decode(const unsigned char* rgbe, int64_t n, int bgr, float* img) {
+    for (int64_t i = 0; i < n; ++i)
+        rgbe_to_float(rgbe + 4 * i, img + 3 * i + (bgr ? 2 : 0), img + 3 * i + 1, img + 3 * i + (bgr ? 0 : 2));
 }
 
 }  // extern "C"

@@ -6,6 +6,7 @@ Public surface (mirrors the reference's names for this path, see DESIGN.md / INT
     Scene, RaycastingScene                      (replaces o3d.t.geometry.RaycastingScene + triangle_uvs + texture)
     ops.query_irf / specular_reflectance / diffuse_reflectance / shade / irradiance / texture_fetch
     models.HotPathMixin / MaterialModel / TracerO3d
+    postprocess.pad_texture / padding_texture / imwrite_hdr / imread_hdr / save_irr_texture   (IrT post-processing)
     parallel.shard_bounds / gather_points / allreduce_gradients / sharded_irradiance
 
 Everything computes in libtexir_b200.so (hand-written CUDA behind the C ABI of include/texir_b200.h);
@@ -28,8 +29,11 @@ def __getattr__(name):  # lazy: importing the package must not require torch.cud
         "point_order": ("ops", "point_order"),
         "HotPathMixin": ("models", "HotPathMixin"), "MaterialModel": ("models", "MaterialModel"),
         "TracerO3d": ("models", "TracerO3d"),
+        "pad_texture": ("postprocess", "pad_texture"), "padding_texture": ("postprocess", "padding_texture"),
+        "imwrite_hdr": ("postprocess", "imwrite_hdr"), "imread_hdr": ("postprocess", "imread_hdr"),
+        "save_irr_texture": ("postprocess", "save_irr_texture"),
     }
-    if name in ("scene", "sample_util", "ops", "models", "parallel", "synth", "build"):
+    if name in ("scene", "sample_util", "ops", "models", "parallel", "synth", "build", "postprocess"):
         return importlib.import_module("." + name, __name__)
     if name in table:
         mod, attr = table[name]
@@ -39,4 +43,5 @@ def __getattr__(name):  # lazy: importing the package must not require torch.cud
 
 __all__ = ["TexirError", "launch_count", "Scene", "RaycastingScene", "generate_dir", "sample_hemisphere", "query_irf",
            "trace", "specular_reflectance", "diffuse_reflectance", "shade", "irradiance", "texture_fetch", "radiance_samples", "gbuffer", "point_order",
-           "HotPathMixin", "MaterialModel", "TracerO3d"]
+           "HotPathMixin", "MaterialModel", "TracerO3d", "pad_texture", "padding_texture", "imwrite_hdr", "imread_hdr",
+           "save_irr_texture"]

@@ -61,6 +61,12 @@ SIGNATURES = {
     "texir_diffuse_reflectance_bwd": (c_int, [_P] * 4 + [c_int64, c_int, c_int] + [_P] * 5),
     "texir_texture_fetch": (c_int, [_P, c_int, c_int, c_int, _P, c_int64, _P, _P]),
     "texir_texture_scatter": (c_int, [_P, c_int, c_int, c_int, _P, c_int64, _P, _P]),
+    "texir_pad_texture": (c_int, [_P, c_int, c_int, c_int, _P, _P, _P, _P]),
+    "texir_rgbe_encode": (c_int, [_P, c_int64, c_int, _P, _P]),
+    "texir_rgbe_decode": (c_int, [_P, c_int64, c_int, _P, _P]),
+    "texir_hdr_write_host": (c_int, [c_char_p, _P, c_int, c_int]),
+    "texir_hdr_read_info": (c_int, [c_char_p, POINTER(c_int), POINTER(c_int)]),
+    "texir_hdr_read_host": (c_int, [c_char_p, _P, c_int, c_int]),
 }
 
 _lib = None

@@ -16,6 +16,7 @@
 
 #include "../../include/texir_b200.h"
 #include "bvh_build.h"
+#include "texir_host.h"
 #include "texir_point.h"
 
 using namespace texir;
@@ -101,6 +102,22 @@ static int finish_launch(const char* what) {
     g_launches.fetch_add(1);
     return 0;
 }
+
+namespace texir_host {  // texir_host.h: the same helpers for the other translation units
+int fail(const std::string& msg, int code) {
+    g_err = msg;
+    return code;
+}
+int finish_launch(const char* what) { return ::finish_launch(what); }
+int device_of(const void* p) { return ::device_of(p); }
+ScopedDevice::ScopedDevice(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev >= 0 && prev != dev) cudaSetDevice(dev);
+}
+ScopedDevice::~ScopedDevice() {
+    if (prev >= 0) cudaSetDevice(prev);
+}
+}  // namespace texir_host
 
 // ------------------------------------------------------------------------------------------------
 // device helpers

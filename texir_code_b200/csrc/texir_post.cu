@@ -1,0 +1,291 @@
+// texir_post.cu -- IrT post-processing on the device: nearest-texel padding of the empty texels of
+// an irradiance texture (tools/padding_texture.py:49-80) and the Radiance RGBE pixel codec behind the
+// reference's cv2.imwrite / cv2.imread of .hdr files (trainer/generate_ir_texture.py:80-82,
+// models/mat_nvdiffrast.py:73,89).  The run-length file format around the codec is host C++ at the end.
+//
+// Padding is an exact Euclidean feature transform in two passes over a [H,W] int32 scratch:
+//   k_pad_columns   one thread per column (coalesced across a warp): nearest non-empty row above / below
+//   k_pad_rows      one CTA per row, the row's sites in shared memory: lower envelope (one thread; W steps of
+//                   integer work, ~0.1 ms for 4096), then every thread binary-searches its texels and copies the
+//                   source texel.  Two launches, a few ms for 4096^2; it runs once per generated texture.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/texir_b200.h"
+#include "texir_host.h"
+#include "texir_post.h"
+
+using namespace texir;
+using texir_host::fail;
+using texir_host::finish_launch;
+
+#define TXP_CUDA(call)                                                                  \
+    do {                                                                                \
+        cudaError_t e_ = (call);                                                        \
+        if (e_ != cudaSuccess) return fail(std::string(#call) + ": " + cudaGetErrorString(e_), 2); \
+    } while (0)
+
+__global__ void __launch_bounds__(128) k_pad_columns(const float* __restrict__ img, int H, int W, int C,
+                                                     int32_t* __restrict__ near_row) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= W) return;
+    int last = -1;
+    for (int i = 0; i < H; ++i) {
+        if (!pad_texel_empty(img + ((int64_t)i * W + j) * C, C)) last = i;
+        near_row[(int64_t)i * W + j] = last;
+    }
+    int next = -1;
+    for (int i = H - 1; i >= 0; --i) {
+        const int up = near_row[(int64_t)i * W + j];
+        if (up == i) next = i;
+        near_row[(int64_t)i * W + j] = pad_pick_row(i, up, next);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_pad_rows(const float* __restrict__ img, int H, int W, int C,
+                                                  const int32_t* __restrict__ near_row, float* __restrict__ out,
+                                                  int32_t* __restrict__ index) {
+    extern __shared__ int sm_pad[];
+    int* nr = sm_pad;      // nearest non-empty row of every column, for this row
+    int* g = sm_pad + W;   // envelope: kept columns
+    __shared__ int s_maxl;
+    const int i = blockIdx.x;
+    for (int x = threadIdx.x; x < W; x += blockDim.x) nr[x] = near_row[(int64_t)i * W + x];
+    __syncthreads();
+    if (threadIdx.x == 0) s_maxl = pad_build_envelope(nr, W, i, g);
+    __syncthreads();
+    const int maxl = s_maxl;
+    for (int x = threadIdx.x; x < W; x += blockDim.x) {
+        int sr = i, sc = x;        // nearest non-empty texel
+        int rr = i, rc = x;        // texel the value is read from
+        if (nr[x] != i && maxl >= 0) {
+            sc = pad_query_envelope(nr, g, maxl, i, x);
+            sr = nr[sc];
+            rr = pad_source_index(sr, H);
+            rc = pad_source_index(sc, W);
+        }
+        const int64_t o = ((int64_t)i * W + x) * C;
+        for (int c = 0; c < C; ++c)
+            out[o + c] = (rr >= 0 && rc >= 0) ? __ldg(img + ((int64_t)rr * W + rc) * C + c) : 0.0f;
+        if (index) {
+            index[2 * ((int64_t)i * W + x) + 0] = sr;
+            index[2 * ((int64_t)i * W + x) + 1] = sc;
+        }
+    }
+}
+
+// pixel codec: img [n,3] float32 in RGB (bgr = 0) or BGR (bgr = 1, cv2's order) <-> rgbe [n,4] bytes (file order)
+__global__ void __launch_bounds__(256) k_rgbe_encode(const float* __restrict__ img, int64_t n, int bgr,
+                                                     uchar4* __restrict__ rgbe) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float a = img[3 * i + 0], b = img[3 * i + 1], c = img[3 * i + 2];
+    unsigned char q[4];
+    rgbe_from_float(bgr ? c : a, b, bgr ? a : c, q);
+    rgbe[i] = make_uchar4(q[0], q[1], q[2], q[3]);
+}
+__global__ void __launch_bounds__(256) k_rgbe_decode(const uchar4* __restrict__ rgbe, int64_t n, int bgr,
+                                                     float* __restrict__ img) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uchar4 v = rgbe[i];
+    const unsigned char q[4] = {v.x, v.y, v.z, v.w};
+    float r, g, b;
+    rgbe_to_float(q, &r, &g, &b);
+    img[3 * i + 0] = bgr ? b : r;
+    img[3 * i + 1] = g;
+    img[3 * i + 2] = bgr ? r : b;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Radiance .hdr container on the host (OpenCV HdrEncoder / HdrDecoder + rgbe.cpp): text header, then per
+// scanline either flat RGBE quadruplets or the "new" run-length form (2, 2, width hi, width lo, then the four
+// byte planes of the scanline, each run-length coded).
+// ------------------------------------------------------------------------------------------------
+static void rle_plane(const unsigned char* data, int numbytes, std::vector<unsigned char>& out) {
+    const int kMinRun = 4;
+    int cur = 0;
+    while (cur < numbytes) {
+        int beg_run = cur, run_count = 0, old_run_count = 0;
+        while (run_count < kMinRun && beg_run < numbytes) {  // next run of at least 4, if any
+            beg_run += run_count;
+            old_run_count = run_count;
+            run_count = 1;
+            while (beg_run + run_count < numbytes && run_count < 127 && data[beg_run] == data[beg_run + run_count])
+                ++run_count;
+        }
+        if (old_run_count > 1 && old_run_count == beg_run - cur) {  // the bytes before it are one short run
+            out.push_back((unsigned char)(128 + old_run_count));
+            out.push_back(data[cur]);
+            cur = beg_run;
+        }
+        while (cur < beg_run) {  // literal bytes up to the run
+            int n = beg_run - cur;
+            if (n > 128) n = 128;
+            out.push_back((unsigned char)n);
+            out.insert(out.end(), data + cur, data + cur + n);
+            cur += n;
+        }
+        if (run_count >= kMinRun) {
+            out.push_back((unsigned char)(128 + run_count));
+            out.push_back(data[beg_run]);
+            cur += run_count;
+        }
+    }
+}
+
+static bool read_line(FILE* fp, std::string& line) {
+    line.clear();
+    int ch;
+    while ((ch = fgetc(fp)) != EOF) {
+        if (ch == '\n') return true;
+        line.push_back((char)ch);
+    }
+    return !line.empty();
+}
+
+static int hdr_open(const char* path, FILE** fp_out, int* H, int* W) {
+    FILE* fp = fopen(path, "rb");
+    if (!fp) return fail(std::string("texir_hdr: cannot open ") + path);
+    std::string line;
+    bool format = false;
+    while (read_line(fp, line)) {  // header lines up to the blank one
+        if (line.empty()) break;
+        if (line.rfind("FORMAT=32-bit_rle_rgbe", 0) == 0) format = true;
+    }
+    int h = 0, w = 0;
+    if (!format || !read_line(fp, line) || sscanf(line.c_str(), "-Y %d +X %d", &h, &w) != 2 || h <= 0 || w <= 0) {
+        fclose(fp);
+        return fail(std::string("texir_hdr: not a '-Y h +X w' 32-bit_rle_rgbe file: ") + path);
+    }
+    *H = h;
+    *W = w;
+    *fp_out = fp;
+    return 0;
+}
+
+extern "C" {
+
+int texir_pad_texture(const float* img, int H, int W, int C, float* out, int32_t* index, int32_t* scratch,
+                      void* stream) {
+    if (H <= 0 || W <= 0 || C <= 0 || C > 4) return fail("texir_pad_texture: bad shape");
+    if (!img || !out || !scratch) return fail("texir_pad_texture: NULL argument");
+    if (img == out) return fail("texir_pad_texture: in-place padding is not supported");
+    const size_t smem = 2 * sizeof(int) * (size_t)W;
+    if (smem > 200 * 1024) return fail("texir_pad_texture: width above 25600 texels");
+    texir_host::ScopedDevice guard(texir_host::device_of(out));
+    if (smem > 48 * 1024)
+        TXP_CUDA(cudaFuncSetAttribute(k_pad_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_pad_columns<<<(W + 127) / 128, 128, 0, (cudaStream_t)stream>>>(img, H, W, C, scratch);
+    if (int rc = finish_launch("k_pad_columns")) return rc;
+    k_pad_rows<<<H, 256, smem, (cudaStream_t)stream>>>(img, H, W, C, scratch, out, index);
+    return finish_launch("k_pad_rows");
+}
+
+int texir_rgbe_encode(const float* img, int64_t n, int bgr, uint8_t* rgbe, void* stream) {
+    if (n < 0) return fail("texir_rgbe_encode: bad size");
+    if (n == 0) return 0;
+    if (!img || !rgbe) return fail("texir_rgbe_encode: NULL argument");
+    texir_host::ScopedDevice guard(texir_host::device_of(rgbe));
+    k_rgbe_encode<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(img, n, bgr, (uchar4*)rgbe);
+    return finish_launch("k_rgbe_encode");
+}
+
+int texir_rgbe_decode(const uint8_t* rgbe, int64_t n, int bgr, float* img, void* stream) {
+    if (n < 0) return fail("texir_rgbe_decode: bad size");
+    if (n == 0) return 0;
+    if (!img || !rgbe) return fail("texir_rgbe_decode: NULL argument");
+    texir_host::ScopedDevice guard(texir_host::device_of(img));
+    k_rgbe_decode<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const uchar4*)rgbe, n, bgr, img);
+    return finish_launch("k_rgbe_decode");
+}
+
+int texir_hdr_write_host(const char* path, const uint8_t* rgbe_host, int H, int W) {
+    if (!path || !rgbe_host || H <= 0 || W <= 0) return fail("texir_hdr_write_host: bad argument");
+    std::vector<unsigned char> out;
+    char head[128];
+    const int hl = snprintf(head, sizeof(head), "#?RADIANCE\nFORMAT=32-bit_rle_rgbe\n\n-Y %d +X %d\n", H, W);
+    out.insert(out.end(), head, head + hl);
+    if (W < 8 || W > 0x7fff) {  // run-length coding is not allowed: flat quadruplets
+        out.insert(out.end(), rgbe_host, rgbe_host + (size_t)H * W * 4);
+    } else {
+        std::vector<unsigned char> plane((size_t)W * 4);
+        for (int y = 0; y < H; ++y) {
+            const uint8_t* row = rgbe_host + (size_t)y * W * 4;
+            const unsigned char mark[4] = {2, 2, (unsigned char)(W >> 8), (unsigned char)(W & 0xFF)};
+            out.insert(out.end(), mark, mark + 4);
+            for (int x = 0; x < W; ++x)
+                for (int c = 0; c < 4; ++c) plane[(size_t)c * W + x] = row[4 * x + c];
+            for (int c = 0; c < 4; ++c) rle_plane(plane.data() + (size_t)c * W, W, out);
+        }
+    }
+    FILE* fp = fopen(path, "wb");
+    if (!fp) return fail(std::string("texir_hdr_write_host: cannot create ") + path);
+    const bool ok = fwrite(out.data(), 1, out.size(), fp) == out.size();
+    if (fclose(fp) != 0 || !ok) return fail(std::string("texir_hdr_write_host: short write to ") + path);
+    return 0;
+}
+
+int texir_hdr_read_info(const char* path, int* H, int* W) {
+    if (!path || !H || !W) return fail("texir_hdr_read_info: NULL argument");
+    FILE* fp = nullptr;
+    if (int rc = hdr_open(path, &fp, H, W)) return rc;
+    fclose(fp);
+    return 0;
+}
+
+int texir_hdr_read_host(const char* path, uint8_t* rgbe_host, int H, int W) {
+    if (!path || !rgbe_host) return fail("texir_hdr_read_host: NULL argument");
+    FILE* fp = nullptr;
+    int h = 0, w = 0;
+    if (int rc = hdr_open(path, &fp, &h, &w)) return rc;
+    struct Closer {
+        FILE* f;
+        ~Closer() { fclose(f); }
+    } closer{fp};
+    if (h != H || w != W) return fail("texir_hdr_read_host: size differs from texir_hdr_read_info");
+    const std::string bad = std::string("texir_hdr_read_host: truncated or malformed pixel data in ") + path;
+    if (W < 8 || W > 0x7fff)
+        return fread(rgbe_host, 4, (size_t)H * W, fp) == (size_t)H * W ? 0 : fail(bad);
+    std::vector<unsigned char> plane((size_t)W * 4);
+    for (int y = 0; y < H; ++y) {
+        uint8_t* row = rgbe_host + (size_t)y * W * 4;
+        unsigned char mark[4];
+        if (fread(mark, 1, 4, fp) != 4) return fail(bad);
+        if (mark[0] != 2 || mark[1] != 2 || (mark[2] & 0x80)) {  // not run-length coded: the rest is flat
+            memcpy(row, mark, 4);
+            const size_t rest = (size_t)(H - y) * W - 1;
+            return fread(row + 4, 4, rest, fp) == rest ? 0 : fail(bad);
+        }
+        if (((int)mark[2] << 8 | mark[3]) != W) return fail(bad);
+        for (int c = 0; c < 4; ++c) {
+            unsigned char* p = plane.data() + (size_t)c * W;
+            int x = 0;
+            while (x < W) {
+                unsigned char b[2];
+                if (fread(b, 1, 2, fp) != 2) return fail(bad);
+                if (b[0] > 128) {  // run
+                    const int n = b[0] - 128;
+                    if (n > W - x) return fail(bad);
+                    memset(p + x, b[1], n);
+                    x += n;
+                } else {  // literal bytes
+                    const int n = b[0];
+                    if (n == 0 || n > W - x) return fail(bad);
+                    p[x++] = b[1];
+                    if (n > 1 && fread(p + x, 1, n - 1, fp) != (size_t)(n - 1)) return fail(bad);
+                    x += n - 1;
+                }
+            }
+        }
+        for (int x = 0; x < W; ++x)
+            for (int c = 0; c < 4; ++c) row[4 * x + c] = plane[(size_t)c * W + x];
+    }
+    return 0;
+}
+
+}  // extern "C"
