@@ -171,7 +171,7 @@ def run_reference(args):
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    print_line(json.dumps(line))
     return 0
 
 
@@ -337,7 +337,7 @@ def run_ours(args):
             line["cpu_baseline"] = cpu
         if mat is not None:
             line["mat_stage"] = mat
-        print(json.dumps(line))
+        print_line(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -399,6 +399,13 @@ def main():
     ap.add_argument("--tex", type=int, default=TEX_RES, help="radiance texture resolution (configs[3]: 8192)")
     args = ap.parse_args()
     globals().update(NUM_TRIS=args.tris, TEX_RES=args.tex)
+    # stdout carries exactly ONE JSON line: anything a library prints on fd 1 meanwhile (NCCL announces its version
+    # there during init) goes to stderr instead
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    real_stdout = os.fdopen(saved, "w")
+    globals()["print_line"] = lambda text: (real_stdout.write(text + "\n"), real_stdout.flush())
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)
