@@ -129,6 +129,13 @@ TEXIR_API int texir_radiance_samples(const texir_scene* scene, const float* pos,
 TEXIR_API int texir_gbuffer(const texir_scene* scene, const float* rays, int64_t R, float* pos, float* nrm, float* uv,
                             uint32_t* prim, float* bary, float* mask, void* stream);
 
+/* screen-space derivatives of the interpolated UVs (the reference's texd = dr.interpolate(..., rast_db,
+ * diff_attrs='all'), models/mat_nvdiffrast.py:128), as a ray differential on the hit triangle's plane.
+ * ddir [R,6] = (d dir/dX, d dir/dY) per pixel, prim [R] from texir_gbuffer -> uv_da [R,4] =
+ * (du/dX, du/dY, dv/dX, dv/dY); uncovered pixels get 0. */
+TEXIR_API int texir_gbuffer_uv_da(const texir_scene* scene, const float* rays, const float* ddir, const uint32_t* prim,
+                                  int64_t R, float* uv_da, void* stream);
+
 /* ---- fused render: MaterialModel.render, models/mat_nvdiffrast.py:201-249 (and the relighting
  *      variant models/test_nvdiffrast.py:256-303 when N_diff > 0).
  * nrm, albedo, pos, irr [P,3]; rough [P]; cam [3]; shift_spec [P,2]; shift_diff [P,2] (N_diff > 0).
@@ -177,6 +184,26 @@ TEXIR_API int texir_texture_fetch(const float* tex, int H, int W, int C, const f
 /* g_out [P,C] scattered with atomics into g_tex [H,W,C] (caller zero-initialises) */
 TEXIR_API int texir_texture_scatter(const float* g_out, int H, int W, int C, const float* uv, int64_t P,
                                     float* g_tex, void* stream);
+
+/* ---- mip-mapped fetch: dr.texture(tex[None], texc, texd, filter_mode='linear-mipmap-linear', max_mip_level=M),
+ *      models/mat_nvdiffrast.py:131-139 (albedo, roughness, irr).  Rules restated in csrc/texir_tex.h.
+ * A pyramid is the caller's level-0 texture [H,W,C] plus `mips`: levels 1..L packed back to back ([h,w,C] each,
+ * h = max(H >> l, 1)).  texir_texture_mip_levels: L for a texture and a max_mip_level cap (< 0: none), -1 when an odd
+ * side would have to be halved (nvdiffrast raises there too).  texir_texture_mip_elems: floats in `mips`. */
+TEXIR_API int texir_texture_mip_levels(int H, int W, int max_mip_level);
+TEXIR_API int64_t texir_texture_mip_elems(int H, int W, int C, int levels);
+/* 2x2 box averages, level by level */
+TEXIR_API int texir_texture_mip_build(const float* tex, int H, int W, int C, int levels, float* mips, void* stream);
+/* uv [P,2] in [0,1] (wrap), uv_da [P,4] = (du/dX, du/dY, dv/dX, dv/dY) per screen pixel -> out [P,C];
+ * lod_out [P] (nullable) receives the fractional level of detail */
+TEXIR_API int texir_texture_fetch_mip(const float* tex, const float* mips, int H, int W, int C, int levels,
+                                      const float* uv, const float* uv_da, int64_t P, float* out, float* lod_out,
+                                      void* stream);
+/* transpose of the fetch: g_out [P,C] scattered with atomics into g_tex / g_mips (caller zero-initialises both) ... */
+TEXIR_API int texir_texture_scatter_mip(const float* g_out, int H, int W, int C, int levels, const float* uv,
+                                        const float* uv_da, int64_t P, float* g_tex, float* g_mips, void* stream);
+/* ... and transpose of the build: g_mips folded down into g_tex, coarsest level first (g_mips is consumed) */
+TEXIR_API int texir_texture_mip_fold(float* g_tex, float* g_mips, int H, int W, int C, int levels, void* stream);
 
 /* ---- IrT post-processing ---------------------------------------------
  * padding_texture (tools/padding_texture.py:49-80): every empty texel (channel sum == 0) takes the value of

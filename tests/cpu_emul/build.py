@@ -11,7 +11,7 @@ CSRC = os.path.join(ROOT, "texir_code_b200", "csrc")
 SO = os.path.join(HERE, "libtexir_emul.so")
 SOURCES = [os.path.join(HERE, "emul.cpp"), os.path.join(CSRC, "bvh_build.cpp")]
 DEPS = SOURCES + [os.path.join(CSRC, h) for h in ("texir_math.h", "texir_bvh.h", "texir_walk.h", "texir_point.h",
-                                                   "texir_post.h", "bvh_build.h")]
+                                                   "texir_post.h", "texir_tex.h", "bvh_build.h")]
 
 
 def build(force: bool = False) -> str:
@@ -40,6 +40,11 @@ def load():
     lib.emul_pad_texture.argtypes = [vp, i32, i32, i32, vp, vp]
     lib.emul_rgbe_encode.argtypes = [vp, i64, i32, vp]
     lib.emul_rgbe_decode.argtypes = [vp, i64, i32, vp]
+    lib.emul_mip_levels.argtypes = [i32, i32, i32]
+    lib.emul_mip_elems.restype = i64
+    lib.emul_mip_elems.argtypes = [i32, i32, i32, i32]
+    lib.emul_mip_build.argtypes = [vp, i32, i32, i32, i32, vp]
+    lib.emul_texture_fetch_mip.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, i64, vp, vp]
     return lib
 
 

@@ -10,6 +10,7 @@
 #include "../../texir_code_b200/csrc/bvh_build.h"
 #include "../../texir_code_b200/csrc/texir_point.h"
 #include "../../texir_code_b200/csrc/texir_post.h"
+#include "../../texir_code_b200/csrc/texir_tex.h"
 
 using namespace texir;
 
@@ -227,6 +228,47 @@ void emul_rgbe_encode(const float* img, int64_t n, int bgr, unsigned char* rgbe)
 void emul_rgbe_decode(const unsigned char* rgbe, int64_t n, int bgr, float* img) {
     for (int64_t i = 0; i < n; ++i)
         rgbe_to_float(rgbe + 4 * i, img + 3 * i + (bgr ? 2 : 0), img + 3 * i + 1, img + 3 * i + (bgr ? 0 : 2));
+}
+
+// ---- mip-mapped material-texture fetch (texir_tex.h), texel arithmetic of k_mip_build_level / k_texture_fetch_mip ----
+int emul_mip_levels(int H, int W, int max_mip_level) { return mip_level_count(H, W, max_mip_level); }
+int64_t emul_mip_elems(int H, int W, int C, int levels) { return mip_offset(H, W, C, levels + 1); }
+void emul_mip_build(const float* tex, int H, int W, int C, int levels, float* mips) {
+    const float* src = tex;
+    for (int l = 1; l <= levels; ++l) {
+        float* dst = mips + mip_offset(H, W, C, l);
+        const int hs = mip_dim(H, l - 1), ws = mip_dim(W, l - 1), hd = mip_dim(H, l), wd = mip_dim(W, l);
+        const int sx = ws > 1 ? 2 : 1, sy = hs > 1 ? 2 : 1;
+        for (int y = 0; y < hd; ++y)
+            for (int x = 0; x < wd; ++x)
+                for (int c = 0; c < C; ++c) {
+                    float acc = 0.f;
+                    for (int dy = 0; dy < sy; ++dy)
+                        for (int dx = 0; dx < sx; ++dx) acc += src[((size_t)(y * sy + dy) * ws + (x * sx + dx)) * C + c];
+                    dst[((size_t)y * wd + x) * C + c] = acc * (1.0f / (float)(sx * sy));
+                }
+        src = dst;
+    }
+}
+void emul_texture_fetch_mip(const float* tex, const float* mips, int H, int W, int C, int L, const float* uv,
+                            const float* uv_da, int64_t P, float* out, float* lod_out) {
+    for (int64_t p = 0; p < P; ++p) {
+        const MipLod m = mip_lod(uv_da[4 * p], uv_da[4 * p + 1], uv_da[4 * p + 2], uv_da[4 * p + 3], H, W, L);
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int k = 0; k < 2; ++k) {
+            const int l = k ? m.level1 : m.level0;
+            const float wl = k ? m.frac : 1.0f - m.frac;
+            if (k && m.frac == 0.f) break;
+            const int h = mip_dim(H, l), w = mip_dim(W, l);
+            const float* t = l ? mips + mip_offset(H, W, C, l) : tex;
+            const TexTap tp = tex_tap(uv[2 * p], uv[2 * p + 1], h, w);
+            for (int c = 0; c < C; ++c)
+                acc[c] += wl * (t[(size_t)tp.i00 * C + c] * tp.w00 + t[(size_t)tp.i10 * C + c] * tp.w10 +
+                                t[(size_t)tp.i01 * C + c] * tp.w01 + t[(size_t)tp.i11 * C + c] * tp.w11);
+        }
+        for (int c = 0; c < C; ++c) out[p * C + c] = acc[c];
+        if (lod_out) lod_out[p] = (float)m.level0 + m.frac;
+    }
 }
 
 }  // extern "C"

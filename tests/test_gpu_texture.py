@@ -1,0 +1,142 @@
+"""GPU (-m gpu): mip-mapped material-texture fetch and its texture-space gradient, and the UV
+derivatives of the G-buffer that drive it, through the package's binding of the C ABI.  Reference: the oracle's torch
+restatement of dr.texture (gradients from torch autograd) and its float64 ray-differential formula.
+Tolerances: forward 1e-5 rel-L2 (fp32 taps and blends), gradients 1e-4 (float atomics in arbitrary order)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def T(x, dev):
+    return torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+
+
+@pytest.fixture(scope="module")
+def tx(cuda_device):
+    import texir_code_b200 as tx
+    tx._lib.load()
+    return tx
+
+
+def _case(H, W, C, P, seed):
+    rng = np.random.default_rng(seed)
+    tex = rng.uniform(0, 1, (H, W, C)).astype(np.float32)
+    uv = rng.uniform(-0.3, 1.3, (P, 2)).astype(np.float32)
+    scale = np.exp(rng.uniform(np.log(0.05), np.log(40.0), (P, 1))) / max(H, W)
+    uv_da = (rng.normal(size=(P, 4)) * scale).astype(np.float32)
+    uv_da[:8] = 0.0
+    g_out = rng.normal(size=(P, C)).astype(np.float32)
+    return tex, uv, uv_da, g_out
+
+
+@pytest.mark.parametrize("shape,max_level", [((64, 64, 3), None), ((32, 128, 1), None), ((256, 256, 3), 13),
+                                             ((64, 64, 3), 2), ((12, 8, 2), 2), ((1, 16, 3), None)])
+def test_mip_fetch_fwd_bwd_vs_oracle(tx, oracle, cuda_device, shape, max_level):
+    tex, uv, uv_da, g_out = _case(*shape, 20000, 3)
+    t = T(tex, cuda_device).requires_grad_(True)
+    out = tx.ops.texture_fetch(t, T(uv, cuda_device), T(uv_da, cuda_device), "linear-mipmap-linear", max_level)
+    (out * T(g_out, cuda_device)).sum().backward()
+    t_ref = torch.from_numpy(tex).requires_grad_(True)
+    ref = oracle.texture_mipmap_linear(t_ref, torch.from_numpy(uv), torch.from_numpy(uv_da), max_level)
+    (ref * torch.from_numpy(g_out)).sum().backward()
+    assert rel_l2(out.detach().cpu().numpy(), ref.detach().numpy()) < 1e-5
+    assert rel_l2(t.grad.cpu().numpy(), t_ref.grad.numpy()) < 1e-4
+    # 'auto' = mip-mapped when derivatives are given, bilinear otherwise (dr.texture's default)
+    auto = tx.ops.texture_fetch(t, T(uv, cuda_device), T(uv_da, cuda_device), max_mip_level=max_level)
+    assert torch.equal(auto, out)
+    lin = tx.ops.texture_fetch(t, T(uv, cuda_device))
+    assert rel_l2(lin.detach().cpu().numpy(), oracle.texture_linear(torch.from_numpy(tex), torch.from_numpy(uv)).numpy()) < 1e-5
+
+
+def test_mip_pyramid_and_fold_are_transposes(tx, oracle, cuda_device):
+    """<build(x), y> == <x, fold(y)>: the gradient fold is the exact transpose of the box-filter pyramid"""
+    rng = np.random.default_rng(5)
+    H, W, C = 64, 32, 3
+    x = rng.normal(size=(H, W, C)).astype(np.float32)
+    mips, L = tx.ops.build_mips(T(x, cuda_device))
+    levels = oracle.mip_pyramid(torch.from_numpy(x))
+    assert L == len(levels) - 1 == 6
+    ref = torch.cat([l.reshape(-1) for l in levels[1:]]).numpy()
+    assert rel_l2(mips.cpu().numpy(), ref) < 1e-6
+    y = rng.normal(size=mips.shape).astype(np.float32)
+    g_tex = torch.zeros(H, W, C, device=cuda_device)
+    g_mips = T(y, cuda_device).clone()
+    lib = tx._lib.load()
+    tx._lib.check(lib.texir_texture_mip_fold(g_tex.data_ptr(), g_mips.data_ptr(), H, W, C, L, None))
+    torch.cuda.synchronize()
+    lhs = float((mips.double().cpu() * torch.from_numpy(y).double()).sum())
+    rhs = float((torch.from_numpy(x).double() * g_tex.double().cpu()).sum())
+    assert abs(lhs - rhs) <= 1e-5 * max(abs(lhs), 1.0)
+
+
+def test_mip_fetch_at_material_texture_sizes(tx, cuda_device):
+    """materials_a 2048^2 x 3 and materials_r 4096^2 x 1 with max_mip_level = get_mip_level(8192) = 13
+    (mat_nvdiffrast.py:65-69): level counts, limits, and gradient mass conservation at full size"""
+    P = 6 * 128 * 128
+    rng = np.random.default_rng(9)
+    uv = T(rng.uniform(0, 1, (P, 2)).astype(np.float32), cuda_device)
+    for res, C, L in ((2048, 3, 11), (4096, 1, 12)):
+        assert tx.ops.mip_levels(res, res, 13) == L
+        tex = torch.rand(res, res, C, device=cuda_device).requires_grad_(True)
+        zero = torch.zeros(P, 4, device=cuda_device)
+        a = tx.ops.texture_fetch(tex, uv, zero, "linear-mipmap-linear", 13)
+        assert torch.allclose(a, tx.ops.texture_fetch(tex, uv), rtol=0, atol=1e-6)      # level 0 == bilinear
+        huge = torch.full((P, 4), 4.0, device=cuda_device)
+        b = tx.ops.texture_fetch(tex, uv, huge, "linear-mipmap-linear", 13)
+        assert torch.allclose(b, tex.detach().reshape(-1, C).mean(0).expand(P, C), rtol=1e-4, atol=1e-5)
+        da = T((rng.normal(size=(P, 4)) * np.exp(rng.uniform(-9, -3, (P, 1)))).astype(np.float32), cuda_device)
+        out = tx.ops.texture_fetch(tex, uv, da, "linear-mipmap-linear", 13)
+        g = torch.rand(P, C, device=cuda_device)
+        (out * g).sum().backward()
+        # every tap's weights sum to 1 on every level and the fold preserves mass
+        assert abs(float(tex.grad.double().sum()) - float(g.double().sum())) < 1e-3 * float(g.double().sum())
+
+
+def test_gbuffer_uv_derivatives(tx, oracle, cuda_device, scene_golden):
+    from texir_code_b200 import synth
+    name, g = scene_golden
+    sc = tx.Scene(g["vertices"], g["triangles"], g["triangle_uvs"], device=cuda_device)
+    res = 32
+    rays = synth.cube_map_rays(res, cam=(0.2, -0.1, 0.3))
+    dd = synth.cube_map_ray_differentials(res)
+    gb = tx.gbuffer(sc, T(rays, cuda_device).reshape(6, res, res, 6), ray_differentials=T(dd, cuda_device))
+    assert gb["texd"].shape == (6, res, res, 4)
+    prim = gb["primitive_ids"].cpu().numpy().reshape(-1).view(np.uint32)
+    ref = oracle.gbuffer_uv_da(g["vertices"], g["triangles"], g["triangle_uvs"], rays, dd, prim)
+    got = gb["texd"].cpu().numpy().reshape(-1, 4)
+    hit = prim != 0xFFFFFFFF
+    assert np.all(got[~hit] == 0)
+    assert rel_l2(got[hit], ref[hit]) < 1e-4
+    # independent check: central differences of the G-buffer's own texc along the ray differentials, on the pixels
+    # whose displaced rays stay on the same triangle
+    h = 0.05
+    for k in range(2):
+        step = dd[:, 3 * k:3 * k + 3] * h
+        plus, minus = rays.copy(), rays.copy()
+        plus[:, 3:] += step
+        minus[:, 3:] -= step
+        gp = tx.gbuffer(sc, T(plus, cuda_device))
+        gm = tx.gbuffer(sc, T(minus, cuda_device))
+        same = hit & (gp["primitive_ids"].cpu().numpy().view(np.uint32) == prim) & \
+            (gm["primitive_ids"].cpu().numpy().view(np.uint32) == prim)
+        assert same.mean() > 0.3
+        fd = (gp["texc"].double() - gm["texc"].double()).cpu().numpy() / (2 * h)
+        an = got[:, [k, 2 + k]]
+        assert rel_l2(an[same], fd[same]) < 5e-3
+
+
+def test_mip_fetch_argument_errors(tx, cuda_device):
+    tex = torch.rand(6, 4, 3, device=cuda_device)
+    uv = torch.rand(10, 2, device=cuda_device)
+    with pytest.raises(ValueError):
+        tx.ops.texture_fetch(tex, uv, torch.zeros(10, 4, device=cuda_device), "linear-mipmap-linear")   # 6 -> 3 -> odd
+    with pytest.raises(ValueError):
+        tx.ops.texture_fetch(tex, uv, None, "linear-mipmap-linear")
+    with pytest.raises(ValueError):
+        tx.ops.texture_fetch(tex, uv, None, "nearest")
+    out = tx.ops.texture_fetch(tex, uv, torch.zeros(10, 4, device=cuda_device), "linear-mipmap-linear", 1)
+    assert out.shape == (10, 3)

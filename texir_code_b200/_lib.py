@@ -53,6 +53,7 @@ SIGNATURES = {
     "texir_point_order": (c_int, [_P, _P, c_int64, _P, _P]),
     "texir_radiance_samples": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int, _P, _P, _P]),
     "texir_gbuffer": (c_int, [_P, _P, c_int64, _P, _P, _P, _P, _P, _P, _P]),
+    "texir_gbuffer_uv_da": (c_int, [_P, _P, _P, _P, c_int64, _P, _P]),
     "texir_shade_fwd": (c_int, [_P] + [_P] * 8 + [c_int64, c_int, c_int, c_int, c_int, c_float, _P, _P, _P, _P]),
     "texir_shade_bwd": (c_int, [_P] + [_P] * 8 + [c_int64, c_int, c_int, c_int, c_int, c_float] + [_P] * 7),
     "texir_specular_reflectance": (c_int, [_P] * 6 + [c_int64, c_int, c_float, _P, _P]),
@@ -61,6 +62,12 @@ SIGNATURES = {
     "texir_diffuse_reflectance_bwd": (c_int, [_P] * 4 + [c_int64, c_int, c_int] + [_P] * 5),
     "texir_texture_fetch": (c_int, [_P, c_int, c_int, c_int, _P, c_int64, _P, _P]),
     "texir_texture_scatter": (c_int, [_P, c_int, c_int, c_int, _P, c_int64, _P, _P]),
+    "texir_texture_mip_levels": (c_int, [c_int, c_int, c_int]),
+    "texir_texture_mip_elems": (c_int64, [c_int, c_int, c_int, c_int]),
+    "texir_texture_mip_build": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P]),
+    "texir_texture_fetch_mip": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P, c_int64, _P, _P, _P]),
+    "texir_texture_scatter_mip": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, c_int64, _P, _P, _P]),
+    "texir_texture_mip_fold": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P]),
     "texir_pad_texture": (c_int, [_P, c_int, c_int, c_int, _P, _P, _P, _P]),
     "texir_rgbe_encode": (c_int, [_P, c_int64, c_int, _P, _P]),
     "texir_rgbe_decode": (c_int, [_P, c_int64, c_int, _P, _P]),

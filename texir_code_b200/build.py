@@ -13,8 +13,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libtexir_b200.so")
-SOURCES = [os.path.join(CSRC, "texir_kernels.cu"), os.path.join(CSRC, "texir_post.cu"), os.path.join(CSRC, "bvh_build.cpp")]
-HEADERS = [os.path.join(CSRC, h) for h in ("texir_math.h", "texir_bvh.h", "texir_walk.h", "texir_point.h", "texir_post.h", "texir_host.h", "bvh_build.h")] + [
+SOURCES = [os.path.join(CSRC, "texir_kernels.cu"), os.path.join(CSRC, "texir_post.cu"), os.path.join(CSRC, "texir_texture.cu"), os.path.join(CSRC, "bvh_build.cpp")]
+HEADERS = [os.path.join(CSRC, h) for h in ("texir_math.h", "texir_bvh.h", "texir_walk.h", "texir_point.h", "texir_post.h", "texir_tex.h", "texir_host.h", "bvh_build.h")] + [
     os.path.join(os.path.dirname(HERE), "include", "texir_b200.h")]
 
 NVCC_FLAGS = [

@@ -18,6 +18,7 @@
 #include "bvh_build.h"
 #include "texir_host.h"
 #include "texir_point.h"
+#include "texir_tex.h"
 
 using namespace texir;
 
@@ -311,6 +312,49 @@ __global__ void __launch_bounds__(128) k_gbuffer(SceneView s, const float* __res
     if (prim) prim[r] = h.prim;
     if (bary) { bary[2 * r + 0] = h.u; bary[2 * r + 1] = h.v; }
     if (mask) mask[r] = hit ? 1.0f : 0.0f;
+}
+
+// screen-space UV derivatives of a G-buffer (dr.interpolate(..., rast_db, diff_attrs='all') -> texd,
+// models/mat_nvdiffrast.py:128): the exact derivative of the perspective-correct interpolation, written as a ray
+// differential on the plane of the hit triangle.  ddir [R,6] = (d dir/dX, d dir/dY) per pixel, for the SAME
+// (un-normalised or normalised) parametrisation of `rays`.  Uncovered pixels get 0.
+__global__ void __launch_bounds__(128) k_gbuffer_uv_da(SceneView s, const float* __restrict__ rays,
+                                                       const float* __restrict__ ddir,
+                                                       const uint32_t* __restrict__ prim, int64_t R,
+                                                       const uint32_t* __restrict__ slot_of_prim,
+                                                       float* __restrict__ uv_da) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
+    const uint32_t id = __ldg(prim + r);
+    if (id != kInvalidId && id < s.num_tris) {
+        const V3 o = v3(__ldg(rays + 6 * r + 0), __ldg(rays + 6 * r + 1), __ldg(rays + 6 * r + 2));
+        const V3 d = v3(__ldg(rays + 6 * r + 3), __ldg(rays + 6 * r + 4), __ldg(rays + 6 * r + 5));
+        const float4* tp = s.tris2 + 3 * (size_t)__ldg(slot_of_prim + id);
+        const float4 ta = __ldg(tp), tb = __ldg(tp + 1), tc = __ldg(tp + 2);
+        const V3 v0 = v3(ta.x, ta.y, ta.z);
+        const V3 E1 = v3(-ta.w, -tb.x, -tb.y), E2 = v3(tb.z, tb.w, tc.x);  // v1 - v0, v2 - v0
+        const V3 n = fcross(E1, E2);
+        const float nd = dot3(n, d), nn = dot3(n, n);
+        if (nd != 0.f && nn > 0.f) {
+            const float t = dot3(n, v3(v0.x - o.x, v0.y - o.y, v0.z - o.z)) / nd;
+            const double* tuv = s.tri_uvs + 6 * (size_t)id;
+            const float du1 = (float)(tuv[2] - tuv[0]), dv1 = (float)(tuv[3] - tuv[1]);
+            const float du2 = (float)(tuv[4] - tuv[0]), dv2 = (float)(tuv[5] - tuv[1]);
+            float res[4];
+            for (int k = 0; k < 2; ++k) {
+                const V3 dd = v3(__ldg(ddir + 6 * r + 3 * k + 0), __ldg(ddir + 6 * r + 3 * k + 1),
+                                 __ldg(ddir + 6 * r + 3 * k + 2));
+                const float dt = -t * dot3(n, dd) / nd;
+                const V3 dx = v3(dt * d.x + t * dd.x, dt * d.y + t * dd.y, dt * d.z + t * dd.z);
+                const float db1 = dot3(fcross(dx, E2), n) / nn, db2 = dot3(fcross(E1, dx), n) / nn;
+                res[k] = db1 * du1 + db2 * du2;      // du/dX, du/dY
+                res[2 + k] = db1 * dv1 + db2 * dv2;  // dv/dX, dv/dY
+            }
+            out = make_float4(res[0], res[1], res[2], res[3]);
+        }
+    }
+    reinterpret_cast<float4*>(uv_da)[r] = out;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -856,32 +900,6 @@ __global__ void __launch_bounds__(128)
 // ------------------------------------------------------------------------------------------------
 // bilinear material-texture fetch and gradient scatter (nvdiffrast 'linear' filter, wrap boundary)
 // ------------------------------------------------------------------------------------------------
-struct TexTap {
-    int i00, i10, i01, i11;
-    float w00, w10, w01, w11;
-};
-__device__ __forceinline__ TexTap tex_tap(float u, float v, int H, int W) {
-    // nvdiffrast: texel centres at (i + 0.5) / size; uv scaled by size, minus 0.5, wrap addressing
-    float x = u * (float)W - 0.5f, y = v * (float)H - 0.5f;
-    float fx = floorf(x), fy = floorf(y);
-    float ax = x - fx, ay = y - fy;
-    int x0 = (int)fx, y0 = (int)fy;
-    int x1 = x0 + 1, y1 = y0 + 1;
-    x0 = ((x0 % W) + W) % W;
-    x1 = ((x1 % W) + W) % W;
-    y0 = ((y0 % H) + H) % H;
-    y1 = ((y1 % H) + H) % H;
-    TexTap t;
-    t.i00 = y0 * W + x0;
-    t.i10 = y0 * W + x1;
-    t.i01 = y1 * W + x0;
-    t.i11 = y1 * W + x1;
-    t.w00 = (1.f - ax) * (1.f - ay);
-    t.w10 = ax * (1.f - ay);
-    t.w01 = (1.f - ax) * ay;
-    t.w11 = ax * ay;
-    return t;
-}
 __global__ void __launch_bounds__(256) k_texture_fetch(const float* __restrict__ tex, int H, int W, int C,
                                                        const float* __restrict__ uv, int64_t P,
                                                        float* __restrict__ out) {
@@ -1312,6 +1330,19 @@ int texir_gbuffer(const texir_scene* sc, const float* rays, int64_t R, float* po
     k_gbuffer<4><<<grid_for(R, 128), 128, 0, (cudaStream_t)stream>>>(sc->view, rays, R, (const uint32_t*)sc->d_slot_of_prim,
                                                                       pos, nrm, uv, prim, bary, mask);
     return finish_launch("k_gbuffer");
+}
+
+int texir_gbuffer_uv_da(const texir_scene* sc, const float* rays, const float* ddir, const uint32_t* prim, int64_t R,
+                        float* uv_da, void* stream) {
+    if (!sc) TX_FAIL("texir_gbuffer_uv_da: NULL scene");
+    if (R < 0) TX_FAIL("texir_gbuffer_uv_da: negative ray count");
+    if (R == 0) return 0;
+    if (!rays || !ddir || !prim || !uv_da) TX_FAIL("texir_gbuffer_uv_da: NULL argument");
+    if (!sc->view.tri_uvs) TX_FAIL("texir_gbuffer_uv_da: the scene has no triangle uvs");
+    DeviceGuard guard(sc->info.device);
+    k_gbuffer_uv_da<<<grid_for(R, 128), 128, 0, (cudaStream_t)stream>>>(sc->view, rays, ddir, prim, R,
+                                                                       (const uint32_t*)sc->d_slot_of_prim, uv_da);
+    return finish_launch("k_gbuffer_uv_da");
 }
 
 int texir_irradiance_fwd(const texir_scene* sc, const float* pos, const float* nrm, const float* shift,

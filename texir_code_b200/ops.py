@@ -296,11 +296,13 @@ def radiance_samples(scene: Scene, position: torch.Tensor, normal: torch.Tensor,
     return (rad, dirs) if return_dirs else rad
 
 
-def gbuffer(scene: Scene, rays: torch.Tensor, offset: float = 0.0) -> dict:
-    """G-buffer from primary rays [...,6] (replaces dr.rasterize + dr.interpolate, mat_nvdiffrast.py:119-126):
+def gbuffer(scene: Scene, rays: torch.Tensor, offset: float = 0.0,
+            ray_differentials: Optional[torch.Tensor] = None) -> dict:
+    """G-buffer from primary rays [...,6] (replaces dr.rasterize + dr.interpolate, mat_nvdiffrast.py:119-128):
     dict(position, normal [...,3], texc [...,2] when the scene has UVs, primitive_ids, primitive_uvs, mask).
     position = hit + offset * normal (the reference shifts by 1e-2, :179); uncovered pixels get position =
-    normal = (1,0,0)."""
+    normal = (1,0,0).  With ray_differentials [...,6] = (d dir/dX, d dir/dY) per pixel also texd [...,4] =
+    (du/dX, du/dY, dv/dX, dv/dY), the uv_da that the mip-mapped texture_fetch takes."""
     _need_cuda("gbuffer", rays)
     dev = rays.device
     r = _f32c(rays).reshape(-1, 6)
@@ -322,11 +324,20 @@ def gbuffer(scene: Scene, rays: torch.Tensor, offset: float = 0.0) -> dict:
            "mask": mask.reshape(shape + (1,))}
     if uv is not None:
         out["texc"] = uv.reshape(shape + (2,))
+    if ray_differentials is not None:
+        dd = _f32c(ray_differentials, dev).reshape(-1, 6)
+        if dd.shape[0] != R:
+            raise ValueError("ray_differentials must have one (d dir/dX, d dir/dY) row per ray")
+        texd = torch.empty(R, 4, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().texir_gbuffer_uv_da(scene.handle, _ptr(r), _ptr(dd), _ptr(prim), R, _ptr(texd),
+                                                       _stream_ptr(dev)), "texir_gbuffer_uv_da")
+        out["texd"] = texd.reshape(shape + (4,))
     return out
 
 
 # --------------------------------------------------------------------------------------------------
-# material-texture fetch / gradient scatter (dr.texture 'linear', models/mat_nvdiffrast.py:131-139)
+# material-texture fetch / gradient scatter (dr.texture, models/mat_nvdiffrast.py:131-139)
 # --------------------------------------------------------------------------------------------------
 class _TextureFetch(torch.autograd.Function):
     @staticmethod
@@ -356,7 +367,77 @@ class _TextureFetch(torch.autograd.Function):
         return g_tex, None
 
 
-def texture_fetch(tex: torch.Tensor, uv: torch.Tensor) -> torch.Tensor:
-    """bilinear fetch of a [H,W,C] material texture at uv [P,2]; backward scatters with atomics"""
+def mip_levels(H: int, W: int, max_mip_level: Optional[int] = None) -> int:
+    """mip levels above level 0 that dr.texture builds for a [H,W] texture under a max_mip_level cap"""
+    L = int(_lib.load().texir_texture_mip_levels(int(H), int(W), -1 if max_mip_level is None else int(max_mip_level)))
+    if L < 0:
+        raise ValueError("a %dx%d texture has an odd side that would have to be halved; lower max_mip_level" % (H, W))
+    return L
+
+
+def build_mips(tex: torch.Tensor, max_mip_level: Optional[int] = None):
+    """-> (packed levels 1..L as one float32 tensor, L); level l is [max(H>>l,1), max(W>>l,1), C]"""
+    _need_cuda("build_mips", tex)
+    H, W, C = (int(x) for x in tex.shape)
+    L = mip_levels(H, W, max_mip_level)
+    lib = _lib.load()
+    t = _f32c(tex)
+    mips = torch.empty(max(int(lib.texir_texture_mip_elems(H, W, C, L)), 1), dtype=torch.float32, device=tex.device)
+    with torch.cuda.device(tex.device):
+        _lib.check(lib.texir_texture_mip_build(_ptr(t), H, W, C, L, _ptr(mips), _stream_ptr(tex.device)),
+                   "texir_texture_mip_build")
+    return mips, L
+
+
+class _TextureFetchMip(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, tex, uv, uv_da, max_mip_level):
+        dev = tex.device
+        H, W, C = (int(x) for x in tex.shape)
+        P = int(uv.shape[0])
+        t, u, d = _f32c(tex), _f32c(uv), _f32c(uv_da)
+        mips, L = build_mips(t, max_mip_level)
+        out = torch.empty(P, C, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().texir_texture_fetch_mip(_ptr(t), _ptr(mips), H, W, C, L, _ptr(u), _ptr(d), P,
+                                                           _ptr(out), None, _stream_ptr(dev)),
+                       "texir_texture_fetch_mip")
+        ctx.save_for_backward(u, d)
+        ctx.shape = (H, W, C, L, mips.numel())
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        u, d = ctx.saved_tensors
+        dev = u.device
+        H, W, C, L, n_mips = ctx.shape
+        g = _f32c(g_out)
+        g_tex = torch.zeros(H, W, C, dtype=torch.float32, device=dev)
+        g_mips = torch.zeros(n_mips, dtype=torch.float32, device=dev)
+        lib = _lib.load()
+        with torch.cuda.device(dev):
+            _lib.check(lib.texir_texture_scatter_mip(_ptr(g), H, W, C, L, _ptr(u), _ptr(d), int(u.shape[0]),
+                                                     _ptr(g_tex), _ptr(g_mips), _stream_ptr(dev)),
+                       "texir_texture_scatter_mip")
+            _lib.check(lib.texir_texture_mip_fold(_ptr(g_tex), _ptr(g_mips), H, W, C, L, _stream_ptr(dev)),
+                       "texir_texture_mip_fold")
+        return g_tex, None, None, None
+
+
+def texture_fetch(tex: torch.Tensor, uv: torch.Tensor, uv_da: Optional[torch.Tensor] = None,
+                  filter_mode: str = "auto", max_mip_level: Optional[int] = None) -> torch.Tensor:
+    """dr.texture(tex[None], uv, uv_da, filter_mode=..., max_mip_level=...) for a [H,W,C] texture, uv [P,2] and
+    uv_da [P,4] = (du/dX, du/dY, dv/dX, dv/dY): 'linear' (bilinear) or 'linear-mipmap-linear' (trilinear over the
+    box-filtered pyramid); 'auto' picks the latter when uv_da is given, as nvdiffrast does.  The backward scatters
+    into the texture (and its pyramid, folded back to level 0) with atomics; uv is not differentiated (the
+    reference's uvs are constants, mat_nvdiffrast.py:56)."""
     _need_cuda("texture_fetch", tex)
-    return _TextureFetch.apply(tex, uv)
+    if filter_mode == "auto":
+        filter_mode = "linear" if uv_da is None else "linear-mipmap-linear"
+    if filter_mode == "linear":
+        return _TextureFetch.apply(tex, uv)
+    if filter_mode != "linear-mipmap-linear":
+        raise ValueError("filter_mode must be 'linear' or 'linear-mipmap-linear', got %r" % (filter_mode,))
+    if uv_da is None:
+        raise ValueError("'linear-mipmap-linear' needs uv_da (the reference always passes texd)")
+    return _TextureFetchMip.apply(tex, uv, uv_da, max_mip_level)

@@ -271,6 +271,31 @@ def cube_map_rays(res: int, cam=(0.0, 0.0, 0.0)) -> np.ndarray:
     return np.ascontiguousarray(np.concatenate([o, d], axis=1), dtype=np.float32)
 
 
+def cube_map_ray_differentials(res: int) -> np.ndarray:
+    """[6*res*res, 6] = (d dir/dX, d dir/dY) of cube_map_rays' normalised directions per pixel step (X = column,
+    Y = row): what texir_gbuffer_uv_da turns into the texd of dr.interpolate(..., diff_attrs='all')"""
+    lin = (np.arange(res) + 0.5) / res * 2.0 - 1.0
+    a, b = np.meshgrid(lin, lin)
+    one, zero = np.ones_like(a), np.zeros_like(a)
+    step = 2.0 / res
+    dirs = [np.stack([one, -b, -a], -1), np.stack([-one, -b, a], -1), np.stack([a, one, b], -1),
+            np.stack([a, -one, -b], -1), np.stack([a, -b, one], -1), np.stack([-a, -b, -one], -1)]
+    # derivatives of the un-normalised directions with respect to a (columns) and b (rows)
+    d_da = [(0, 0, -1), (0, 0, 1), (1, 0, 0), (1, 0, 0), (1, 0, 0), (-1, 0, 0)]
+    d_db = [(0, -1, 0), (0, -1, 0), (0, 0, 1), (0, 0, -1), (0, -1, 0), (0, -1, 0)]
+    out = []
+    for face in range(6):
+        d = dirs[face].reshape(-1, 3)
+        ln = np.linalg.norm(d, axis=1, keepdims=True)
+        dh = d / ln
+        cols = []
+        for dv in (d_da[face], d_db[face]):
+            g = np.broadcast_to(np.asarray(dv, np.float64) * step, d.shape)
+            cols.append((g - dh * np.sum(dh * g, axis=1, keepdims=True)) / ln)
+        out.append(np.concatenate(cols, axis=1))
+    return np.ascontiguousarray(np.concatenate(out), dtype=np.float32)
+
+
 def gbuffer_from_hits(scene: SynthScene, rays: np.ndarray, t_hit: np.ndarray, prim_ids: np.ndarray):
     """pos = hit + 1e-2 n, geometric normal; uncovered pixels get pos = n = (1,0,0)
     (mat_nvdiffrast.py:125, :179)"""
