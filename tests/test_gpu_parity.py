@@ -408,8 +408,8 @@ def test_material_textures_receive_scattered_gradients(tx, gscene, oracle, cuda_
     P = len(g["pos"])
     texc = rng.uniform(0.05, 0.95, size=(P, 2)).astype(np.float32)
     torch.manual_seed(666)
-    out = mm(T(g["nrm"], cuda_device), T(g["pos"], cuda_device), T(g["cam"], cuda_device), T(g["irr"], cuda_device),
-             texc=T(texc, cuda_device))
+    out = mm.forward_gbuffer(T(g["nrm"], cuda_device), T(g["pos"], cuda_device), T(g["cam"], cuda_device),
+                             T(g["irr"], cuda_device), texc=T(texc, cuda_device))
     (out["rgb"] * T(g["g_rgb"], cuda_device)).sum().backward()
     # torch / oracle chain on the CPU
     ta = mm.materials_a.detach().cpu().clone().requires_grad_(True)

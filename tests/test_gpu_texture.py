@@ -140,3 +140,68 @@ def test_mip_fetch_argument_errors(tx, cuda_device):
         tx.ops.texture_fetch(tex, uv, None, "nearest")
     out = tx.ops.texture_fetch(tex, uv, torch.zeros(10, 4, device=cuda_device), "linear-mipmap-linear", 1)
     assert out.shape == (10, 3)
+
+
+def test_material_model_forward_reference_signature(tx, oracle, cuda_device, scene_golden):
+    """MaterialModel.forward(mvp, id, cam_position, stage) as in mat_nvdiffrast.py:105-191: primary rays from the
+    reference's own cube-face mvps -> G-buffer -> mip-mapped fetches -> fused render.  Checked: the G-buffer ids
+    against the brute-force oracle, the result keys / shapes, which textures receive gradients per stage, the
+    stage -1 texture swap, and stage 2 against the same chain assembled op by op on the oracle (CPU, torch autograd)."""
+    from test_host_logic import _reference_cube_mvps
+    name, g = scene_golden
+    res = 8
+    c2w = np.eye(4, dtype=np.float32)
+    c2w[:3, 3] = [0.2, -0.1, 0.3]
+    mvp, cam = _reference_cube_mvps(c2w)
+    rng = np.random.default_rng(3)
+    irrt = rng.uniform(0.5, 3.0, (32, 32, 3)).astype(np.float32)
+    mm = tx.MaterialModel(g["vertices"], g["triangles"], g["triangle_uvs"], torch.from_numpy(g["texture"]),
+                          sample_l=[16, 16], device=cuda_device, materials_a_res=32, materials_r_res=64, cube_res=res,
+                          irrt=irrt, max_mip_level=13, hdr_exposure=5.0)
+    with torch.no_grad():
+        mm.materials_a.copy_(T(rng.uniform(0.1, 0.9, (32, 32, 3)).astype(np.float32), cuda_device))
+        mm.materials_r.copy_(T(rng.uniform(0.05, 0.7, (64, 64, 1)).astype(np.float32), cuda_device))
+    gb = mm.gbuffers(mvp, cam)
+    rays, dd = tx.models.rays_from_mvp(mvp, cam, res)
+    t0, i0, u0 = oracle.OracleScene(g["vertices"], g["triangles"], brute=True).cast_rays_np(rays.reshape(-1, 6).numpy())
+    assert np.array_equal(gb["primitive_ids"].cpu().numpy().reshape(-1).view(np.uint32), i0)
+    keys = {"rgb", "albedo", "normal", "position", "empty_mask", "roughness_womipmap", "roughness"}
+    grads = {}
+    for stage in (-1, 0, 1, 2):
+        mm.zero_grad()
+        tex_before = mm.texture
+        torch.manual_seed(666)
+        out = mm(mvp.to(cuda_device), 0, cam, stage)
+        assert mm.texture is tex_before                                     # stage -1 swaps and restores
+        assert set(out) == keys
+        assert out["rgb"].shape == (6, res, res, 3) and out["empty_mask"].shape == (6, res, res, 1)
+        assert out["roughness"].shape == (6, res, res, 1) and bool(torch.isfinite(out["rgb"]).all())
+        if stage >= 0:
+            out["rgb"].sum().backward()
+        grads[stage] = (mm.materials_a.grad is not None and bool((mm.materials_a.grad != 0).any()),
+                        mm.materials_r.grad is not None and bool((mm.materials_r.grad != 0).any()))
+    assert grads[0] == (True, False)       # lambertian initialisation: albedo only
+    assert grads[1] == (False, True)       # albedo detached, un-mip-mapped roughness
+    assert grads[2] == (True, True)
+    # stage 2 on the oracle: same G-buffer, torch restatement of dr.texture, reference render restatement
+    P = 6 * res * res
+    texc, texd = gb["texc"].reshape(P, 2).cpu(), gb["texd"].reshape(P, 4).cpu()
+    ta = mm.materials_a.detach().cpu().clone().requires_grad_(True)
+    tr = mm.materials_r.detach().cpu().clone().requires_grad_(True)
+    a = oracle.texture_mipmap_linear(ta, texc, texd, 13)
+    r = oracle.texture_mipmap_linear(tr, texc, texd, 13)
+    irr = oracle.texture_mipmap_linear(torch.from_numpy(irrt), texc, texd, 13)
+    nrm, pos = gb["normal"].reshape(P, 3).cpu(), gb["position"].reshape(P, 3).cpu()
+    torch.manual_seed(666)
+    shift = torch.rand(P, 1, 2)
+    ref = oracle.render(oracle.OracleScene(g["vertices"], g["triangles"]), g["triangle_uvs"], torch.from_numpy(g["texture"]),
+                        [16, 16], ["uniform", "importance"], nrm, a, r, pos + 1e-2 * nrm, cam, irr, shift_spec=shift)
+    g_rgb = torch.from_numpy(rng.normal(size=(P, 3)).astype(np.float32))
+    (ref["rgb"] * g_rgb).sum().backward()
+    mm.zero_grad()
+    torch.manual_seed(666)
+    out = mm(mvp.to(cuda_device), 0, cam, 2)
+    (out["rgb"].reshape(P, 3) * g_rgb.to(cuda_device)).sum().backward()
+    assert rel_l2(out["rgb"].detach().cpu().numpy().reshape(P, 3), ref["rgb"].detach().numpy()) < 1e-4
+    assert rel_l2(mm.materials_a.grad.cpu().numpy(), ta.grad.numpy()) < 1e-3
+    assert rel_l2(mm.materials_r.grad.cpu().numpy(), tr.grad.numpy()) < 1e-3

@@ -109,3 +109,55 @@ def test_single_process_parallel_helpers_are_noops():
     p = torch.nn.Parameter(torch.zeros(2))
     p.grad = torch.ones(2)
     assert allreduce_gradients([p]) == 0
+
+
+def _reference_cube_mvps(c2w: np.ndarray):
+    """datasets/dataset.py:419-463: six world-to-camera matrices from one extrinsic, times projection(), transposed"""
+    import torch
+    ext = torch.from_numpy(c2w).float()
+    faces = []
+    f0 = ext.clone(); R, F = f0[0:3, 0].clone(), f0[0:3, 2].clone(); f0[0:3, 2] = -R; f0[0:3, 0] = F; faces.append(torch.inverse(f0))
+    faces.append(torch.inverse(ext))
+    f2 = ext.clone(); R, F = f2[0:3, 0].clone(), f2[0:3, 2].clone(); f2[0:3, 2] = R; f2[0:3, 0] = -F; faces.append(torch.inverse(f2))
+    f3 = ext.clone(); R, F = f3[0:3, 0].clone(), f3[0:3, 2].clone(); f3[0:3, 2] = -F; f3[0:3, 0] = -R; faces.append(torch.inverse(f3))
+    f4 = ext.clone(); F, R = f4[0:3, 2].clone(), f4[0:3, 0].clone(); U = torch.linalg.cross(R, F); f4[0:3, 2] = U; f4[0:3, 1] = F; faces.append(torch.inverse(f4))
+    f5 = ext.clone(); F, R = f5[0:3, 2].clone(), f5[0:3, 0].clone(); U = torch.linalg.cross(R, F); f5[0:3, 2] = -U; f5[0:3, 1] = -F; faces.append(torch.inverse(f5))
+    w2c = torch.stack(faces)
+    n, f = 1e-4, 100.0
+    proj = torch.tensor([[1.0, 0, 0, 0], [0, 1.0, 0, 0], [0, 0, (f + n) / (f - n), -(2 * f * n) / (f - n)], [0, 0, 1, 0]])
+    mvp = torch.einsum("ijk,ikl->ijl", proj.expand(6, 4, 4), w2c)
+    return torch.transpose(mvp, 1, 2).float(), ext[0:3, -1].clone()
+
+
+def test_rays_from_mvp_invert_the_reference_cameras():
+    """every ray of rays_from_mvp projects back to its own pixel centre through the reference's mvp, the six faces
+    cover the sphere, and the differentials match central differences between neighbouring pixels"""
+    import torch
+    from texir_code_b200.models import rays_from_mvp
+    rng = np.random.default_rng(4)
+    q, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+    if np.linalg.det(q) < 0:
+        q[:, 0] = -q[:, 0]
+    c2w = np.eye(4, dtype=np.float32)
+    c2w[:3, :3] = q
+    c2w[:3, 3] = [0.4, -0.3, 1.1]
+    mvp, cam = _reference_cube_mvps(c2w)
+    res = 16
+    rays, dd = rays_from_mvp(mvp, cam, res)
+    assert rays.shape == (6, res, res, 6) and dd.shape == (6, res, res, 6)
+    assert torch.allclose(rays[..., :3], cam.expand(6, res, res, 3))
+    assert torch.allclose(torch.linalg.norm(rays[..., 3:], dim=-1), torch.ones(6, res, res), atol=1e-6)
+    pts = torch.cat([rays[..., :3].double() + 3.0 * rays[..., 3:].double(), torch.ones(6, res, res, 1, dtype=torch.float64)], -1)
+    clip = torch.einsum("vhwk,vkl->vhwl", pts, mvp.double())
+    ndc = clip[..., :2] / clip[..., 3:4]
+    lin = (torch.arange(res, dtype=torch.float64) + 0.5) / res * 2 - 1
+    assert torch.allclose(ndc[..., 0], lin.view(1, 1, res).expand(6, res, res), atol=1e-4)   # X = column
+    assert torch.allclose(ndc[..., 1], lin.view(1, res, 1).expand(6, res, res), atol=1e-4)   # Y = row, row 0 at -1
+    assert bool((clip[..., 3] > 0).all())                                                    # in front of the camera
+    d = rays[..., 3:].double()
+    assert torch.linalg.norm(d.reshape(-1, 3).mean(0)) < 1e-6                                # faces tile the sphere
+    fdx = (d[:, :, 2:] - d[:, :, :-2]) / 2
+    fdy = (d[:, 2:] - d[:, :-2]) / 2
+    scale = float(dd.abs().max())
+    assert float((fdx - dd[:, :, 1:-1, :3]).abs().max()) < 0.02 * scale
+    assert float((fdy - dd[:, 1:-1, :, 3:]).abs().max()) < 0.02 * scale

@@ -99,14 +99,49 @@ class HotPathMixin:
     shade = render
 
 
+def rays_from_mvp(mvp: torch.Tensor, cam_position: torch.Tensor, res: int):
+    """Primary rays of the views the reference rasterises (models/mat_nvdiffrast.py:116-119: clip = [v,1] @ mvp[i],
+    dr.rasterize at res x res), one per pixel centre, row 0 at ndc y = -1 as in nvdiffrast's images.
+    mvp [V,4,4] (datasets/dataset.py:461-463: transpose(proj @ w2c)), cam_position [3]  ->
+    rays [V,res,res,6] (origin, unit direction) and ray differentials [V,res,res,6] = (d dir/dX, d dir/dY) per
+    pixel step (X = column, Y = row).  Host-side set-up of V small matrices in float64; no hot-path work."""
+    dev = mvp.device
+    inv = torch.linalg.inv(mvp.detach().double())                      # world_h = clip_h @ inv
+    cam = cam_position.detach().double().to(dev)
+    lin = (torch.arange(res, dtype=torch.float64, device=dev) + 0.5) / res * 2.0 - 1.0
+    y, x = torch.meshgrid(lin, lin, indexing="ij")
+    clip = torch.stack([x, y, torch.ones_like(x), torch.ones_like(x)], -1)            # far plane, w = 1
+    wh = torch.einsum("hwk,vkl->vhwl", clip, inv)
+    H3, w = wh[..., :3], wh[..., 3:4]
+    d = H3 / w - cam
+    ln = torch.linalg.norm(d, dim=-1, keepdim=True)
+    dh = d / ln
+    cols = []
+    for axis in (0, 1):                                                # d/d(ndc x), d/d(ndc y)
+        row = inv[:, axis, :].reshape(-1, 1, 1, 4)
+        dP = (row[..., :3] * w - H3 * row[..., 3:4]) / (w * w) * (2.0 / res)
+        cols.append((dP - dh * (dh * dP).sum(-1, keepdim=True)) / ln)
+    rays = torch.cat([cam.expand_as(dh), dh], -1).float().contiguous()
+    return rays, torch.cat(cols, -1).float().contiguous()
+
+
+def rgb_to_intensity(t: torch.Tensor, dim: int = -1) -> torch.Tensor:
+    """utils/general.py:95-111 (dim = -1 and dim = 1 are the forms the hot path uses)"""
+    sl = lambda k: t.narrow(dim if dim >= 0 else t.dim() - 1, k, 1)
+    return 0.29900 * sl(0) + 0.58700 * sl(1) + 0.11400 * sl(2)
+
+
 class MaterialModel(HotPathMixin, nn.Module):
-    """Hot-path state of models.mat_nvdiffrast.MaterialModel (and, with relighting=True / brdf_eps=1e-6,
-    of models.test_nvdiffrast.MaterialModel), built from arrays."""
+    """models.mat_nvdiffrast.MaterialModel (and, with relighting=True / brdf_eps=1e-6, the hot path of
+    models.test_nvdiffrast.MaterialModel), built from arrays.  ``forward(mvp, id, cam_position, stage)`` is the
+    reference's (mat_nvdiffrast.py:105-191) with the OpenGL rasteriser and dr.interpolate replaced by primary rays
+    through the scene BVH (ops.gbuffer) and dr.texture by ops.texture_fetch."""
 
     def __init__(self, vertices, triangles, triangle_uvs, texture, sample_l: Sequence[int] = (32, 64),
                  sample_type: Sequence[str] = ("uniform", "importance"), relighting: bool = False,
                  brdf_eps: float = 1e-14, device=None, materials_a_res: int = 0, materials_r_res: int = 0,
-                 fused: bool = True, backward_mode: str = "stash"):
+                 fused: bool = True, backward_mode: str = "stash", cube_res: int = 128, irrt=None,
+                 max_mip_level: Optional[int] = 13, hdr_exposure: float = 5.0, vertex_normals=None):
         super().__init__()
         self.scene = Scene(vertices, triangles, triangle_uvs, device=device)
         self.triangle_uvs = np.asarray(triangle_uvs)
@@ -117,21 +152,84 @@ class MaterialModel(HotPathMixin, nn.Module):
         self.brdf_eps = brdf_eps
         self.fused = fused
         self.backward_mode = backward_mode
+        self.cube_res = int(cube_res)
+        self.max_mip_level = max_mip_level      # get_mip_level(8192) = 13, mat_nvdiffrast.py:65
+        self.hdr_exposure = float(hdr_exposure)
         dev = self.scene.device
         # trainable material textures, same names / initial values as mat_nvdiffrast.py:68-69
         if materials_a_res > 0:
             self.materials_a = nn.Parameter(torch.full((materials_a_res, materials_a_res, 3), 0.5, device=dev))
         if materials_r_res > 0:
             self.materials_r = nn.Parameter(torch.full((materials_r_res, materials_r_res, 1), 0.1, device=dev))
+        if irrt is not None:                    # the padded / denoised IrT, mat_nvdiffrast.py:72-76
+            self.irrt = nn.Parameter(torch.as_tensor(irrt, dtype=torch.float32).to(dev), requires_grad=False)
+        if vertex_normals is not None:          # the reference interpolates the OBJ's vertex normals (:120)
+            self.normals = nn.Parameter(torch.as_tensor(vertex_normals, dtype=torch.float32).to(dev), requires_grad=False)
+            self.triangles = nn.Parameter(torch.as_tensor(np.asarray(triangles), dtype=torch.int64).to(dev),
+                                          requires_grad=False)
 
-    def forward(self, normal, points, cam_position, irr, albedo=None, roughness=None, texc=None):
-        """G-buffer in, shaded colour out.  Materials come either as per-pixel tensors or, given texc [P,2],
-        from the trainable textures through the bilinear fetch whose backward scatters into them."""
+    def forward_gbuffer(self, normal, points, cam_position, irr, albedo=None, roughness=None, texc=None, texd=None):
+        """G-buffer in, shaded colour out.  Materials come either as per-pixel tensors or, given texc [P,2] (and texd
+        [P,4] for the mip-mapped filter), from the trainable textures through the fetch whose backward scatters
+        into them."""
         if texc is not None:
             flat = texc.reshape(-1, 2)
-            albedo = ops.texture_fetch(self.materials_a, flat).reshape(*normal.shape[:-1], 3)
-            roughness = ops.texture_fetch(self.materials_r, flat).reshape(*normal.shape[:-1], 1)
+            da = texd.reshape(-1, 4) if texd is not None else None
+            albedo = ops.texture_fetch(self.materials_a, flat, da, max_mip_level=self.max_mip_level)
+            roughness = ops.texture_fetch(self.materials_r, flat, da, max_mip_level=self.max_mip_level)
+            albedo = albedo.reshape(*normal.shape[:-1], 3)
+            roughness = roughness.reshape(*normal.shape[:-1], 1)
         return self.render(normal, albedo, roughness, points, cam_position, irr)
+
+    def gbuffers(self, mvp: torch.Tensor, cam_position: torch.Tensor) -> dict:
+        """mat_nvdiffrast.py:116-128: position / normal / texc / texd / mask of the 6 cube faces"""
+        dev = self.scene.device
+        rays, ddir = rays_from_mvp(mvp.to(dev), cam_position.to(dev), self.cube_res)
+        gb = ops.gbuffer(self._scene(), rays, ray_differentials=ddir)
+        if hasattr(self, "normals"):
+            tri = self.triangles[gb["primitive_ids"].long().clamp_(min=0) % self.triangles.shape[0]]
+            b = gb["primitive_uvs"]
+            n = (self.normals[tri[..., 0]] * (1 - b[..., 0:1] - b[..., 1:2]) + self.normals[tri[..., 1]] * b[..., 0:1]
+                 + self.normals[tri[..., 2]] * b[..., 1:2])
+            fixed = torch.tensor([1.0, 0.0, 0.0], device=dev)
+            gb["normal"] = torch.where(gb["mask"] > 0, n, fixed)
+        return gb
+
+    def forward(self, mvp, id, cam_position, stage=1):
+        """mat_nvdiffrast.py:105-191, same arguments and result keys (rgb, albedo, normal, position, empty_mask,
+        roughness_womipmap, roughness); stage -1 / 0 / 1 / 2 as in the reference."""
+        dev = self.scene.device
+        cam_position = cam_position.to(dev)
+        gb = self.gbuffers(mvp, cam_position)
+        normal, pos, mask = gb["normal"].detach(), gb["position"].detach(), gb["mask"]
+        shp = normal.shape[:-1]
+        texc, texd = gb["texc"].reshape(-1, 2), gb["texd"].reshape(-1, 4)
+        mip = dict(filter_mode="linear-mipmap-linear", max_mip_level=self.max_mip_level)
+        albedo = ops.texture_fetch(self.materials_a, texc, texd, **mip).reshape(*shp, 3)
+        roughness_womipmap = ops.texture_fetch(self.materials_r, texc, None, "linear").reshape(*shp, 1)
+        roughness = ops.texture_fetch(self.materials_r, texc, texd, **mip).reshape(*shp, 1)
+        irr = ops.texture_fetch(self.irrt, texc, texd, **mip).reshape(*shp, 3)
+        if stage == -1:
+            # "a simple trick to locate the light source": only texels brighter than 0.5 (before exposure) emit
+            source = self.texture
+            t = source.to(dev) if isinstance(source, torch.Tensor) else torch.as_tensor(source).to(dev)
+            intensity = rgb_to_intensity(t * (2 ** -self.hdr_exposure), dim=1)
+            self.texture = torch.where(intensity >= 0.5, t, torch.zeros_like(t))
+            try:
+                res = self.render(normal, torch.zeros_like(albedo), torch.ones_like(roughness) * 0.01, pos + 1e-2 * normal,
+                                  cam_position, irr)
+            finally:
+                self.texture = source
+        elif stage == 0:
+            res = {"rgb": irr * albedo / np.pi, "albedo": albedo, "normal": normal, "position": pos + 1e-1 * normal}
+        elif stage == 1:
+            res = self.render(normal, albedo.detach(), roughness_womipmap, pos + 1e-2 * normal, cam_position, irr)
+        elif stage == 2:
+            res = self.render(normal, albedo, roughness, pos + 1e-2 * normal, cam_position, irr)
+        else:
+            raise ValueError("stage must be -1, 0, 1 or 2")
+        res.update({"empty_mask": mask, "roughness_womipmap": roughness_womipmap, "roughness": roughness})
+        return res
 
 
 class TracerO3d(nn.Module):
