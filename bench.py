@@ -292,7 +292,7 @@ def run_ours(args):
     # ---- material stage (C3 shape: 98 304 pixels, 256 spp importance, forward + backward) ----------
     mat = None
     if rank == 0 and not args.no_mat:
-        mat = bench_material_stage(tracer.scene, sc, dev, args)
+        mat = bench_material_stage(tracer.scene, sc, dev, args, tracer.texture)
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) ------------------------------------------------
     cpu = None
@@ -343,7 +343,7 @@ def run_ours(args):
     return 0
 
 
-def bench_material_stage(scene, sc, dev, args):
+def bench_material_stage(scene, sc, dev, args, texture):
     """BASELINE configs[2] shape: 6x128^2 cube-map pixels, 256 importance samples, forward + backward"""
     import numpy as np
     import torch
@@ -382,6 +382,60 @@ def bench_material_stage(scene, sc, dev, args):
         ms = e0.elapsed_time(e1) / reps
         out["fwd_bwd_%s_ms" % mode] = ms
         out["fwd_bwd_%s_ray_samples_per_s" % mode] = P * N / (ms * 1e-3)
+
+    def timed(fn, reps=5):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / reps
+
+    # BASELINE configs[4] shape (relighting, forward only): 3072 uniform Monte-Carlo diffuse + 1024 importance
+    # specular samples per pixel = 4096 spp; and the reference's own default 1024 + 256 (test_relighting.conf)
+    sh2 = torch.rand(P, 1, 2).to(dev)
+    a0, r0 = t(albedo), t(rough)
+    for tag, nd, ns in (("relight_3072_1024", 3072, 1024), ("relight_1024_256", 1024, 256)):
+        ms = timed(lambda: ops.shade(scene, nrm_d, a0, r0, pos_d, cam, None, sh, num_spec=ns, shift_diff=sh2,
+                                     num_diff=nd, mode_diff="uniform", eps=1e-6), reps=3)
+        out[tag + "_ms"] = ms
+        out[tag + "_ray_samples_per_s"] = P * (nd + ns) / (ms * 1e-3)
+
+    # one whole optimisation step of the Mat stage through the reference-signature call (stage 2): primary rays from
+    # the cube-face mvps -> G-buffer + UV derivatives -> mip-mapped fetches of materials_a (2048^2 x 3), materials_r
+    # (4096^2 x 1) and the IrT (1024^2 x 3) -> fused render (256 spp) -> backward into the two textures
+    from texir_code_b200 import models
+    n_, f_ = 1e-4, 100.0
+    proj = torch.tensor([[1.0, 0, 0, 0], [0, 1.0, 0, 0], [0, 0, (f_ + n_) / (f_ - n_), -(2 * f_ * n_) / (f_ - n_)],
+                         [0, 0, 1.0, 0]])
+    faces = []
+    for fwd, up in (((1, 0, 0), (0, 1, 0)), ((-1, 0, 0), (0, 1, 0)), ((0, 1, 0), (0, 0, -1)), ((0, -1, 0), (0, 0, 1)),
+                    ((0, 0, 1), (0, 1, 0)), ((0, 0, -1), (0, 1, 0))):
+        fz, uy = torch.tensor(fwd, dtype=torch.float32), torch.tensor(up, dtype=torch.float32)
+        rx = torch.linalg.cross(uy, fz)
+        w2c = torch.eye(4)
+        w2c[:3, :3] = torch.stack([rx, uy, fz])          # camera at the origin looking along fwd
+        faces.append((proj @ w2c).t())
+    mvp = torch.stack(faces).to(dev)
+    mm = models.MaterialModel(None, None, sc.triangle_uvs, texture, sample_l=[32, 256], scene=scene,
+                              materials_a_res=2048, materials_r_res=4096, cube_res=128,
+                              irrt=torch.rand(1024, 1024, 3) * 3.0, max_mip_level=13)
+
+    def train_step():
+        mm.zero_grad(set_to_none=True)
+        res = mm(mvp, 0, cam, 2)
+        res["rgb"].backward(g_d.reshape(res["rgb"].shape))
+
+    ms = timed(train_step)
+    out["train_step_stage2_ms"] = ms
+    out["train_step_stage2_ray_samples_per_s"] = P * 256 / (ms * 1e-3)
+    out["train_step_stage2_what"] = ("MaterialModel.forward(mvp, id, cam, stage=2) + backward: G-buffer of 6x128^2 primary "
+                                     "rays, 4 texture fetches (3 mip-mapped: 2048^2x3, 4096^2x1, 1024^2x3), fused render "
+                                     "256 spp, gradient scatter + pyramid fold into materials_a / materials_r")
     return out
 
 

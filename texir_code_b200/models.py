@@ -141,9 +141,11 @@ class MaterialModel(HotPathMixin, nn.Module):
                  sample_type: Sequence[str] = ("uniform", "importance"), relighting: bool = False,
                  brdf_eps: float = 1e-14, device=None, materials_a_res: int = 0, materials_r_res: int = 0,
                  fused: bool = True, backward_mode: str = "stash", cube_res: int = 128, irrt=None,
-                 max_mip_level: Optional[int] = 13, hdr_exposure: float = 5.0, vertex_normals=None):
+                 max_mip_level: Optional[int] = 13, hdr_exposure: float = 5.0, vertex_normals=None,
+                 scene: Optional[Scene] = None):
         super().__init__()
-        self.scene = Scene(vertices, triangles, triangle_uvs, device=device)
+        # `scene`: share an already built Scene (BVH + uploads) instead of building another one from the arrays
+        self.scene = scene if scene is not None else Scene(vertices, triangles, triangle_uvs, device=device)
         self.triangle_uvs = np.asarray(triangle_uvs)
         self.texture = texture if isinstance(texture, torch.Tensor) else torch.from_numpy(np.asarray(texture))
         self.sample_l = list(sample_l)
