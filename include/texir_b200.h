@@ -129,6 +129,14 @@ TEXIR_API int texir_radiance_samples(const texir_scene* scene, const float* pos,
 TEXIR_API int texir_gbuffer(const texir_scene* scene, const float* rays, int64_t R, float* pos, float* nrm, float* uv,
                             uint32_t* prim, float* bary, float* mask, void* stream);
 
+/* The same G-buffer straight from the reference's camera matrices, ONE launch for all views (replaces
+ * `clip = vertices @ mvp; dr.rasterize; dr.interpolate x2`, models/mat_nvdiffrast.py:116-128): mvp [V,4,4] in the
+ * reference's row-vector convention (clip = [v,1] @ mvp[i]; datasets/dataset.py:461-463), cam [3], res x res pixels
+ * per view, pixel row 0 at ndc y = -1.  Outputs as texir_gbuffer, [V*res*res, .], plus uv_da [.,4] = the reference's
+ * texd (du/dX, du/dY, dv/dX, dv/dY) and rays_out [.,6] (origin, unit direction); each nullable. */
+TEXIR_API int texir_gbuffer_mvp(const texir_scene* scene, const float* mvp, const float* cam, int V, int res, float* pos,
+                                float* nrm, float* uv, float* uv_da, uint32_t* prim, float* bary, float* mask,
+                                float* rays_out, void* stream);
 /* screen-space derivatives of the interpolated UVs (the reference's texd = dr.interpolate(..., rast_db,
  * diff_attrs='all'), models/mat_nvdiffrast.py:128), as a ray differential on the hit triangle's plane.
  * ddir [R,6] = (d dir/dX, d dir/dY) per pixel, prim [R] from texir_gbuffer -> uv_da [R,4] =

@@ -205,3 +205,35 @@ def test_material_model_forward_reference_signature(tx, oracle, cuda_device, sce
     assert rel_l2(out["rgb"].detach().cpu().numpy().reshape(P, 3), ref["rgb"].detach().numpy()) < 1e-4
     assert rel_l2(mm.materials_a.grad.cpu().numpy(), ta.grad.numpy()) < 1e-3
     assert rel_l2(mm.materials_r.grad.cpu().numpy(), tr.grad.numpy()) < 1e-3
+
+
+def test_gbuffer_mvp_one_launch_equals_rays_plus_gbuffer(tx, cuda_device, scene_golden):
+    """ops.gbuffer_mvp (camera matrices -> rays -> BVH -> G-buffer + texd in one kernel) against the two-step path
+    rays_from_mvp (torch, float64) -> ops.gbuffer(..., ray_differentials)"""
+    from test_host_logic import _reference_cube_mvps
+    name, g = scene_golden
+    sc = tx.Scene(g["vertices"], g["triangles"], g["triangle_uvs"], device=cuda_device)
+    rng = np.random.default_rng(8)
+    q, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+    if np.linalg.det(q) < 0:
+        q[:, 0] = -q[:, 0]
+    c2w = np.eye(4, dtype=np.float32)
+    c2w[:3, :3] = q
+    c2w[:3, 3] = [0.3, 0.1, -0.4]
+    mvp, cam = _reference_cube_mvps(c2w)
+    res = 24
+    n0 = tx.launch_count()
+    a = tx.gbuffer_mvp(sc, mvp.to(cuda_device), cam.to(cuda_device), res, return_rays=True)
+    assert tx.launch_count() - n0 == 1
+    rays, dd = tx.models.rays_from_mvp(mvp, cam, res)
+    assert float((a["rays"].cpu() - rays).abs().max()) < 2e-7
+    b = tx.gbuffer(sc, a["rays"], ray_differentials=dd.to(cuda_device))      # same rays: everything but texd is identical
+    for k in ("position", "normal", "texc", "primitive_ids", "primitive_uvs", "mask"):
+        assert torch.equal(a[k], b[k]), k
+    hit = a["mask"].reshape(-1) > 0
+    assert float(hit.float().mean()) > 0.9
+    assert rel_l2(a["texd"].reshape(-1, 4)[hit].cpu().numpy(), b["texd"].reshape(-1, 4)[hit].cpu().numpy()) < 1e-5
+    assert bool((a["texd"].reshape(-1, 4)[~hit] == 0).all())
+    bad = torch.zeros(1, 4, 4, device=cuda_device)                            # singular mvp: no hits, no NaNs
+    z = tx.gbuffer_mvp(sc, bad, cam.to(cuda_device), 4)
+    assert bool((z["mask"] == 0).all()) and bool(torch.isfinite(z["position"]).all())

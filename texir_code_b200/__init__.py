@@ -26,7 +26,7 @@ def __getattr__(name):  # lazy: importing the package must not require torch.cud
         "diffuse_reflectance": ("ops", "diffuse_reflectance"),
         "shade": ("ops", "shade"), "irradiance": ("ops", "irradiance"), "texture_fetch": ("ops", "texture_fetch"),
         "radiance_samples": ("ops", "radiance_samples"), "gbuffer": ("ops", "gbuffer"),
-        "point_order": ("ops", "point_order"),
+        "point_order": ("ops", "point_order"), "gbuffer_mvp": ("ops", "gbuffer_mvp"),
         "HotPathMixin": ("models", "HotPathMixin"), "MaterialModel": ("models", "MaterialModel"),
         "TracerO3d": ("models", "TracerO3d"),
         "pad_texture": ("postprocess", "pad_texture"), "padding_texture": ("postprocess", "padding_texture"),
@@ -42,6 +42,6 @@ def __getattr__(name):  # lazy: importing the package must not require torch.cud
 
 
 __all__ = ["TexirError", "launch_count", "Scene", "RaycastingScene", "generate_dir", "sample_hemisphere", "query_irf",
-           "trace", "specular_reflectance", "diffuse_reflectance", "shade", "irradiance", "texture_fetch", "radiance_samples", "gbuffer", "point_order",
+           "trace", "specular_reflectance", "diffuse_reflectance", "shade", "irradiance", "texture_fetch", "radiance_samples", "gbuffer", "gbuffer_mvp", "point_order",
            "HotPathMixin", "MaterialModel", "TracerO3d", "pad_texture", "padding_texture", "imwrite_hdr", "imread_hdr",
            "save_irr_texture"]

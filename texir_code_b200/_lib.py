@@ -53,6 +53,7 @@ SIGNATURES = {
     "texir_point_order": (c_int, [_P, _P, c_int64, _P, _P]),
     "texir_radiance_samples": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int, _P, _P, _P]),
     "texir_gbuffer": (c_int, [_P, _P, c_int64, _P, _P, _P, _P, _P, _P, _P]),
+    "texir_gbuffer_mvp": (c_int, [_P, _P, _P, c_int, c_int] + [_P] * 9),
     "texir_gbuffer_uv_da": (c_int, [_P, _P, _P, _P, c_int64, _P, _P]),
     "texir_shade_fwd": (c_int, [_P] + [_P] * 8 + [c_int64, c_int, c_int, c_int, c_int, c_float, _P, _P, _P, _P]),
     "texir_shade_bwd": (c_int, [_P] + [_P] * 8 + [c_int64, c_int, c_int, c_int, c_int, c_float] + [_P] * 7),

@@ -273,16 +273,20 @@ __global__ void __launch_bounds__(128) k_radiance_samples(SceneView s, const flo
     }
 }
 
+struct GBufferOut {
+    float* pos;
+    float* nrm;
+    float* uv;
+    uint32_t* prim;
+    float* bary;
+    float* mask;
+    float* uv_da;  // only written by the kernels that know the ray differentials
+};
+
+// one G-buffer pixel from its primary ray: hit point, geometric normal turned against the ray, interpolated UVs
 template <int KIND>
-__global__ void __launch_bounds__(128) k_gbuffer(SceneView s, const float* __restrict__ rays, int64_t R,
-                                                 const uint32_t* __restrict__ slot_of_prim, float* __restrict__ pos,
-                                                 float* __restrict__ nrm, float* __restrict__ uv,
-                                                 uint32_t* __restrict__ prim, float* __restrict__ bary,
-                                                 float* __restrict__ mask) {
-    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= R) return;
-    V3 o = v3(__ldg(rays + 6 * r + 0), __ldg(rays + 6 * r + 1), __ldg(rays + 6 * r + 2));
-    V3 d = v3(__ldg(rays + 6 * r + 3), __ldg(rays + 6 * r + 4), __ldg(rays + 6 * r + 5));
+__device__ __forceinline__ Hit gbuffer_pixel(const SceneView& s, const uint32_t* __restrict__ slot_of_prim, V3 o, V3 d,
+                                             int64_t r, const GBufferOut& g) {
     Hit h = trace<KIND>(s, o, d);
     const bool hit = h.prim != kInvalidId;
     V3 x = v3(1.f, 0.f, 0.f), n = v3(1.f, 0.f, 0.f);
@@ -306,18 +310,56 @@ __global__ void __launch_bounds__(128) k_gbuffer(SceneView s, const float* __res
             interp_uv(tuv, h.u, h.v, &tu, &tv);
         }
     }
-    if (pos) { pos[3 * r + 0] = x.x; pos[3 * r + 1] = x.y; pos[3 * r + 2] = x.z; }
-    if (nrm) { nrm[3 * r + 0] = n.x; nrm[3 * r + 1] = n.y; nrm[3 * r + 2] = n.z; }
-    if (uv) { uv[2 * r + 0] = tu; uv[2 * r + 1] = tv; }
-    if (prim) prim[r] = h.prim;
-    if (bary) { bary[2 * r + 0] = h.u; bary[2 * r + 1] = h.v; }
-    if (mask) mask[r] = hit ? 1.0f : 0.0f;
+    if (g.pos) { g.pos[3 * r + 0] = x.x; g.pos[3 * r + 1] = x.y; g.pos[3 * r + 2] = x.z; }
+    if (g.nrm) { g.nrm[3 * r + 0] = n.x; g.nrm[3 * r + 1] = n.y; g.nrm[3 * r + 2] = n.z; }
+    if (g.uv) { g.uv[2 * r + 0] = tu; g.uv[2 * r + 1] = tv; }
+    if (g.prim) g.prim[r] = h.prim;
+    if (g.bary) { g.bary[2 * r + 0] = h.u; g.bary[2 * r + 1] = h.v; }
+    if (g.mask) g.mask[r] = hit ? 1.0f : 0.0f;
+    return h;
 }
 
-// screen-space UV derivatives of a G-buffer (dr.interpolate(..., rast_db, diff_attrs='all') -> texd,
+// screen-space UV derivatives of a G-buffer pixel (dr.interpolate(..., rast_db, diff_attrs='all') -> texd,
 // models/mat_nvdiffrast.py:128): the exact derivative of the perspective-correct interpolation, written as a ray
-// differential on the plane of the hit triangle.  ddir [R,6] = (d dir/dX, d dir/dY) per pixel, for the SAME
-// (un-normalised or normalised) parametrisation of `rays`.  Uncovered pixels get 0.
+// differential on the plane of the hit triangle.  ddx, ddy = d dir/dX, d dir/dY for the SAME parametrisation of the
+// ray direction d.  Uncovered pixels get 0.
+__device__ __forceinline__ float4 gbuffer_uv_da(const SceneView& s, const uint32_t* __restrict__ slot_of_prim, V3 o, V3 d,
+                                                V3 ddx, V3 ddy, uint32_t id) {
+    float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (id == kInvalidId || id >= s.num_tris) return out;
+    const float4* tp = s.tris2 + 3 * (size_t)__ldg(slot_of_prim + id);
+    const float4 ta = __ldg(tp), tb = __ldg(tp + 1), tc = __ldg(tp + 2);
+    const V3 v0 = v3(ta.x, ta.y, ta.z);
+    const V3 E1 = v3(-ta.w, -tb.x, -tb.y), E2 = v3(tb.z, tb.w, tc.x);  // v1 - v0, v2 - v0
+    const V3 n = fcross(E1, E2);
+    const float nd = dot3(n, d), nn = dot3(n, n);
+    if (nd == 0.f || !(nn > 0.f)) return out;
+    const float t = dot3(n, v3(v0.x - o.x, v0.y - o.y, v0.z - o.z)) / nd;
+    const double* tuv = s.tri_uvs + 6 * (size_t)id;
+    const float du1 = (float)(tuv[2] - tuv[0]), dv1 = (float)(tuv[3] - tuv[1]);
+    const float du2 = (float)(tuv[4] - tuv[0]), dv2 = (float)(tuv[5] - tuv[1]);
+    float res[4];
+    for (int k = 0; k < 2; ++k) {
+        const V3 dd = k ? ddy : ddx;
+        const float dt = -t * dot3(n, dd) / nd;
+        const V3 dx = v3(dt * d.x + t * dd.x, dt * d.y + t * dd.y, dt * d.z + t * dd.z);
+        const float db1 = dot3(fcross(dx, E2), n) / nn, db2 = dot3(fcross(E1, dx), n) / nn;
+        res[k] = db1 * du1 + db2 * du2;      // du/dX, du/dY
+        res[2 + k] = db1 * dv1 + db2 * dv2;  // dv/dX, dv/dY
+    }
+    return make_float4(res[0], res[1], res[2], res[3]);
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(128) k_gbuffer(SceneView s, const float* __restrict__ rays, int64_t R,
+                                                 const uint32_t* __restrict__ slot_of_prim, GBufferOut g) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    V3 o = v3(__ldg(rays + 6 * r + 0), __ldg(rays + 6 * r + 1), __ldg(rays + 6 * r + 2));
+    V3 d = v3(__ldg(rays + 6 * r + 3), __ldg(rays + 6 * r + 4), __ldg(rays + 6 * r + 5));
+    gbuffer_pixel<KIND>(s, slot_of_prim, o, d, r, g);
+}
+
 __global__ void __launch_bounds__(128) k_gbuffer_uv_da(SceneView s, const float* __restrict__ rays,
                                                        const float* __restrict__ ddir,
                                                        const uint32_t* __restrict__ prim, int64_t R,
@@ -325,36 +367,79 @@ __global__ void __launch_bounds__(128) k_gbuffer_uv_da(SceneView s, const float*
                                                        float* __restrict__ uv_da) {
     int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= R) return;
-    float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
-    const uint32_t id = __ldg(prim + r);
-    if (id != kInvalidId && id < s.num_tris) {
-        const V3 o = v3(__ldg(rays + 6 * r + 0), __ldg(rays + 6 * r + 1), __ldg(rays + 6 * r + 2));
-        const V3 d = v3(__ldg(rays + 6 * r + 3), __ldg(rays + 6 * r + 4), __ldg(rays + 6 * r + 5));
-        const float4* tp = s.tris2 + 3 * (size_t)__ldg(slot_of_prim + id);
-        const float4 ta = __ldg(tp), tb = __ldg(tp + 1), tc = __ldg(tp + 2);
-        const V3 v0 = v3(ta.x, ta.y, ta.z);
-        const V3 E1 = v3(-ta.w, -tb.x, -tb.y), E2 = v3(tb.z, tb.w, tc.x);  // v1 - v0, v2 - v0
-        const V3 n = fcross(E1, E2);
-        const float nd = dot3(n, d), nn = dot3(n, n);
-        if (nd != 0.f && nn > 0.f) {
-            const float t = dot3(n, v3(v0.x - o.x, v0.y - o.y, v0.z - o.z)) / nd;
-            const double* tuv = s.tri_uvs + 6 * (size_t)id;
-            const float du1 = (float)(tuv[2] - tuv[0]), dv1 = (float)(tuv[3] - tuv[1]);
-            const float du2 = (float)(tuv[4] - tuv[0]), dv2 = (float)(tuv[5] - tuv[1]);
-            float res[4];
-            for (int k = 0; k < 2; ++k) {
-                const V3 dd = v3(__ldg(ddir + 6 * r + 3 * k + 0), __ldg(ddir + 6 * r + 3 * k + 1),
-                                 __ldg(ddir + 6 * r + 3 * k + 2));
-                const float dt = -t * dot3(n, dd) / nd;
-                const V3 dx = v3(dt * d.x + t * dd.x, dt * d.y + t * dd.y, dt * d.z + t * dd.z);
-                const float db1 = dot3(fcross(dx, E2), n) / nn, db2 = dot3(fcross(E1, dx), n) / nn;
-                res[k] = db1 * du1 + db2 * du2;      // du/dX, du/dY
-                res[2 + k] = db1 * dv1 + db2 * dv2;  // dv/dX, dv/dY
-            }
-            out = make_float4(res[0], res[1], res[2], res[3]);
-        }
+    const V3 o = v3(__ldg(rays + 6 * r + 0), __ldg(rays + 6 * r + 1), __ldg(rays + 6 * r + 2));
+    const V3 d = v3(__ldg(rays + 6 * r + 3), __ldg(rays + 6 * r + 4), __ldg(rays + 6 * r + 5));
+    const V3 ddx = v3(__ldg(ddir + 6 * r + 0), __ldg(ddir + 6 * r + 1), __ldg(ddir + 6 * r + 2));
+    const V3 ddy = v3(__ldg(ddir + 6 * r + 3), __ldg(ddir + 6 * r + 4), __ldg(ddir + 6 * r + 5));
+    reinterpret_cast<float4*>(uv_da)[r] = gbuffer_uv_da(s, slot_of_prim, o, d, ddx, ddy, __ldg(prim + r));
+}
+
+// The whole G-buffer of the views the reference rasterises (mat_nvdiffrast.py:116-128) in ONE launch: blockIdx.y is
+// the view; the CTA inverts that view's 4x4 mvp once (float64 cofactors, shared memory), every thread un-projects its
+// pixel centre to a unit ray direction and its two screen-space differentials, walks the BVH and writes position,
+// normal, texc, texd and mask.  clip = [v,1] @ mvp (row vectors), pixel row 0 at ndc y = -1 (nvdiffrast's layout).
+template <int KIND>
+__global__ void __launch_bounds__(128) k_gbuffer_mvp(SceneView s, const float* __restrict__ mvp,
+                                                     const float* __restrict__ cam, int res,
+                                                     const uint32_t* __restrict__ slot_of_prim, GBufferOut g,
+                                                     float* __restrict__ rays_out) {
+    __shared__ double inv[16];
+    __shared__ int ok;
+    const int view = blockIdx.y;
+    if (threadIdx.x < 16) {  // cofactor (i, j) -> inverse entry (j, i)
+        const float* m = mvp + 16 * view;
+        const int i = threadIdx.x >> 2, j = threadIdx.x & 3;
+        double sub[9];
+        int k = 0;
+        for (int a = 0; a < 4; ++a)
+            for (int b = 0; b < 4; ++b)
+                if (a != i && b != j) sub[k++] = (double)m[4 * a + b];
+        const double c = sub[0] * (sub[4] * sub[8] - sub[5] * sub[7]) - sub[1] * (sub[3] * sub[8] - sub[5] * sub[6]) +
+                         sub[2] * (sub[3] * sub[7] - sub[4] * sub[6]);
+        inv[4 * j + i] = ((i + j) & 1) ? -c : c;
     }
-    reinterpret_cast<float4*>(uv_da)[r] = out;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const float* m = mvp + 16 * view;
+        const double det = (double)m[0] * inv[0] + (double)m[1] * inv[4] + (double)m[2] * inv[8] + (double)m[3] * inv[12];
+        ok = det != 0.0;
+        if (ok)
+            for (int k = 0; k < 16; ++k) inv[k] /= det;
+    }
+    __syncthreads();
+    const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= res * res) return;
+    const int64_t r = (int64_t)view * res * res + pix;
+    const int row = pix / res, col = pix - row * res;
+    const double x = ((double)col + 0.5) / (double)res * 2.0 - 1.0, y = ((double)row + 0.5) / (double)res * 2.0 - 1.0;
+    // world_h = (x, y, 1, 1) @ inv
+    double wh[4];
+    for (int k = 0; k < 4; ++k) wh[k] = x * inv[k] + y * inv[4 + k] + inv[8 + k] + inv[12 + k];
+    const double cx = (double)__ldg(cam + 0), cy = (double)__ldg(cam + 1), cz = (double)__ldg(cam + 2);
+    const double dx = wh[0] / wh[3] - cx, dy = wh[1] / wh[3] - cy, dz = wh[2] / wh[3] - cz;
+    const double ln = sqrt(dx * dx + dy * dy + dz * dz);
+    const bool valid = ok && ln > 0.0 && isfinite(ln);
+    const double hx = valid ? dx / ln : 0.0, hy = valid ? dy / ln : 0.0, hz = valid ? dz / ln : 0.0;
+    V3 dd[2];
+    for (int axis = 0; axis < 2; ++axis) {  // derivative of the unit direction per pixel step along X / Y
+        const double* rw = inv + 4 * axis;
+        const double sc = 2.0 / (double)res / (wh[3] * wh[3]);
+        const double px = (rw[0] * wh[3] - wh[0] * rw[3]) * sc, py = (rw[1] * wh[3] - wh[1] * rw[3]) * sc,
+                     pz = (rw[2] * wh[3] - wh[2] * rw[3]) * sc;
+        const double along = hx * px + hy * py + hz * pz;
+        dd[axis] = valid ? v3((float)((px - hx * along) / ln), (float)((py - hy * along) / ln),
+                              (float)((pz - hz * along) / ln))
+                         : v3(0.f, 0.f, 0.f);
+    }
+    const V3 o = v3((float)cx, (float)cy, (float)cz), d = v3((float)hx, (float)hy, (float)hz);
+    if (rays_out) {
+        rays_out[6 * r + 0] = o.x; rays_out[6 * r + 1] = o.y; rays_out[6 * r + 2] = o.z;
+        rays_out[6 * r + 3] = d.x; rays_out[6 * r + 4] = d.y; rays_out[6 * r + 5] = d.z;
+    }
+    const Hit h = gbuffer_pixel<KIND>(s, slot_of_prim, o, d, r, g);
+    if (g.uv_da)
+        reinterpret_cast<float4*>(g.uv_da)[r] =
+            s.tri_uvs ? gbuffer_uv_da(s, slot_of_prim, o, d, dd[0], dd[1], h.prim) : make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1327,9 +1412,24 @@ int texir_gbuffer(const texir_scene* sc, const float* rays, int64_t R, float* po
     if (!rays) TX_FAIL("texir_gbuffer: NULL rays");
     if (uv && !sc->view.tri_uvs) TX_FAIL("texir_gbuffer: uv requested but the scene has no triangle uvs");
     DeviceGuard guard(sc->info.device);
-    k_gbuffer<4><<<grid_for(R, 128), 128, 0, (cudaStream_t)stream>>>(sc->view, rays, R, (const uint32_t*)sc->d_slot_of_prim,
-                                                                      pos, nrm, uv, prim, bary, mask);
+    GBufferOut g{pos, nrm, uv, prim, bary, mask, nullptr};
+    k_gbuffer<4><<<grid_for(R, 128), 128, 0, (cudaStream_t)stream>>>(sc->view, rays, R, (const uint32_t*)sc->d_slot_of_prim, g);
     return finish_launch("k_gbuffer");
+}
+
+int texir_gbuffer_mvp(const texir_scene* sc, const float* mvp, const float* cam, int V, int res, float* pos, float* nrm,
+                      float* uv, float* uv_da, uint32_t* prim, float* bary, float* mask, float* rays_out, void* stream) {
+    if (!sc) TX_FAIL("texir_gbuffer_mvp: NULL scene");
+    if (V < 0 || res <= 0 || res > 16384 || V > 65535) TX_FAIL("texir_gbuffer_mvp: bad view count or resolution");
+    if (V == 0) return 0;
+    if (!mvp || !cam) TX_FAIL("texir_gbuffer_mvp: NULL mvp / cam");
+    if ((uv || uv_da) && !sc->view.tri_uvs) TX_FAIL("texir_gbuffer_mvp: uv requested but the scene has no triangle uvs");
+    DeviceGuard guard(sc->info.device);
+    GBufferOut g{pos, nrm, uv, prim, bary, mask, uv_da};
+    dim3 grid(grid_for((int64_t)res * res, 128), (unsigned)V);
+    k_gbuffer_mvp<4><<<grid, 128, 0, (cudaStream_t)stream>>>(sc->view, mvp, cam, res, (const uint32_t*)sc->d_slot_of_prim, g,
+                                                             rays_out);
+    return finish_launch("k_gbuffer_mvp");
 }
 
 int texir_gbuffer_uv_da(const texir_scene* sc, const float* rays, const float* ddir, const uint32_t* prim, int64_t R,

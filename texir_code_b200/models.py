@@ -104,7 +104,8 @@ def rays_from_mvp(mvp: torch.Tensor, cam_position: torch.Tensor, res: int):
     dr.rasterize at res x res), one per pixel centre, row 0 at ndc y = -1 as in nvdiffrast's images.
     mvp [V,4,4] (datasets/dataset.py:461-463: transpose(proj @ w2c)), cam_position [3]  ->
     rays [V,res,res,6] (origin, unit direction) and ray differentials [V,res,res,6] = (d dir/dX, d dir/dY) per
-    pixel step (X = column, Y = row).  Host-side set-up of V small matrices in float64; no hot-path work."""
+    pixel step (X = column, Y = row).  Plain torch in float64: the readable statement of what the one-launch kernel
+    behind ops.gbuffer_mvp computes per pixel (the model uses that kernel; tests compare the two)."""
     dev = mvp.device
     inv = torch.linalg.inv(mvp.detach().double())                      # world_h = clip_h @ inv
     cam = cam_position.detach().double().to(dev)
@@ -186,8 +187,7 @@ class MaterialModel(HotPathMixin, nn.Module):
     def gbuffers(self, mvp: torch.Tensor, cam_position: torch.Tensor) -> dict:
         """mat_nvdiffrast.py:116-128: position / normal / texc / texd / mask of the 6 cube faces"""
         dev = self.scene.device
-        rays, ddir = rays_from_mvp(mvp.to(dev), cam_position.to(dev), self.cube_res)
-        gb = ops.gbuffer(self._scene(), rays, ray_differentials=ddir)
+        gb = ops.gbuffer_mvp(self._scene(), mvp.to(dev), cam_position.to(dev), self.cube_res)
         if hasattr(self, "normals"):
             tri = self.triangles[gb["primitive_ids"].long().clamp_(min=0) % self.triangles.shape[0]]
             b = gb["primitive_uvs"]

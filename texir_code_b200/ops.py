@@ -336,6 +336,40 @@ def gbuffer(scene: Scene, rays: torch.Tensor, offset: float = 0.0,
     return out
 
 
+def gbuffer_mvp(scene: Scene, mvp: torch.Tensor, cam_position: torch.Tensor, res: int, return_rays: bool = False
+                ) -> dict:
+    """The G-buffer of the views the reference rasterises, straight from its camera matrices and in one launch
+    (mat_nvdiffrast.py:116-128): mvp [V,4,4] (clip = [v,1] @ mvp[i]), cam_position [3] -> dict(position, normal
+    [V,res,res,3], texc [..,2], texd [..,4], primitive_ids, primitive_uvs, mask [..,1]) (+ rays [..,6])."""
+    _need_cuda("gbuffer_mvp", mvp)
+    dev = mvp.device
+    m = _f32c(mvp).reshape(-1, 4, 4)
+    cam = _f32c(cam_position, dev).reshape(3)
+    V, res = int(m.shape[0]), int(res)
+    R = V * res * res
+    f32 = dict(dtype=torch.float32, device=dev)
+    pos, nrm, bary = torch.empty(R, 3, **f32), torch.empty(R, 3, **f32), torch.empty(R, 2, **f32)
+    uv = torch.empty(R, 2, **f32) if scene.has_uvs else None
+    texd = torch.empty(R, 4, **f32) if scene.has_uvs else None
+    prim = torch.empty(R, dtype=torch.int32, device=dev)
+    mask = torch.empty(R, **f32)
+    rays = torch.empty(R, 6, **f32) if return_rays else None
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().texir_gbuffer_mvp(scene.handle, _ptr(m), _ptr(cam), V, res, _ptr(pos), _ptr(nrm), _ptr(uv),
+                                                 _ptr(texd), _ptr(prim), _ptr(bary), _ptr(mask), _ptr(rays),
+                                                 _stream_ptr(dev)), "texir_gbuffer_mvp")
+    shape = (V, res, res)
+    out = {"position": pos.reshape(shape + (3,)), "normal": nrm.reshape(shape + (3,)),
+           "primitive_ids": prim.reshape(shape), "primitive_uvs": bary.reshape(shape + (2,)),
+           "mask": mask.reshape(shape + (1,))}
+    if uv is not None:
+        out["texc"] = uv.reshape(shape + (2,))
+        out["texd"] = texd.reshape(shape + (4,))
+    if rays is not None:
+        out["rays"] = rays.reshape(shape + (6,))
+    return out
+
+
 # --------------------------------------------------------------------------------------------------
 # material-texture fetch / gradient scatter (dr.texture, models/mat_nvdiffrast.py:131-139)
 # --------------------------------------------------------------------------------------------------
