@@ -36,6 +36,9 @@ def main():
                 d[h] = {"value": vals[i], "unit": units[i]}
             if "issue_stalled" in h and h.endswith("per_warp_active.pct"):
                 d.setdefault("stalls_pct_of_warp_active", {})[h.split("issue_stalled_")[1].replace("_per_warp_active.pct", "")] = float(vals[i] or 0)
+            if h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("_per_issue_active.ratio"):
+                # warps of this scheduler waiting for that reason, per issued instruction
+                d.setdefault("stalled_warps_per_issue", {})[h[len("smsp__average_warps_issue_stalled_"):-len("_per_issue_active.ratio")]] = float(vals[i] or 0)
         def num(k):
             v, u = float(d[k]["value"].replace(",", "")), d[k]["unit"]
             mult = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1, "ms": 1e-3, "us": 1e-6, "ns": 1e-9, "s": 1}.get(u, 1)
@@ -50,6 +53,8 @@ def main():
             "warp_inst_per_ray_sample": float(d["smsp__inst_executed.sum"]["value"]) / rays,
             "thread_inst_per_ray_sample": float(d["smsp__inst_executed.sum"]["value"]) * float(d["smsp__thread_inst_executed_per_inst_executed.ratio"]["value"]) / rays,
         }
+        if "stalled_warps_per_issue" in d:
+            d["stalled_warps_per_issue"] = dict(sorted(d["stalled_warps_per_issue"].items(), key=lambda kv: -kv[1])[:8])
         if "stalls_pct_of_warp_active" in d:
             d["stalls_pct_of_warp_active"] = dict(sorted(d["stalls_pct_of_warp_active"].items(), key=lambda kv: -kv[1])[:8])
         out.append(d)
@@ -60,7 +65,7 @@ def main():
             if isinstance(v, dict) and "value" in v:
                 print("  %-70s %s %s" % (k, v["value"], v["unit"]))
         print("  derived:", json.dumps(d["derived"]))
-        print("  stalls:", json.dumps(d.get("stalls_pct_of_warp_active")))
+        print("  stalled warps per issued instruction:", json.dumps(d.get("stalled_warps_per_issue")))
 
 
 if __name__ == "__main__":
