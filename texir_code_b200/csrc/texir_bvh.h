@@ -46,6 +46,28 @@ struct alignas(16) uint4 {
 #define TX_LDG(p) (*(p))
 #endif
 
+// Leaf-level data (triangles, per-corner UVs, radiance texels) is touched once per ray with no reuse inside the SM;
+// TX_LEAF_NOALLOC=1 loads it with L1::no_allocate so that it does not push BVH nodes out of L1.
+#ifndef TX_LEAF_NOALLOC
+#define TX_LEAF_NOALLOC 0
+#endif
+#if defined(__CUDA_ARCH__) && TX_LEAF_NOALLOC
+__device__ __forceinline__ float4 tx_ld_leaf(const float4* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ double2 tx_ld_leaf(const double2* p) {
+    double2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+#define TX_LD_LEAF(p) tx_ld_leaf(p)
+#else
+#define TX_LD_LEAF(p) TX_LDG(p)
+#endif
+
 namespace texir {
 
 constexpr int kStackSize = 64;
@@ -105,9 +127,9 @@ TX_HD bool slab(float lox, float hix, float loy, float hiy, float loz, float hiz
 }
 
 TX_HD void test_slot(const float4* __restrict__ tris, int slot, V3 o, V3 d, Hit& hit) {
-    float4 a = TX_LDG(&tris[3 * slot + 0]);
-    float4 b = TX_LDG(&tris[3 * slot + 1]);
-    float4 c = TX_LDG(&tris[3 * slot + 2]);
+    float4 a = TX_LD_LEAF(&tris[3 * slot + 0]);
+    float4 b = TX_LD_LEAF(&tris[3 * slot + 1]);
+    float4 c = TX_LD_LEAF(&tris[3 * slot + 2]);
     const V3 e1 = v3(a.w, b.x, b.y), e2 = v3(b.z, b.w, c.x);
     float t, u, v;
     if (tri_test(v3(a.x, a.y, a.z), e1, e2, fcross(e2, e1), o, d, &t, &u, &v)) {
@@ -315,7 +337,7 @@ TX_HD V3 fetch_radiance(const SceneView& s, const Hit& h) {
     double tuv[6];
 #ifdef __CUDA_ARCH__
     const double2* up = reinterpret_cast<const double2*>(s.tri_uvs + 6 * (size_t)h.prim);
-    double2 a = __ldg(up + 0), b = __ldg(up + 1), c = __ldg(up + 2);
+    double2 a = TX_LD_LEAF(up + 0), b = TX_LD_LEAF(up + 1), c = TX_LD_LEAF(up + 2);
     tuv[0] = a.x; tuv[1] = a.y; tuv[2] = b.x; tuv[3] = b.y; tuv[4] = c.x; tuv[5] = c.y;
 #else
     for (int i = 0; i < 6; ++i) tuv[i] = s.tri_uvs[6 * (size_t)h.prim + i];
@@ -325,7 +347,7 @@ TX_HD V3 fetch_radiance(const SceneView& s, const Hit& h) {
     Bilerp b4 = bilerp_setup(gu, gv, s.tex_w, s.tex_h);
     const float4* r0 = s.tex + (size_t)b4.y0 * (size_t)s.tex_w;
     const float4* r1 = s.tex + (size_t)b4.y1 * (size_t)s.tex_w;
-    float4 nw = TX_LDG(r0 + b4.x0), ne = TX_LDG(r0 + b4.x1), sw = TX_LDG(r1 + b4.x0), se = TX_LDG(r1 + b4.x1);
+    float4 nw = TX_LD_LEAF(r0 + b4.x0), ne = TX_LD_LEAF(r0 + b4.x1), sw = TX_LD_LEAF(r1 + b4.x0), se = TX_LD_LEAF(r1 + b4.x1);
     return v3(bilerp_apply(b4, nw.x, ne.x, sw.x, se.x), bilerp_apply(b4, nw.y, ne.y, sw.y, se.y),
               bilerp_apply(b4, nw.z, ne.z, sw.z, se.z));
 }

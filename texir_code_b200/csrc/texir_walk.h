@@ -144,9 +144,17 @@ TX_HD void rayq_setup(const SceneView& s, RayQ& r, V3 o, V3 d) {
 }
 
 #ifdef __CUDA_ARCH__
+#ifndef TX_NODE_EVICT_LAST
+#define TX_NODE_EVICT_LAST 0
+#endif
 TX_D uint4 ld_nc_u4(const uint4* p) {
     uint4 v;
+#if TX_NODE_EVICT_LAST
+    asm volatile("ld.global.nc.L1::evict_last.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+#else
     asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+#endif
     return v;
 }
 #else
@@ -157,7 +165,13 @@ TX_HD float qplane_(uint32_t w, uint32_t sel, float S, float O) {
     return tx_fma(int_as_float_((int)byte_perm_(w, 0x4B000000u, sel)), S, O);
 }
 
-TX_HD int qbvh2_step(const SceneView& s, const RayQ& r, float tbest, int node, int* stack, int& sp) {
+#ifndef TX_STACK_TOP
+#define TX_STACK_TOP 0
+#endif
+#ifndef TX_NODE_EXIT_BELOW
+#define TX_NODE_EXIT_BELOW 0
+#endif
+TX_HD int qbvh2_step(const SceneView& s, const RayQ& r, float tbest, int node, int* stack, int& sp, int& top) {
     const uint4* np = s.qnodes2 + 2 * (size_t)node;
     // two 128-bit loads: sm_100's 256-bit LDG (LDG.E.ENL2.256) was measured 23 % slower here -- it does not
     // allocate in L1, and the upper tree lives there
@@ -173,6 +187,21 @@ TX_HD int qbvh2_step(const SceneView& s, const RayQ& r, float tbest, int node, i
                             fminf(qplane_(q1.y, fz, r.S.z, r.O.z), tbest));
     const int c0 = (int)q1.z, c1 = (int)q1.w;
     const bool h0 = t0n <= t0f, h1 = t1n <= t1f;
+#if TX_STACK_TOP
+    // the top of the stack lives in a register: a pop hands it out at once and re-fills it with a load whose
+    // latency hides behind the next node step instead of sitting between the pop and the next node fetch
+    if (h0 && h1) {
+        const bool swap = t1n < t0n;
+        stack[sp++] = top;
+        top = swap ? c0 : c1;
+        return swap ? c1 : c0;
+    }
+    if (h0) return c0;
+    if (h1) return c1;
+    const int popped = top;
+    top = stack[--sp];
+    return popped;
+#else
     if (h0 && h1) {
         const bool swap = t1n < t0n;
         stack[sp++] = swap ? c0 : c1;
@@ -181,6 +210,7 @@ TX_HD int qbvh2_step(const SceneView& s, const RayQ& r, float tbest, int node, i
     if (h0) return c0;
     if (h1) return c1;
     return stack[--sp];
+#endif
 }
 
 TX_HD Hit trace_qbvh2(const SceneView& s, V3 o, V3 d) {
@@ -191,14 +221,29 @@ TX_HD Hit trace_qbvh2(const SceneView& s, V3 o, V3 d) {
     int stack[kStackSize];
     int sp = 0;
     stack[sp++] = kSentinel;
+    int top = kSentinel;  // TX_STACK_TOP: register copy of the top entry (stack[0] then backs the final pop)
     int node = 0;
     while (node != kSentinel) {
-        while (node >= 0 && node != kSentinel) node = qbvh2_step(s, r, hit.t, node, stack, sp);
+#if defined(__CUDA_ARCH__) && TX_NODE_EXIT_BELOW
+        // leave the node loop once fewer than TX_NODE_EXIT_BELOW lanes are still in it, so that the lanes waiting at
+        // a leaf do not wait for the last stragglers (they re-enter with the next round)
+        while (node >= 0 && node != kSentinel) {
+            node = qbvh2_step(s, r, hit.t, node, stack, sp, top);
+            if (__popc(__activemask()) < TX_NODE_EXIT_BELOW) break;
+        }
+#else
+        while (node >= 0 && node != kSentinel) node = qbvh2_step(s, r, hit.t, node, stack, sp, top);
+#endif
         if (node < 0) {
             const int ref = ~node;
             const int first = ref >> 3, cnt = (ref & 7) + 1;
             for (int i = 0; i < cnt; ++i) test_slot(s.tris2, first + i, r.o, r.d, hit);
+#if TX_STACK_TOP
+            node = top;
+            top = stack[--sp];
+#else
             node = stack[--sp];
+#endif
         }
     }
     return hit;
