@@ -40,6 +40,8 @@ def load():
     lib.emul_pad_texture.argtypes = [vp, i32, i32, i32, vp, vp]
     lib.emul_rgbe_encode.argtypes = [vp, i64, i32, vp]
     lib.emul_rgbe_decode.argtypes = [vp, i64, i32, vp]
+    lib.emul_trace_segments.argtypes = [vp, vp, i64, i32, vp, vp, vp]
+    lib.emul_simulate_warp.argtypes = [vp, vp, i32, i32, i32, vp]
     lib.emul_mip_levels.argtypes = [i32, i32, i32]
     lib.emul_mip_elems.restype = i64
     lib.emul_mip_elems.argtypes = [i32, i32, i32, i32]

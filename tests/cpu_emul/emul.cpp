@@ -271,4 +271,133 @@ void emul_texture_fetch_mip(const float* tex, const float* mips, int H, int W, i
     }
 }
 
+// ---- divergence analysis (profiles/simulate_warp_divergence.py): for every ray the number of QBVH2 node steps between
+// consecutive leaf visits ("segments"), i.e. what one lane does between two reconvergence points of the while-while loop
+void emul_trace_segments(EmulScene* s, const float* rays, int64_t R, int max_seg, int32_t* n_seg, int32_t* seg,
+                         int32_t* leaf_tris) {
+    for (int64_t q = 0; q < R; ++q) {
+        RayQ r;
+        rayq_setup(s->view, r, v3(rays[6 * q], rays[6 * q + 1], rays[6 * q + 2]),
+                   v3(rays[6 * q + 3], rays[6 * q + 4], rays[6 * q + 5]));
+        Hit hit;
+        hit_reset(hit);
+        int stack[kStackSize];
+        int sp = 0, top = kSentinel, node = 0, k = 0;
+        stack[sp++] = kSentinel;
+        while (node != kSentinel) {
+            int steps = 0;
+            while (node >= 0 && node != kSentinel) {
+                node = qbvh2_step(s->view, r, hit.t, node, stack, sp, top);
+                ++steps;
+            }
+            int cnt = 0;
+            if (node < 0) {
+                const int ref = ~node;
+                const int first = ref >> 3;
+                cnt = (ref & 7) + 1;
+                for (int i = 0; i < cnt; ++i) test_slot(s->view.tris2, first + i, r.o, r.d, hit);
+#if TX_STACK_TOP
+                node = top;
+                top = stack[--sp];
+#else
+                node = stack[--sp];
+#endif
+            }
+            if (k < max_seg) {
+                seg[q * max_seg + k] = steps;
+                leaf_tris[q * max_seg + k] = cnt;
+            }
+            ++k;
+        }
+        n_seg[q] = k;
+    }
+}
+
+// Lock-step model of one warp walking `lanes` rays (<= 32) with a per-lane queue of `Q` postponed leaves:
+//   Q = 0  the kernels' while-while loop: a lane that reaches a leaf waits until no lane is at an inner node;
+//   Q >= 1 speculative traversal (Aila & Laine 2009): the lane parks the leaf and keeps walking with its old t_best;
+//          with stop_when_all_found the node phase ends as soon as every unfinished lane has parked a leaf.
+// out[0] = warp node iterations, out[1] = warp triangle iterations, out[2] = lane node steps, out[3] = lane triangle tests
+void emul_simulate_warp(EmulScene* s, const float* rays, int lanes, int Q, int stop_when_all_found, int64_t* out) {
+    struct Lane {
+        RayQ r;
+        Hit hit;
+        int stack[kStackSize];
+        int sp, top, node;
+        int queue[8], nq;
+    };
+    std::vector<Lane> L((size_t)lanes);
+    for (int q = 0; q < lanes; ++q) {
+        Lane& l = L[q];
+        rayq_setup(s->view, l.r, v3(rays[6 * q], rays[6 * q + 1], rays[6 * q + 2]),
+                   v3(rays[6 * q + 3], rays[6 * q + 4], rays[6 * q + 5]));
+        hit_reset(l.hit);
+        l.sp = 0;
+        l.stack[l.sp++] = kSentinel;
+        l.top = kSentinel;
+        l.node = 0;
+        l.nq = 0;
+    }
+    auto pop = [](Lane& l) {
+#if TX_STACK_TOP
+        int n = l.top;
+        l.top = l.stack[--l.sp];
+        return n;
+#else
+        return l.stack[--l.sp];
+#endif
+    };
+    int64_t node_it = 0, tri_it = 0, node_steps = 0, tri_tests = 0;
+    for (;;) {
+        bool any_alive = false;
+        for (auto& l : L) any_alive |= (l.node != kSentinel || l.nq > 0);
+        if (!any_alive) break;
+        // node phase
+        for (;;) {
+            bool stepped = false;
+            for (auto& l : L) {
+                if (l.node >= 0 && l.node != kSentinel) {
+                    l.node = qbvh2_step(s->view, l.r, l.hit.t, l.node, l.stack, l.sp, l.top);
+                    ++node_steps;
+                    stepped = true;
+                    while (l.node < 0 && l.nq < Q) {  // park the leaf, keep walking
+                        l.queue[l.nq++] = l.node;
+                        l.node = pop(l);
+                    }
+                }
+            }
+            if (!stepped) break;
+            ++node_it;
+            if (stop_when_all_found) {
+                bool searching = false;
+                for (auto& l : L) searching |= (l.node != kSentinel && l.node >= 0 && l.nq == 0);
+                if (!searching) break;
+            }
+        }
+        // leaf phase: every lane tests what it has parked (and the leaf it is blocked on)
+        int64_t worst = 0;
+        for (auto& l : L) {
+            int64_t mine = 0;
+            if (l.node < 0) {
+                l.queue[l.nq++] = l.node;  // queue has Q + 1 slots
+                l.node = pop(l);
+            }
+            for (int k = 0; k < l.nq; ++k) {
+                const int ref = ~l.queue[k];
+                const int first = ref >> 3, cnt = (ref & 7) + 1;
+                for (int i = 0; i < cnt; ++i) test_slot(s->view.tris2, first + i, l.r.o, l.r.d, l.hit);
+                mine += cnt;
+            }
+            l.nq = 0;
+            tri_tests += mine;
+            worst = mine > worst ? mine : worst;
+        }
+        tri_it += worst;
+    }
+    out[0] = node_it;
+    out[1] = tri_it;
+    out[2] = node_steps;
+    out[3] = tri_tests;
+}
+
 }  // extern "C"

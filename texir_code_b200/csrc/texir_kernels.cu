@@ -94,6 +94,13 @@ static bool use_qnodes() {  // TEXIR_QNODES=0: walk the 64-byte float nodes inst
     static const bool on = env_int("TEXIR_QNODES", 1) != 0;
     return on;
 }
+static int patch_bits(int N) {  // TEXIR_COHERENT_BITS=a overrides coherent_bits(N): shape of a warp's sample patch
+    static const int forced = env_int("TEXIR_COHERENT_BITS", -1);
+    if (forced < 0) return coherent_bits(N);
+    int a = forced;
+    while (a > 0 && (N >> a) < 32) --a;
+    return a;
+}
 static int finish_launch(const char* what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
@@ -1454,7 +1461,7 @@ int texir_irradiance_fwd(const texir_scene* sc, const float* pos, const float* n
     if (P == 0) return 0;
     if (!pos || !nrm || !shift || !E) TX_FAIL("texir_irradiance_fwd: NULL argument");
     DeviceGuard guard(sc->info.device);
-    const int G = group_lanes(N), ab = coherent_bits(N);
+    const int G = group_lanes(N), ab = patch_bits(N);
     const int64_t warps = (P + (32 / G) - 1) / (32 / G);
     unsigned g = grid_for(warps * 32, 128);
     if (sc->info.bvh_kind == TEXIR_BVH8)
@@ -1492,8 +1499,8 @@ static int shade_common(const char* fn, const texir_scene* sc, ShadeArgs& a) {
     int gs = group_lanes(a.N_spec);
     int gd = a.N_diff > 0 ? group_lanes(a.N_diff) : gs;
     a.G = gs > gd ? gs : gd;
-    a.a_spec = coherent_bits(a.N_spec);
-    a.a_diff = a.N_diff > 0 ? coherent_bits(a.N_diff) : 0;
+    a.a_spec = patch_bits(a.N_spec);
+    a.a_diff = a.N_diff > 0 ? patch_bits(a.N_diff) : 0;
     return 0;
 }
 
