@@ -86,3 +86,18 @@ for label, Q, stop in (("while-while (kernels)", 0, 0), ("1 postponed leaf, stop
             tot += out
             groups += 1
     print("%-46s %9.1f %9.1f %11.1f %10.2f" % (label, tot[0] / groups, tot[1] / groups, tot[2] / groups / 32, tot[3] / groups / 32))
+
+# ---- ray pools: all 2048 rays of a point handed to one warp in the kernels' order ----
+order = idx.reshape(-1)
+print()
+print("%-46s %9s %9s %9s %12s   (per 32 rays)" % ("ray pool of one point (2048 rays, one warp)", "node it.", "tri it.", "rounds", "rounds w/ end"))
+for label, mode in (("refill finished lanes at round boundaries", 0), ("two rays per lane, step whichever can", 1)):
+    tot = np.zeros(4, np.int64)
+    out = np.zeros(4, np.int64)
+    npts = min(P, 6)
+    for p in range(npts):
+        r = np.ascontiguousarray(rays_pn[p, order])
+        lib.emul_simulate_stream(h, r.ctypes.data, N, mode, out.ctypes.data)
+        tot += out
+    k = npts * N / 32
+    print("%-46s %9.1f %9.1f %9.1f %12.1f" % (label, tot[0] / k, tot[1] / k, tot[2] / k, tot[3] / k))

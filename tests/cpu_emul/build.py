@@ -42,6 +42,7 @@ def load():
     lib.emul_rgbe_decode.argtypes = [vp, i64, i32, vp]
     lib.emul_trace_segments.argtypes = [vp, vp, i64, i32, vp, vp, vp]
     lib.emul_simulate_warp.argtypes = [vp, vp, i32, i32, i32, vp]
+    lib.emul_simulate_stream.argtypes = [vp, vp, i32, i32, vp]
     lib.emul_mip_levels.argtypes = [i32, i32, i32]
     lib.emul_mip_elems.restype = i64
     lib.emul_mip_elems.argtypes = [i32, i32, i32, i32]

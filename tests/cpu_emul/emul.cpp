@@ -400,4 +400,106 @@ void emul_simulate_warp(EmulScene* s, const float* rays, int lanes, int Q, int s
     out[3] = tri_tests;
 }
 
+// Two more lock-step models over a pool of `total` rays handed to 32 lanes:
+//   mode 0  refill at round boundaries: a lane whose ray has finished takes the next ray of the pool when the warp
+//           reconverges after a leaf phase (a ray stream with warp-wide refill points);
+//   mode 1  two rays per lane: in the node phase a lane steps its first ray that stands at an inner node, so it idles
+//           only when both of its rays wait at a leaf (or are finished); pairs are replaced when both are finished
+//           and all lanes have finished theirs (no refill).
+// out[0] = warp node iterations, out[1] = warp triangle iterations, out[2] = rounds, out[3] = rounds in which a lane finished
+void emul_simulate_stream(EmulScene* s, const float* rays, int total, int mode, int64_t* out) {
+    struct Ray {
+        RayQ r;
+        Hit hit;
+        int stack[kStackSize];
+        int sp, top, node;
+        bool live;
+    };
+    const int per_lane = mode == 1 ? 2 : 1;
+    std::vector<Ray> R((size_t)32 * per_lane);
+    int next = 0;
+    auto start = [&](Ray& l) {
+        if (next >= total) {
+            l.live = false;
+            l.node = kSentinel;
+            return;
+        }
+        const float* q = rays + 6 * (size_t)next++;
+        rayq_setup(s->view, l.r, v3(q[0], q[1], q[2]), v3(q[3], q[4], q[5]));
+        hit_reset(l.hit);
+        l.sp = 0;
+        l.stack[l.sp++] = kSentinel;
+        l.top = kSentinel;
+        l.node = 0;
+        l.live = true;
+    };
+    auto pop = [](Ray& l) {
+#if TX_STACK_TOP
+        int n = l.top;
+        l.top = l.stack[--l.sp];
+        return n;
+#else
+        return l.stack[--l.sp];
+#endif
+    };
+    for (auto& l : R) start(l);
+    int64_t node_it = 0, tri_it = 0, rounds = 0, finishing_rounds = 0;
+    for (;;) {
+        bool any = false;
+        for (auto& l : R) any |= l.live;
+        if (!any) break;
+        for (;;) {  // node phase
+            bool stepped = false;
+            for (int lane = 0; lane < 32; ++lane)
+                for (int k = 0; k < per_lane; ++k) {
+                    Ray& l = R[(size_t)lane * per_lane + k];
+                    if (l.live && l.node >= 0 && l.node != kSentinel) {
+                        l.node = qbvh2_step(s->view, l.r, l.hit.t, l.node, l.stack, l.sp, l.top);
+                        stepped = true;
+                        break;  // one step per lane per iteration
+                    }
+                }
+            if (!stepped) break;
+            ++node_it;
+        }
+        int64_t worst = 0;  // leaf phase
+        bool finished = false;
+        for (int lane = 0; lane < 32; ++lane) {
+            int64_t mine = 0;
+            for (int k = 0; k < per_lane; ++k) {
+                Ray& l = R[(size_t)lane * per_lane + k];
+                if (!l.live) continue;
+                if (l.node < 0) {
+                    const int ref = ~l.node;
+                    const int first = ref >> 3, cnt = (ref & 7) + 1;
+                    for (int i = 0; i < cnt; ++i) test_slot(s->view.tris2, first + i, l.r.o, l.r.d, l.hit);
+                    mine += cnt;
+                    l.node = pop(l);
+                }
+                if (l.node == kSentinel) {
+                    l.live = false;
+                    finished = true;
+                }
+            }
+            worst = mine > worst ? mine : worst;
+        }
+        tri_it += worst;
+        ++rounds;
+        finishing_rounds += finished;
+        if (mode == 0) {
+            for (auto& l : R)
+                if (!l.live) start(l);
+        } else {
+            bool all_done = true;
+            for (auto& l : R) all_done &= !l.live;
+            if (all_done)
+                for (auto& l : R) start(l);
+        }
+    }
+    out[0] = node_it;
+    out[1] = tri_it;
+    out[2] = rounds;
+    out[3] = finishing_rounds;
+}
+
 }  // extern "C"

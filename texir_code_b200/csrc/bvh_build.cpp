@@ -56,7 +56,10 @@ struct BNode {
 #define TX_COST_NODE 1.2
 #endif
 constexpr int kBins = TX_BINS;
-constexpr int kMaxLeaf = 3;       // triangles per leaf (BVH8 child slots hold at most 3)
+#ifndef TX_MAX_LEAF
+#define TX_MAX_LEAF 3
+#endif
+constexpr int kMaxLeaf = TX_MAX_LEAF;  // triangles per leaf (BVH8 child slots hold at most 3)
 constexpr int kSahDepthLimit = 40;  // beyond this depth fall back to object-median splits
 constexpr double kCostNode = TX_COST_NODE, kCostTri = 1.0;
 
