@@ -213,6 +213,25 @@ TX_HD int qbvh2_step(const SceneView& s, const RayQ& r, float tbest, int node, i
 #endif
 }
 
+#ifndef TX_SPECULATIVE
+#define TX_SPECULATIVE 0
+#endif
+TX_HD int qstack_pop(int* stack, int& sp, int& top) {
+#if TX_STACK_TOP
+    const int n = top;
+    top = stack[--sp];
+    return n;
+#else
+    (void)top;
+    return stack[--sp];
+#endif
+}
+TX_HD void qbvh2_leaf(const SceneView& s, const RayQ& r, int node, Hit& hit) {
+    const int ref = ~node;
+    const int first = ref >> 3, cnt = (ref & 7) + 1;
+    for (int i = 0; i < cnt; ++i) test_slot(s.tris2, first + i, r.o, r.d, hit);
+}
+
 TX_HD Hit trace_qbvh2(const SceneView& s, V3 o, V3 d) {
     RayQ r;
     rayq_setup(s, r, o, d);
@@ -223,6 +242,33 @@ TX_HD Hit trace_qbvh2(const SceneView& s, V3 o, V3 d) {
     stack[sp++] = kSentinel;
     int top = kSentinel;  // TX_STACK_TOP: register copy of the top entry (stack[0] then backs the final pop)
     int node = 0;
+#if TX_SPECULATIVE
+    // Speculative traversal (Aila & Laine 2009): the first leaf a lane finds is parked and the lane keeps walking with
+    // its old t_best; the node loop ends once every lane still in it has parked a leaf.  Modelled in
+    // profiles/simulate_warp_divergence.py ("1 postponed leaf, stop when all found").
+    int leaf = 0;  // 0 = none (leaf references are negative)
+    for (;;) {
+        while (node >= 0 && node != kSentinel) {
+            node = qbvh2_step(s, r, hit.t, node, stack, sp, top);
+            if (node < 0 && leaf == 0) {
+                leaf = node;
+                node = qstack_pop(stack, sp, top);
+            }
+#ifdef __CUDA_ARCH__
+            if (!__any_sync(__activemask(), leaf == 0)) break;
+#endif
+        }
+        while (leaf < 0) {
+            qbvh2_leaf(s, r, leaf, hit);
+            leaf = 0;
+            if (node < 0) {
+                leaf = node;
+                node = qstack_pop(stack, sp, top);
+            }
+        }
+        if (node == kSentinel) break;
+    }
+#else
     while (node != kSentinel) {
 #if defined(__CUDA_ARCH__) && TX_NODE_EXIT_BELOW
         // leave the node loop once fewer than TX_NODE_EXIT_BELOW lanes are still in it, so that the lanes waiting at
@@ -235,17 +281,11 @@ TX_HD Hit trace_qbvh2(const SceneView& s, V3 o, V3 d) {
         while (node >= 0 && node != kSentinel) node = qbvh2_step(s, r, hit.t, node, stack, sp, top);
 #endif
         if (node < 0) {
-            const int ref = ~node;
-            const int first = ref >> 3, cnt = (ref & 7) + 1;
-            for (int i = 0; i < cnt; ++i) test_slot(s.tris2, first + i, r.o, r.d, hit);
-#if TX_STACK_TOP
-            node = top;
-            top = stack[--sp];
-#else
-            node = stack[--sp];
-#endif
+            qbvh2_leaf(s, r, node, hit);
+            node = qstack_pop(stack, sp, top);
         }
     }
+#endif
     return hit;
 }
 
