@@ -282,26 +282,22 @@ void emul_trace_segments(EmulScene* s, const float* rays, int64_t R, int max_seg
         Hit hit;
         hit_reset(hit);
         int stack[kStackSize];
-        int sp = 0, top = kSentinel, node = 0, k = 0;
-        stack[sp++] = kSentinel;
-        while (node != kSentinel) {
+        int* sp = stack;
+        int top = kQSentinel, node = 0, k = 0;
+        *sp++ = kQSentinel;
+        while (node != kQSentinel) {
             int steps = 0;
-            while (node >= 0 && node != kSentinel) {
-                node = qbvh2_step(s->view, r, hit.t, node, stack, sp, top);
+            while (node >= 0) {
+                node = qbvh2_step(s->view, r, hit.t, node, sp, top);
                 ++steps;
             }
             int cnt = 0;
-            if (node < 0) {
+            if (node != kQSentinel) {
                 const int ref = ~node;
                 const int first = ref >> 3;
                 cnt = (ref & 7) + 1;
                 for (int i = 0; i < cnt; ++i) test_slot(s->view.tris2, first + i, r.o, r.d, hit);
-#if TX_STACK_TOP
-                node = top;
-                top = stack[--sp];
-#else
-                node = stack[--sp];
-#endif
+                node = qstack_pop(sp, top);
             }
             if (k < max_seg) {
                 seg[q * max_seg + k] = steps;
@@ -323,7 +319,8 @@ void emul_simulate_warp(EmulScene* s, const float* rays, int lanes, int Q, int s
         RayQ r;
         Hit hit;
         int stack[kStackSize];
-        int sp, top, node;
+        int* sp;
+        int top, node;
         int queue[8], nq;
     };
     std::vector<Lane> L((size_t)lanes);
@@ -332,35 +329,27 @@ void emul_simulate_warp(EmulScene* s, const float* rays, int lanes, int Q, int s
         rayq_setup(s->view, l.r, v3(rays[6 * q], rays[6 * q + 1], rays[6 * q + 2]),
                    v3(rays[6 * q + 3], rays[6 * q + 4], rays[6 * q + 5]));
         hit_reset(l.hit);
-        l.sp = 0;
-        l.stack[l.sp++] = kSentinel;
-        l.top = kSentinel;
+        l.sp = l.stack;
+        *l.sp++ = kQSentinel;
+        l.top = kQSentinel;
         l.node = 0;
         l.nq = 0;
     }
-    auto pop = [](Lane& l) {
-#if TX_STACK_TOP
-        int n = l.top;
-        l.top = l.stack[--l.sp];
-        return n;
-#else
-        return l.stack[--l.sp];
-#endif
-    };
+    auto pop = [](Lane& l) { return qstack_pop(l.sp, l.top); };
     int64_t node_it = 0, tri_it = 0, node_steps = 0, tri_tests = 0;
     for (;;) {
         bool any_alive = false;
-        for (auto& l : L) any_alive |= (l.node != kSentinel || l.nq > 0);
+        for (auto& l : L) any_alive |= (l.node != kQSentinel || l.nq > 0);
         if (!any_alive) break;
         // node phase
         for (;;) {
             bool stepped = false;
             for (auto& l : L) {
-                if (l.node >= 0 && l.node != kSentinel) {
-                    l.node = qbvh2_step(s->view, l.r, l.hit.t, l.node, l.stack, l.sp, l.top);
+                if (l.node >= 0) {
+                    l.node = qbvh2_step(s->view, l.r, l.hit.t, l.node, l.sp, l.top);
                     ++node_steps;
                     stepped = true;
-                    while (l.node < 0 && l.nq < Q) {  // park the leaf, keep walking
+                    while (l.node < 0 && l.node != kQSentinel && l.nq < Q) {  // park the leaf, keep walking
                         l.queue[l.nq++] = l.node;
                         l.node = pop(l);
                     }
@@ -370,7 +359,7 @@ void emul_simulate_warp(EmulScene* s, const float* rays, int lanes, int Q, int s
             ++node_it;
             if (stop_when_all_found) {
                 bool searching = false;
-                for (auto& l : L) searching |= (l.node != kSentinel && l.node >= 0 && l.nq == 0);
+                for (auto& l : L) searching |= (l.node >= 0 && l.nq == 0);
                 if (!searching) break;
             }
         }
@@ -378,7 +367,7 @@ void emul_simulate_warp(EmulScene* s, const float* rays, int lanes, int Q, int s
         int64_t worst = 0;
         for (auto& l : L) {
             int64_t mine = 0;
-            if (l.node < 0) {
+            if (l.node < 0 && l.node != kQSentinel) {
                 l.queue[l.nq++] = l.node;  // queue has Q + 1 slots
                 l.node = pop(l);
             }
@@ -412,7 +401,8 @@ void emul_simulate_stream(EmulScene* s, const float* rays, int total, int mode, 
         RayQ r;
         Hit hit;
         int stack[kStackSize];
-        int sp, top, node;
+        int* sp;
+        int top, node;
         bool live;
     };
     const int per_lane = mode == 1 ? 2 : 1;
@@ -421,27 +411,19 @@ void emul_simulate_stream(EmulScene* s, const float* rays, int total, int mode, 
     auto start = [&](Ray& l) {
         if (next >= total) {
             l.live = false;
-            l.node = kSentinel;
+            l.node = kQSentinel;
             return;
         }
         const float* q = rays + 6 * (size_t)next++;
         rayq_setup(s->view, l.r, v3(q[0], q[1], q[2]), v3(q[3], q[4], q[5]));
         hit_reset(l.hit);
-        l.sp = 0;
-        l.stack[l.sp++] = kSentinel;
-        l.top = kSentinel;
+        l.sp = l.stack;
+        *l.sp++ = kQSentinel;
+        l.top = kQSentinel;
         l.node = 0;
         l.live = true;
     };
-    auto pop = [](Ray& l) {
-#if TX_STACK_TOP
-        int n = l.top;
-        l.top = l.stack[--l.sp];
-        return n;
-#else
-        return l.stack[--l.sp];
-#endif
-    };
+    auto pop = [](Ray& l) { return qstack_pop(l.sp, l.top); };
     for (auto& l : R) start(l);
     int64_t node_it = 0, tri_it = 0, rounds = 0, finishing_rounds = 0;
     for (;;) {
@@ -453,8 +435,8 @@ void emul_simulate_stream(EmulScene* s, const float* rays, int total, int mode, 
             for (int lane = 0; lane < 32; ++lane)
                 for (int k = 0; k < per_lane; ++k) {
                     Ray& l = R[(size_t)lane * per_lane + k];
-                    if (l.live && l.node >= 0 && l.node != kSentinel) {
-                        l.node = qbvh2_step(s->view, l.r, l.hit.t, l.node, l.stack, l.sp, l.top);
+                    if (l.live && l.node >= 0) {
+                        l.node = qbvh2_step(s->view, l.r, l.hit.t, l.node, l.sp, l.top);
                         stepped = true;
                         break;  // one step per lane per iteration
                     }
@@ -469,14 +451,14 @@ void emul_simulate_stream(EmulScene* s, const float* rays, int total, int mode, 
             for (int k = 0; k < per_lane; ++k) {
                 Ray& l = R[(size_t)lane * per_lane + k];
                 if (!l.live) continue;
-                if (l.node < 0) {
+                if (l.node < 0 && l.node != kQSentinel) {
                     const int ref = ~l.node;
                     const int first = ref >> 3, cnt = (ref & 7) + 1;
                     for (int i = 0; i < cnt; ++i) test_slot(s->view.tris2, first + i, l.r.o, l.r.d, l.hit);
                     mine += cnt;
                     l.node = pop(l);
                 }
-                if (l.node == kSentinel) {
+                if (l.node == kQSentinel) {
                     l.live = false;
                     finished = true;
                 }

@@ -171,7 +171,7 @@ TX_HD float qplane_(uint32_t w, uint32_t sel, float S, float O) {
 #ifndef TX_NODE_EXIT_BELOW
 #define TX_NODE_EXIT_BELOW 0
 #endif
-TX_HD int qbvh2_step(const SceneView& s, const RayQ& r, float tbest, int node, int* stack, int& sp, int& top) {
+TX_HD int qbvh2_step(const SceneView& s, const RayQ& r, float tbest, int node, int*& sp, int& top) {
     const uint4* np = s.qnodes2 + 2 * (size_t)node;
     // two 128-bit loads: sm_100's 256-bit LDG (LDG.E.ENL2.256) was measured 23 % slower here -- it does not
     // allocate in L1, and the upper tree lives there
@@ -192,38 +192,42 @@ TX_HD int qbvh2_step(const SceneView& s, const RayQ& r, float tbest, int node, i
     // latency hides behind the next node step instead of sitting between the pop and the next node fetch
     if (h0 && h1) {
         const bool swap = t1n < t0n;
-        stack[sp++] = top;
+        *sp++ = top;
         top = swap ? c0 : c1;
         return swap ? c1 : c0;
     }
     if (h0) return c0;
     if (h1) return c1;
     const int popped = top;
-    top = stack[--sp];
+    top = *--sp;
     return popped;
 #else
     if (h0 && h1) {
         const bool swap = t1n < t0n;
-        stack[sp++] = swap ? c0 : c1;
+        *sp++ = swap ? c0 : c1;
         return swap ? c1 : c0;
     }
     if (h0) return c0;
     if (h1) return c1;
-    return stack[--sp];
+    return *--sp;
 #endif
 }
 
 #ifndef TX_SPECULATIVE
 #define TX_SPECULATIVE 0
 #endif
-TX_HD int qstack_pop(int* stack, int& sp, int& top) {
+// The QBVH2 walk keeps its stack pointer as an address (no index scaling per push / pop) and ends on a NEGATIVE
+// sentinel that no leaf reference can equal (leaf = ~((first_slot << 3) | (count - 1)) with first_slot < 2^27), so the
+// node loop tests `node >= 0` only.
+constexpr int kQSentinel = (int)0x80000000u;
+TX_HD int qstack_pop(int*& sp, int& top) {
 #if TX_STACK_TOP
     const int n = top;
-    top = stack[--sp];
+    top = *--sp;
     return n;
 #else
     (void)top;
-    return stack[--sp];
+    return *--sp;
 #endif
 }
 TX_HD void qbvh2_leaf(const SceneView& s, const RayQ& r, int node, Hit& hit) {
@@ -238,9 +242,9 @@ TX_HD Hit trace_qbvh2(const SceneView& s, V3 o, V3 d) {
     Hit hit;
     hit_reset(hit);
     int stack[kStackSize];
-    int sp = 0;
-    stack[sp++] = kSentinel;
-    int top = kSentinel;  // TX_STACK_TOP: register copy of the top entry (stack[0] then backs the final pop)
+    int* sp = stack;
+    *sp++ = kQSentinel;
+    int top = kQSentinel;  // TX_STACK_TOP: register copy of the top entry (stack[0] then backs the final pop)
     int node = 0;
 #if TX_SPECULATIVE
     // Speculative traversal (Aila & Laine 2009): the first leaf a lane finds is parked and the lane keeps walking with
@@ -248,11 +252,11 @@ TX_HD Hit trace_qbvh2(const SceneView& s, V3 o, V3 d) {
     // profiles/simulate_warp_divergence.py ("1 postponed leaf, stop when all found").
     int leaf = 0;  // 0 = none (leaf references are negative)
     for (;;) {
-        while (node >= 0 && node != kSentinel) {
-            node = qbvh2_step(s, r, hit.t, node, stack, sp, top);
-            if (node < 0 && leaf == 0) {
+        while (node >= 0) {
+            node = qbvh2_step(s, r, hit.t, node, sp, top);
+            if (node < 0 && node != kQSentinel && leaf == 0) {
                 leaf = node;
-                node = qstack_pop(stack, sp, top);
+                node = qstack_pop(sp, top);
             }
 #ifdef __CUDA_ARCH__
             if (!__any_sync(__activemask(), leaf == 0)) break;
@@ -261,28 +265,28 @@ TX_HD Hit trace_qbvh2(const SceneView& s, V3 o, V3 d) {
         while (leaf < 0) {
             qbvh2_leaf(s, r, leaf, hit);
             leaf = 0;
-            if (node < 0) {
+            if (node < 0 && node != kQSentinel) {
                 leaf = node;
-                node = qstack_pop(stack, sp, top);
+                node = qstack_pop(sp, top);
             }
         }
-        if (node == kSentinel) break;
+        if (node == kQSentinel) break;
     }
 #else
-    while (node != kSentinel) {
+    while (node != kQSentinel) {
 #if defined(__CUDA_ARCH__) && TX_NODE_EXIT_BELOW
         // leave the node loop once fewer than TX_NODE_EXIT_BELOW lanes are still in it, so that the lanes waiting at
         // a leaf do not wait for the last stragglers (they re-enter with the next round)
-        while (node >= 0 && node != kSentinel) {
-            node = qbvh2_step(s, r, hit.t, node, stack, sp, top);
+        while (node >= 0) {
+            node = qbvh2_step(s, r, hit.t, node, sp, top);
             if (__popc(__activemask()) < TX_NODE_EXIT_BELOW) break;
         }
 #else
-        while (node >= 0 && node != kSentinel) node = qbvh2_step(s, r, hit.t, node, stack, sp, top);
+        while (node >= 0) node = qbvh2_step(s, r, hit.t, node, sp, top);
 #endif
-        if (node < 0) {
+        if (node < 0 && node != kQSentinel) {
             qbvh2_leaf(s, r, node, hit);
-            node = qstack_pop(stack, sp, top);
+            node = qstack_pop(sp, top);
         }
     }
 #endif
