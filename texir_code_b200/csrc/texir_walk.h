@@ -121,7 +121,10 @@ struct RayQ {
 
 TX_HD uint32_t byte_perm_(uint32_t x, uint32_t y, uint32_t sel) {
 #ifdef __CUDA_ARCH__
-    return __byte_perm(x, y, sel);
+    // prmt.b32 directly: __byte_perm masks a run-time selector with 0x7777 first (one more ALU instruction)
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(y), "r"(sel));
+    return r;
 #else
     uint64_t both = ((uint64_t)y << 32) | x;
     uint32_t r = 0;
