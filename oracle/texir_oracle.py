@@ -29,7 +29,6 @@ reference has no golden vectors for it); see cast_rays_oracle.c.
 from __future__ import annotations
 
 import ctypes
-import math
 import os
 import subprocess
 from typing import Optional

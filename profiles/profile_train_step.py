@@ -1,6 +1,6 @@
 """Times the pieces of one stage-2 Mat training step (MaterialModel.forward + backward) on cuda:0 and prints the torch profiler
 kernel table:  python profiles/profile_train_step.py"""
-import sys, time, torch, numpy as np
+import sys, time, torch
 import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from texir_code_b200 import models, synth, ops
 dev = torch.device('cuda:0')

@@ -2,7 +2,6 @@
 written by the reference's own tools/padding_texture.py + cv2, against the oracle (scipy + torch on the CPU) at
 sizes it finishes in seconds, and through size-independent properties at the 4096^2 texture size.
 Everything on this row is index / byte work: the bar is bit-exact."""
-import os
 
 import numpy as np
 import pytest
