@@ -484,4 +484,24 @@ void emul_simulate_stream(EmulScene* s, const float* rays, int total, int mode, 
     out[3] = finishing_rounds;
 }
 
+// closest hits of R rays that all start at org[0..3), through the shared first descent (texir_walk.h)
+void emul_cast_rays_front(EmulScene* s, const float* org, const float* dirs, int64_t R, float* t, uint32_t* id, float* uv,
+                          int32_t* front_info) {
+    uint4 entries[kMaxFront];
+    int count = 0, start = 0;
+    const V3 o = v3(org[0], org[1], org[2]);
+    qbvh2_point_front(s->view, o, entries, &count, &start);
+    if (front_info) {
+        front_info[0] = count;
+        front_info[1] = start;
+    }
+    for (int64_t q = 0; q < R; ++q) {
+        Hit h = trace_qbvh2_front(s->view, o, v3(dirs[3 * q], dirs[3 * q + 1], dirs[3 * q + 2]), entries, count, start);
+        t[q] = h.t;
+        id[q] = h.prim;
+        uv[2 * q] = h.u;
+        uv[2 * q + 1] = h.v;
+    }
+}
+
 }  // extern "C"

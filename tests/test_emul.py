@@ -181,3 +181,40 @@ def test_quantised_nodes_on_degenerate_scenes(emul, oracle):
         t, i, uv = np.empty(len(rays), np.float32), np.empty(len(rays), np.uint32), np.empty((len(rays), 2), np.float32)
         emul.emul_cast_rays_fast(es.h, 1, rays.ctypes.data, len(rays), t.ctypes.data, i.ctypes.data, uv.ctypes.data)
         assert np.array_equal(i, i0) and np.array_equal(t, t0) and np.array_equal(uv, u0)
+
+
+def test_shared_first_descent_bit_exact_vs_plain_walk(emul):
+    """texir_walk.h: rays that share an origin start from the per-point chain of siblings (qbvh2_point_front /
+    trace_qbvh2_front) instead of the root; hits must be bit-identical to the plain QBVH2 walk, for origins on the
+    surface (+1e-2 n, the hot path's), in free space, at the scene centre, outside the scene and on seams (0,0,0)"""
+    from texir_code_b200 import synth
+    rng = np.random.default_rng(0)
+    for num_tris, clutter in ((4000, 6), (60000, 16)):
+        sc = synth.make_room_scene(num_tris, seed=666, clutter=clutter)
+        es = EmulScene(emul, sc.vertices, sc.triangles)
+        pos, _ = synth.sample_surface_points(sc, 24, seed=3, seam_fraction=0.1)
+        extra = np.array([[0, 0, 0], [100, 0, 0], [3.99, 1.49, 2.99], [0.3, -0.2, 0.5]], np.float32)
+        sizes = []
+        for p in np.concatenate([pos, extra]).astype(np.float32):
+            d = rng.normal(size=(256, 3)).astype(np.float32)
+            d[:5] = [[1, 0, 0], [0, -1, 0], [0, 0, 1], [0, 0, 0], [-1, 0, 0]]
+            rays = np.ascontiguousarray(np.concatenate([np.repeat(p[None], 256, 0), d], 1), np.float32)
+            t0, i0, u0 = np.empty(256, np.float32), np.empty(256, np.uint32), np.empty((256, 2), np.float32)
+            emul.emul_cast_rays_fast(es.h, 1, rays.ctypes.data, 256, t0.ctypes.data, i0.ctypes.data, u0.ctypes.data)
+            t1, i1, u1 = np.empty(256, np.float32), np.empty(256, np.uint32), np.empty((256, 2), np.float32)
+            info = np.zeros(2, np.int32)
+            p = np.ascontiguousarray(p)
+            d = np.ascontiguousarray(d)
+            emul.emul_cast_rays_front(es.h, p.ctypes.data, d.ctypes.data, 256, t1.ctypes.data, i1.ctypes.data, u1.ctypes.data,
+                                      info.ctypes.data)
+            assert np.array_equal(t0.view(np.uint32), t1.view(np.uint32))
+            assert np.array_equal(i0, i1) and np.array_equal(u0.view(np.uint32), u1.view(np.uint32))
+            sizes.append(int(info[0]))
+        assert max(sizes) >= 8 and min(sizes) == 0      # surface points share a long chain; outside points none
+    # single-triangle scene: the root's two children are the same leaf
+    one = EmulScene(emul, np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32), np.array([[0, 1, 2]], np.int32))
+    p = np.array([0.2, 0.2, 1.0], np.float32)
+    d = np.ascontiguousarray(np.array([[0, 0, -1], [0, 0, 1], [0.1, 0.1, -1]], np.float32))
+    t1, i1, u1 = np.empty(3, np.float32), np.empty(3, np.uint32), np.empty((3, 2), np.float32)
+    emul.emul_cast_rays_front(one.h, p.ctypes.data, d.ctypes.data, 3, t1.ctypes.data, i1.ctypes.data, u1.ctypes.data, None)
+    assert i1.tolist() == [0, 0xFFFFFFFF, 0] and t1[0] == 1.0 and np.isinf(t1[1])

@@ -94,6 +94,10 @@ static bool use_qnodes() {  // TEXIR_QNODES=0: walk the 64-byte float nodes inst
     static const bool on = env_int("TEXIR_QNODES", 1) != 0;
     return on;
 }
+static bool use_front() {  // TEXIR_FRONT=0: every ray walks from the root (no shared first descent)
+    static const bool on = env_int("TEXIR_FRONT", 1) != 0;
+    return on;
+}
 static int patch_bits(int N) {  // TEXIR_COHERENT_BITS=a overrides coherent_bits(N): shape of a warp's sample patch
     static const int forced = env_int("TEXIR_COHERENT_BITS", -1);
     if (forced < 0) return coherent_bits(N);
@@ -491,7 +495,7 @@ struct IrtPointSmem {
 #ifndef TX_LEAN_MINB
 #define TX_LEAN_MINB 12
 #endif
-template <int KIND>
+template <int KIND, bool FRONT = false>
 __global__ void __launch_bounds__(128, TX_LEAN_MINB) k_irradiance_lean(SceneView s, const float* __restrict__ pos,
                                                              const float* __restrict__ nrm,
                                                              const float* __restrict__ shift,
@@ -518,8 +522,13 @@ __global__ void __launch_bounds__(128, TX_LEAN_MINB) k_irradiance_lean(SceneView
     sm_acc[0][threadIdx.x] = 0.f;
     sm_acc[1][threadIdx.x] = 0.f;
     sm_acc[2][threadIdx.x] = 0.f;
-    __syncwarp();
     const V3 o = load3(pos, p);
+    // FRONT: the first descent of the walk is the same for all N rays of the point (texir_walk.h): lane 0 walks it
+    // once, the siblings along it wait in shared memory
+    __shared__ uint4 sm_front[FRONT ? 4 : 1][FRONT ? kMaxFront : 1];
+    __shared__ int sm_front_n[4], sm_front_start[4];
+    if (FRONT && lane == 0) qbvh2_point_front(s, o, sm_front[wid], &sm_front_n[wid], &sm_front_start[wid]);
+    __syncwarp();
     const volatile IrtPointSmem* q = &sm_pt[wid];
     const int M = (N + (1 << abits) - 1) >> abits;
     for (int c = 0; c < (1 << abits); ++c) {
@@ -536,7 +545,9 @@ __global__ void __launch_bounds__(128, TX_LEAN_MINB) k_irradiance_lean(SceneView
                 float s1 = shift_wrap_clamp(radical_inverse(i), q->sh1);
                 d = sample_dir<false>(f, mode, s0, s1, 0.f).d;
             }
-            Hit h = trace<KIND>(s, o, d);
+            Hit h = FRONT ? trace_qbvh2_front(s, o, d, sm_front[wid], ((volatile int*)sm_front_n)[wid],
+                                              ((volatile int*)sm_front_start)[wid])
+                          : trace<KIND>(s, o, d);
             V3 L = fetch_radiance(s, h);
             float ndl = clamp01(rn_dot(v3(q->nx, q->ny, q->nz), d));
             sm_acc[0][threadIdx.x] += L.x * ndl;
@@ -680,15 +691,18 @@ struct ShadePointSmem {
 #ifndef TX_SHADE_LEAN_MINB
 #define TX_SHADE_LEAN_MINB 10
 #endif
-template <int KIND, bool TANGENT>
+template <int KIND, bool TANGENT, bool FRONT = false>
 __global__ void __launch_bounds__(128, TX_SHADE_LEAN_MINB) k_shade_lean(SceneView s, ShadeArgs a) {
     __shared__ ShadePointSmem sm_pt[4];
     __shared__ float sm_acc[TANGENT ? 9 : 6][128];
+    __shared__ uint4 sm_front[FRONT ? 4 : 1][FRONT ? kMaxFront : 1];  // shared first descent, see k_irradiance_lean
+    __shared__ int sm_front_n[4], sm_front_start[4];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, tid = threadIdx.x;
     int64_t p = (int64_t)blockIdx.x * 4 + wid;
     const bool live = p < a.P;
     if (!live) p = a.P - 1;
     const V3 o = load3(a.pos, p);
+    if (FRONT && lane == 0) qbvh2_point_front(s, o, sm_front[wid], &sm_front_n[wid], &sm_front_start[wid]);
     if (lane == 0) {
         ShadePointSmem& q = sm_pt[wid];
         const V3 n = load3(a.nrm, p);
@@ -735,7 +749,9 @@ __global__ void __launch_bounds__(128, TX_SHADE_LEAN_MINB) k_shade_lean(SceneVie
                     l = reflect_dir(ds.d, sp.v, &vdh_raw);
                     w = spec_weight<TANGENT>(sp, f, ds, l, vdh_raw, &dw);
                 }
-                Hit h = trace<KIND>(s, o, l);
+                Hit h = FRONT ? trace_qbvh2_front(s, o, l, sm_front[wid], ((volatile int*)sm_front_n)[wid],
+                                                  ((volatile int*)sm_front_start)[wid])
+                              : trace<KIND>(s, o, l);
                 V3 L = fetch_radiance(s, h);
                 sm_acc[0][tid] += L.x * w;
                 sm_acc[1][tid] += L.y * w;
@@ -763,7 +779,9 @@ __global__ void __launch_bounds__(128, TX_SHADE_LEAN_MINB) k_shade_lean(SceneVie
                     wgt = (a.mode_diff == MODE_COSINE) ? 1.0f
                                                        : clamp01(rn_dot(v3(q->sp.n.x, q->sp.n.y, q->sp.n.z), d));
                 }
-                Hit h = trace<KIND>(s, o, d);
+                Hit h = FRONT ? trace_qbvh2_front(s, o, d, sm_front[wid], ((volatile int*)sm_front_n)[wid],
+                                                  ((volatile int*)sm_front_start)[wid])
+                              : trace<KIND>(s, o, d);
                 V3 L = fetch_radiance(s, h);
                 sm_acc[3][tid] += L.x * wgt;
                 sm_acc[4][tid] += L.y * wgt;
@@ -1467,7 +1485,10 @@ int texir_irradiance_fwd(const texir_scene* sc, const float* pos, const float* n
     if (sc->info.bvh_kind == TEXIR_BVH8)
         k_irradiance<8><<<g, 128, 0, (cudaStream_t)stream>>>(sc->view, pos, nrm, shift, order, P, N, mode, G, ab, E);
     else if (stream_mode() == 3 && G == 32 && use_qnodes())
-        k_irradiance_lean<4><<<g, 128, 0, (cudaStream_t)stream>>>(sc->view, pos, nrm, shift, order, P, N, mode, ab, E);
+        if (use_front())
+            k_irradiance_lean<4, true><<<g, 128, 0, (cudaStream_t)stream>>>(sc->view, pos, nrm, shift, order, P, N, mode, ab, E);
+        else
+            k_irradiance_lean<4><<<g, 128, 0, (cudaStream_t)stream>>>(sc->view, pos, nrm, shift, order, P, N, mode, ab, E);
     else if (stream_mode() == 3 && G == 32)
         k_irradiance_lean<3><<<g, 128, 0, (cudaStream_t)stream>>>(sc->view, pos, nrm, shift, order, P, N, mode, ab, E);
     else if (stream_mode() >= 2 && use_qnodes())
@@ -1513,7 +1534,10 @@ static int launch_shade(const texir_scene* sc, const ShadeArgs& a, void* stream)
     if (sc->info.bvh_kind == TEXIR_BVH8)
         k_shade<8, TANGENT><<<g, 128, 0, (cudaStream_t)stream>>>(sc->view, a);
     else if (stream_mode() == 3 && a.G == 32 && use_qnodes())
-        k_shade_lean<4, TANGENT><<<g, 128, 0, (cudaStream_t)stream>>>(sc->view, a);
+        if (use_front())
+            k_shade_lean<4, TANGENT, true><<<g, 128, 0, (cudaStream_t)stream>>>(sc->view, a);
+        else
+            k_shade_lean<4, TANGENT><<<g, 128, 0, (cudaStream_t)stream>>>(sc->view, a);
     else if (stream_mode() >= 2 && use_qnodes())
         k_shade<4, TANGENT><<<g, 128, 0, (cudaStream_t)stream>>>(sc->view, a);
     else if (stream_mode() >= 2)

@@ -296,4 +296,87 @@ TX_HD Hit trace_qbvh2(const SceneView& s, V3 o, V3 d) {
     return hit;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Shared first descent.  All rays of a surface point start at the same origin, and a near-first walk always
+// descends first into the child whose box CONTAINS the origin (its entry distance is 0): the chain of nodes from the
+// root to the leaf around the origin is the same for every ray of the point, only the siblings along it are
+// direction dependent.  qbvh2_point_front() walks that chain once per point and records the siblings (their three
+// plane words + reference, 16 bytes each); trace_qbvh2_front() then starts a ray by testing just those boxes -- one
+// box instead of two per level, read from shared memory instead of a dependent global load -- pushes the hit ones
+// (shallow first, so the deepest lies on top exactly as the plain walk leaves its stack) and continues with the
+// ordinary loop from the node where the chain ended.  Same visiting order, same hits, bit for bit.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kMaxFront = 48;
+
+TX_HD bool qbox_contains_(const SceneView& s, uint32_t wx, uint32_t wy, uint32_t wz, V3 o) {
+    const float lx = tx_fma((float)(wx & 0xFFFFu), s.qstep[0], s.qmin[0]), hx = tx_fma((float)(wx >> 16), s.qstep[0], s.qmin[0]);
+    const float ly = tx_fma((float)(wy & 0xFFFFu), s.qstep[1], s.qmin[1]), hy = tx_fma((float)(wy >> 16), s.qstep[1], s.qmin[1]);
+    const float lz = tx_fma((float)(wz & 0xFFFFu), s.qstep[2], s.qmin[2]), hz = tx_fma((float)(wz >> 16), s.qstep[2], s.qmin[2]);
+    return o.x >= lx && o.x <= hx && o.y >= ly && o.y <= hy && o.z >= lz && o.z <= hz;
+}
+
+// one thread per point: entries[0 .. *count) = siblings along the containing chain, root side first;
+// *start = the node (inner index or leaf reference) where the chain ends and the ordinary walk takes over
+TX_HD void qbvh2_point_front(const SceneView& s, V3 o, uint4* entries, int* count, int* start) {
+    int node = 0, n = 0;
+    while (node >= 0 && n < kMaxFront) {
+        const uint4* np = s.qnodes2 + 2 * (size_t)node;
+        const uint4 q0 = ld_nc_u4(np + 0), q1 = ld_nc_u4(np + 1);
+        const bool in0 = qbox_contains_(s, q0.x, q0.y, q0.z, o), in1 = qbox_contains_(s, q0.w, q1.x, q1.y, o);
+        uint4 e;
+        if (in0) {  // also when the origin lies in both boxes: the plain walk breaks that tie towards child 0
+            e.x = q0.w; e.y = q1.x; e.z = q1.y; e.w = q1.w;
+            node = (int)q1.z;
+        } else if (in1) {
+            e.x = q0.x; e.y = q0.y; e.z = q0.z; e.w = q1.z;
+            node = (int)q1.w;
+        } else {
+            break;  // the origin is in neither child: the ordinary walk starts here
+        }
+        entries[n++] = e;
+    }
+    *count = n;
+    *start = node;
+}
+
+TX_HD Hit trace_qbvh2_front(const SceneView& s, V3 o, V3 d, const uint4* entries, int count, int start) {
+    RayQ r;
+    rayq_setup(s, r, o, d);
+    Hit hit;
+    hit_reset(hit);
+    int stack[kStackSize];
+    int* sp = stack;
+    *sp++ = kQSentinel;
+    int top = kQSentinel;
+    {
+        const uint32_t fx = r.selx ^ 0x0022u, fy = r.sely ^ 0x0022u, fz = r.selz ^ 0x0022u;
+        for (int k = 0; k < count; ++k) {
+            const uint4 e = entries[k];  // one 128-bit load (shared memory in the kernels: a broadcast)
+            const uint32_t wx = e.x, wy = e.y, wz = e.z;
+            const int ref = (int)e.w;
+            const float tn = fmaxf(fmaxf(qplane_(wx, r.selx, r.S.x, r.O.x), qplane_(wy, r.sely, r.S.y, r.O.y)),
+                                   fmaxf(qplane_(wz, r.selz, r.S.z, r.O.z), 0.0f));
+            const float tf = fminf(fminf(qplane_(wx, fx, r.S.x, r.O.x), qplane_(wy, fy, r.S.y, r.O.y)),
+                                   qplane_(wz, fz, r.S.z, r.O.z));
+            if (tn <= tf) {
+#if TX_STACK_TOP
+                *sp++ = top;
+                top = ref;
+#else
+                *sp++ = ref;
+#endif
+            }
+        }
+    }
+    int node = start;
+    while (node != kQSentinel) {
+        while (node >= 0) node = qbvh2_step(s, r, hit.t, node, sp, top);
+        if (node < 0 && node != kQSentinel) {
+            qbvh2_leaf(s, r, node, hit);
+            node = qstack_pop(sp, top);
+        }
+    }
+    return hit;
+}
+
 }  // namespace texir
