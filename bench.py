@@ -325,7 +325,7 @@ def run_ours(args):
             },
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic_bytes_per_launch(P, SPP), "peak_source": peak_src,
-                         "kernel": "k_irradiance_lean<4> (QBVH2)" if info["bvh_kind"] == 2 else "k_irradiance<8>", "kernel_ms": k_ms, "alg_bytes_per_ray_sample": balg},
+                         "kernel": "k_irradiance_lean<4,FRONT> (QBVH2, shared first descent)" if info["bvh_kind"] == 2 else "k_irradiance<8>", "kernel_ms": k_ms, "alg_bytes_per_ray_sample": balg},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / args.steps, "checksum": checksum},
             "gpu_launches": launches,
