@@ -164,6 +164,20 @@ TEXIR_API int texir_shade_bwd(const texir_scene* scene, const float* nrm, const 
                               int mode_diff, float eps, const float* g_rgb, const float* drgb_drough,
                               const float* ediff, float* g_albedo, float* g_rough, float* g_irr, void* stream);
 
+/* The same backward, accumulated straight into TEXTURE SPACE by the same kernel: instead of per-pixel g_albedo /
+ * g_rough, every pixel's gradient is scattered with atomics (red.global.add.f32) into the gradient textures of
+ * materials_a [Ha,Wa,3] and materials_r [Hr,Wr,1] at its uv [P,2] -- the transpose of the dr.texture fetch of
+ * models/mat_nvdiffrast.py:131-139 ('linear-mipmap-linear' with uv_da [P,4] and La / Lr pyramid levels in g_mips_*,
+ * plain bilinear when uv_da is NULL and La = Lr = 0).  Gradient textures and pyramids are zero-initialised by the
+ * caller; texir_texture_mip_fold then folds each pyramid into its level 0.  Either texture may be NULL. */
+TEXIR_API int texir_shade_bwd_tex(const texir_scene* scene, const float* nrm, const float* albedo, const float* rough,
+                                  const float* pos, const float* cam, const float* irr, const float* shift_spec,
+                                  const float* shift_diff, int64_t P, int N_spec, int N_diff, int mode_spec,
+                                  int mode_diff, float eps, const float* g_rgb, const float* drgb_drough,
+                                  const float* ediff, const float* uv, const float* uv_da, float* g_tex_a,
+                                  float* g_mips_a, int Ha, int Wa, int La, float* g_tex_r, float* g_mips_r, int Hr,
+                                  int Wr, int Lr, void* stream);
+
 /* ---- stand-alone BRDF reductions with the reference's tensor signatures --------------------
  * specular_reflectance(lighting, h, n, v, l, roughness): mat_nvdiffrast.py:260-279.
  * lighting, h, l [P,N,3]; n, v [P,3]; rough [P]; out [P,3] (NOT divided by N, as in the reference). */

@@ -237,3 +237,59 @@ def test_gbuffer_mvp_one_launch_equals_rays_plus_gbuffer(tx, cuda_device, scene_
     bad = torch.zeros(1, 4, 4, device=cuda_device)                            # singular mvp: no hits, no NaNs
     z = tx.gbuffer_mvp(sc, bad, cam.to(cuda_device), 4)
     assert bool((z["mask"] == 0).all()) and bool(torch.isfinite(z["position"]).all())
+
+
+@pytest.mark.parametrize("mode", ["stash", "recompute"])
+def test_shade_textured_backward_lands_in_texture_space(tx, cuda_device, scene_golden, mode):
+    """ops.shade_textured (ONE backward kernel: render backward + atomic scatter into the material textures' gradients,
+    then the pyramid folds) against the two-step path texture_fetch -> shade -> autograd, for the mip-mapped filter
+    (stage 2), the bilinear roughness-only routing (stage 1), and a mixed call"""
+    name, g = scene_golden
+    sc = tx.Scene(g["vertices"], g["triangles"], g["triangle_uvs"], device=cuda_device)
+    sc.set_texture(torch.from_numpy(g["texture"]))
+    P = len(g["pos"])
+    rng = np.random.default_rng(12)
+    ta = T(rng.uniform(0.1, 0.9, (32, 32, 3)).astype(np.float32), cuda_device).requires_grad_(True)
+    tr = T(rng.uniform(0.05, 0.7, (64, 64, 1)).astype(np.float32), cuda_device).requires_grad_(True)
+    texc = T(rng.uniform(0, 1, (P, 2)).astype(np.float32), cuda_device)
+    texd = T((rng.normal(size=(P, 4)) * 0.03).astype(np.float32), cuda_device)
+    nrm, pos, cam, irr = (T(g[k], cuda_device) for k in ("nrm", "pos", "cam", "irr"))
+    shift = T(g["render_e14_16_shift"], cuda_device)
+    g_rgb = T(g["g_rgb"], cuda_device)
+
+    def two_step(da_a, da_r, use_a):
+        ta.grad = tr.grad = None
+        a = tx.ops.texture_fetch(ta, texc, da_a, max_mip_level=13)
+        r = tx.ops.texture_fetch(tr, texc, da_r, max_mip_level=13)
+        rgb = tx.shade(sc, nrm, a if use_a else a.detach(), r, pos, cam, irr, shift, num_spec=16, backward=mode)
+        rgb.backward(g_rgb)
+        return rgb.detach(), None if ta.grad is None else ta.grad.clone(), tr.grad.clone()
+
+    def fused(da, use_a, albedo_mipmap=True, rough_mipmap=True):
+        ta.grad = tr.grad = None
+        with torch.no_grad():
+            a = tx.ops.texture_fetch(ta, texc, da if albedo_mipmap else None, max_mip_level=13)
+            r = tx.ops.texture_fetch(tr, texc, da if rough_mipmap else None, max_mip_level=13)
+        n0 = tx.launch_count()
+        rgb = tx.ops.shade_textured(sc, ta if use_a else None, tr, nrm, a, r, pos, cam, irr, shift, texc, da, num_spec=16,
+                                    albedo_mipmap=albedo_mipmap, rough_mipmap=rough_mipmap, max_mip_level=13, backward=mode)
+        n1 = tx.launch_count()
+        rgb.backward(g_rgb)
+        return rgb.detach(), None if ta.grad is None else ta.grad.clone(), tr.grad.clone(), tx.launch_count() - n1, n1 - n0
+
+    # stage 2: both textures mip-mapped
+    ref = two_step(texd, texd, True)
+    got = fused(texd, True)
+    assert torch.equal(got[0], ref[0])
+    assert rel_l2(got[1].cpu().numpy(), ref[1].cpu().numpy()) < 1e-5 and rel_l2(got[2].cpu().numpy(), ref[2].cpu().numpy()) < 1e-5
+    assert got[4] == 1                                            # forward: the render kernel alone
+    assert got[3] == 1 + tx.ops.mip_levels(32, 32, 13) + tx.ops.mip_levels(64, 64, 13)   # backward: one kernel + the folds
+    # stage 1: albedo detached, roughness fetched bilinearly
+    ref = two_step(None, None, False)
+    got = fused(None, False)
+    assert got[1] is None and ref[1] is None
+    assert rel_l2(got[2].cpu().numpy(), ref[2].cpu().numpy()) < 1e-5 and got[3] == 1
+    # mixed: mip-mapped albedo next to a bilinear roughness, one call
+    ref = two_step(texd, None, True)
+    got = fused(texd, True, rough_mipmap=False)
+    assert rel_l2(got[1].cpu().numpy(), ref[1].cpu().numpy()) < 1e-5 and rel_l2(got[2].cpu().numpy(), ref[2].cpu().numpy()) < 1e-5

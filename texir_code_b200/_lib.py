@@ -57,6 +57,8 @@ SIGNATURES = {
     "texir_gbuffer_uv_da": (c_int, [_P, _P, _P, _P, c_int64, _P, _P]),
     "texir_shade_fwd": (c_int, [_P] + [_P] * 8 + [c_int64, c_int, c_int, c_int, c_int, c_float, _P, _P, _P, _P]),
     "texir_shade_bwd": (c_int, [_P] + [_P] * 8 + [c_int64, c_int, c_int, c_int, c_int, c_float] + [_P] * 7),
+    "texir_shade_bwd_tex": (c_int, [_P] + [_P] * 8 + [c_int64, c_int, c_int, c_int, c_int, c_float] + [_P] * 5
+                            + [_P, _P, c_int, c_int, c_int, _P, _P, c_int, c_int, c_int, _P]),
     "texir_specular_reflectance": (c_int, [_P] * 6 + [c_int64, c_int, c_float, _P, _P]),
     "texir_specular_reflectance_bwd": (c_int, [_P] * 6 + [c_int64, c_int, c_float] + [_P] * 6),
     "texir_diffuse_reflectance": (c_int, [_P] * 4 + [c_int64, c_int, c_int, _P, _P]),

@@ -589,7 +589,32 @@ struct ShadeArgs {
     float* g_albedo;
     float* g_rough;
     float* g_irr;
+    // backward straight into texture space (texir_shade_bwd_tex): per-pixel uv (+ uv_da for the mip-mapped filter, else
+    // bilinear) and the gradient textures of albedo (3 channels) and roughness (1 channel)
+    const float* uv;
+    const float* uv_da;
+    TexGrad ga, gr;
 };
+
+// gradient of one pixel's albedo / roughness, written per pixel and / or scattered into the material textures' gradients
+__device__ __forceinline__ void shade_emit_material_grads(const ShadeArgs& a, int64_t p, const float ga[3], float gr,
+                                                          bool have_a, bool have_r) {
+    if (have_a && a.g_albedo) {
+        a.g_albedo[3 * p + 0] = ga[0];
+        a.g_albedo[3 * p + 1] = ga[1];
+        a.g_albedo[3 * p + 2] = ga[2];
+    }
+    if (have_r && a.g_rough) a.g_rough[p] = gr;
+    if (a.uv && (a.ga.tex || a.gr.tex)) {
+        const float u = __ldg(a.uv + 2 * p), v = __ldg(a.uv + 2 * p + 1);
+        float4 da = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a.uv_da) da = __ldg(reinterpret_cast<const float4*>(a.uv_da) + p);
+        if (have_a && a.ga.tex)
+            tex_scatter_point(a.ga, u, v, mip_lod(da.x, da.y, da.z, da.w, a.ga.H, a.ga.W, a.ga.L), ga);
+        if (have_r && a.gr.tex)
+            tex_scatter_point(a.gr, u, v, mip_lod(da.x, da.y, da.z, da.w, a.gr.H, a.gr.W, a.gr.L), &gr);
+    }
+}
 
 // per-point epilogue of k_shade / k_shade_lean (lane gl == 0 of a live point)
 template <bool TANGENT>
@@ -620,12 +645,8 @@ __device__ __forceinline__ void shade_epilogue(const ShadeArgs& a, int64_t p, fl
         }
     } else {
         V3 g = load3(a.g_rgb, p);
-        if (a.g_albedo) {
-            a.g_albedo[3 * p + 0] = g.x * dfac[0];
-            a.g_albedo[3 * p + 1] = g.y * dfac[1];
-            a.g_albedo[3 * p + 2] = g.z * dfac[2];
-        }
-        if (a.g_rough) a.g_rough[p] = (g.x * dx + g.y * dy + g.z * dz) * inv_ns;
+        const float ga[3] = {g.x * dfac[0], g.y * dfac[1], g.z * dfac[2]};
+        shade_emit_material_grads(a, p, ga, (g.x * dx + g.y * dy + g.z * dz) * inv_ns, true, true);
         if (a.g_irr) {
             V3 al = load3(a.albedo, p);
             bool lit = a.N_diff == 0;
@@ -802,7 +823,9 @@ __global__ void __launch_bounds__(256) k_shade_bwd_stash(ShadeArgs a) {
     int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= a.P) return;
     V3 g = load3(a.g_rgb, p);
-    if (a.g_albedo) {
+    const bool want_a = a.g_albedo || a.ga.tex, want_r = a.g_rough || a.gr.tex;
+    float ga[3] = {0.f, 0.f, 0.f}, gr = 0.f;
+    if (want_a) {
         V3 fac;
         if (a.N_diff > 0) {
             fac = load3(a.ediff, p);
@@ -810,14 +833,15 @@ __global__ void __launch_bounds__(256) k_shade_bwd_stash(ShadeArgs a) {
             V3 irr = load3(a.irr, p);
             fac = v3(irr.x / kPi, irr.y / kPi, irr.z / kPi);
         }
-        a.g_albedo[3 * p + 0] = g.x * fac.x;
-        a.g_albedo[3 * p + 1] = g.y * fac.y;
-        a.g_albedo[3 * p + 2] = g.z * fac.z;
+        ga[0] = g.x * fac.x;
+        ga[1] = g.y * fac.y;
+        ga[2] = g.z * fac.z;
     }
-    if (a.g_rough) {
+    if (want_r) {
         V3 d = load3(a.drgb_drough, p);
-        a.g_rough[p] = g.x * d.x + g.y * d.y + g.z * d.z;
+        gr = g.x * d.x + g.y * d.y + g.z * d.z;
     }
+    shade_emit_material_grads(a, p, ga, gr, want_a, want_r);
     if (a.g_irr) {
         V3 al = load3(a.albedo, p);
         bool lit = a.N_diff == 0;
@@ -1565,6 +1589,49 @@ int texir_shade_fwd(const texir_scene* sc, const float* nrm, const float* albedo
     return drgb_drough ? launch_shade<true>(sc, a, stream) : launch_shade<false>(sc, a, stream);
 }
 
+static int shade_bwd_impl(const char* fn, const texir_scene* sc, ShadeArgs& a, void* stream) {
+    if (shade_common(fn, sc, a)) return 1;
+    if (a.P == 0) return 0;
+    if (!a.g_rgb) {
+        g_err = std::string(fn) + ": g_rgb is NULL";
+        return 1;
+    }
+    DeviceGuard guard(sc->info.device);
+    // rays are needed only for a gradient whose forward stash is missing
+    const bool want_r = a.g_rough || a.gr.tex, want_a = a.g_albedo || a.ga.tex;
+    const bool need_rays = (want_r && !a.drgb_drough) || (want_a && a.N_diff > 0 && !a.ediff);
+    if (!need_rays) {
+        k_shade_bwd_stash<<<grid_for(a.P, 256), 256, 0, (cudaStream_t)stream>>>(a);
+        return finish_launch("k_shade_bwd_stash");
+    }
+    return launch_shade<true>(sc, a, stream);
+}
+
+int texir_shade_bwd_tex(const texir_scene* sc, const float* nrm, const float* albedo, const float* rough,
+                        const float* pos, const float* cam, const float* irr, const float* shift_spec,
+                        const float* shift_diff, int64_t P, int N_spec, int N_diff, int mode_spec, int mode_diff,
+                        float eps, const float* g_rgb, const float* drgb_drough, const float* ediff, const float* uv,
+                        const float* uv_da, float* g_tex_a, float* g_mips_a, int Ha, int Wa, int La, float* g_tex_r,
+                        float* g_mips_r, int Hr, int Wr, int Lr, void* stream) {
+    ShadeArgs a{};
+    a.nrm = nrm; a.albedo = albedo; a.rough = rough; a.pos = pos; a.cam = cam; a.irr = irr;
+    a.shift_spec = shift_spec; a.shift_diff = shift_diff;
+    a.P = P; a.N_spec = N_spec; a.N_diff = N_diff; a.mode_spec = mode_spec; a.mode_diff = mode_diff; a.eps = eps;
+    a.g_rgb = g_rgb;
+    a.drgb_drough = const_cast<float*>(drgb_drough);
+    a.ediff = const_cast<float*>(ediff);
+    a.uv = uv; a.uv_da = uv_da;
+    a.ga = TexGrad{g_tex_a, g_mips_a, Ha, Wa, 3, La};
+    a.gr = TexGrad{g_tex_r, g_mips_r, Hr, Wr, 1, Lr};
+    if (!uv) TX_FAIL("texir_shade_bwd_tex: uv is NULL");
+    if (!g_tex_a && !g_tex_r) TX_FAIL("texir_shade_bwd_tex: no gradient texture given");
+    if ((g_tex_a && (Ha <= 0 || Wa <= 0 || La < 0 || La != mip_level_count(Ha, Wa, La) || (La > 0 && !g_mips_a))) ||
+        (g_tex_r && (Hr <= 0 || Wr <= 0 || Lr < 0 || Lr != mip_level_count(Hr, Wr, Lr) || (Lr > 0 && !g_mips_r))))
+        TX_FAIL("texir_shade_bwd_tex: bad gradient-texture shape / level count");
+    if (!uv_da && (La > 0 || Lr > 0)) TX_FAIL("texir_shade_bwd_tex: mip levels given without uv_da");
+    return shade_bwd_impl("texir_shade_bwd_tex", sc, a, stream);
+}
+
 int texir_shade_bwd(const texir_scene* sc, const float* nrm, const float* albedo, const float* rough,
                     const float* pos, const float* cam, const float* irr, const float* shift_spec,
                     const float* shift_diff, int64_t P, int N_spec, int N_diff, int mode_spec, int mode_diff,
@@ -1577,17 +1644,7 @@ int texir_shade_bwd(const texir_scene* sc, const float* nrm, const float* albedo
     a.g_rgb = g_rgb; a.g_albedo = g_albedo; a.g_rough = g_rough; a.g_irr = g_irr;
     a.drgb_drough = const_cast<float*>(drgb_drough);
     a.ediff = const_cast<float*>(ediff);
-    if (shade_common("texir_shade_bwd", sc, a)) return 1;
-    if (P == 0) return 0;
-    if (!g_rgb) TX_FAIL("texir_shade_bwd: g_rgb is NULL");
-    DeviceGuard guard(sc->info.device);
-    // rays are needed only for a gradient whose forward stash is missing
-    const bool need_rays = (g_rough && !drgb_drough) || (g_albedo && N_diff > 0 && !ediff);
-    if (!need_rays) {
-        k_shade_bwd_stash<<<grid_for(P, 256), 256, 0, (cudaStream_t)stream>>>(a);
-        return finish_launch("k_shade_bwd_stash");
-    }
-    return launch_shade<true>(sc, a, stream);
+    return shade_bwd_impl("texir_shade_bwd", sc, a, stream);
 }
 
 int texir_specular_reflectance(const float* lighting, const float* h, const float* n, const float* v, const float* l,

@@ -98,4 +98,33 @@ TX_HD MipLod mip_lod(float dudx, float dudy, float dvdx, float dvdy, int H, int 
     return m;
 }
 
+// a texture-space gradient target: level 0 [H,W,C] and the packed pyramid (levels 1..L), both zero-initialised by the
+// caller; tex == nullptr means "no texture-space gradient wanted"
+struct TexGrad {
+    float* tex;
+    float* mips;
+    int H, W, C, L;
+};
+
+#ifdef __CUDACC__
+// transpose of the (tri)linear fetch for ONE pixel: g[0..C) scattered with atomics into both levels of detail
+__device__ __forceinline__ void tex_scatter_point(const TexGrad& t, float u, float v, const MipLod& m, const float* g) {
+    for (int k = 0; k < 2; ++k) {
+        const int l = k ? m.level1 : m.level0;
+        const float wl = k ? m.frac : 1.0f - m.frac;
+        if (k && m.frac == 0.f) break;
+        const int h = mip_dim(t.H, l), w = mip_dim(t.W, l);
+        float* dst = l ? t.mips + mip_offset(t.H, t.W, t.C, l) : t.tex;
+        const TexTap tp = tex_tap(u, v, h, w);
+        for (int c = 0; c < t.C; ++c) {
+            const float gc = g[c] * wl;
+            atomicAdd(dst + (int64_t)tp.i00 * t.C + c, gc * tp.w00);
+            atomicAdd(dst + (int64_t)tp.i10 * t.C + c, gc * tp.w10);
+            atomicAdd(dst + (int64_t)tp.i01 * t.C + c, gc * tp.w01);
+            atomicAdd(dst + (int64_t)tp.i11 * t.C + c, gc * tp.w11);
+        }
+    }
+}
+#endif
+
 }  // namespace texir

@@ -80,23 +80,10 @@ __global__ void __launch_bounds__(256) k_texture_scatter_mip(const float* __rest
                                                              float* __restrict__ g_tex, float* __restrict__ g_mips) {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P) return;
-    const float u = __ldg(uv + 2 * p), v = __ldg(uv + 2 * p + 1);
-    const MipLod m = lod_of(uv_da, p, H, W, L);
-    for (int k = 0; k < 2; ++k) {
-        const int l = k ? m.level1 : m.level0;
-        const float wl = k ? m.frac : 1.0f - m.frac;
-        if (k && m.frac == 0.f) break;
-        const int h = mip_dim(H, l), w = mip_dim(W, l);
-        float* t = l ? g_mips + mip_offset(H, W, C, l) : g_tex;
-        const TexTap tp = tex_tap(u, v, h, w);
-        for (int c = 0; c < C; ++c) {
-            const float g = __ldg(g_out + p * C + c) * wl;
-            atomicAdd(t + (int64_t)tp.i00 * C + c, g * tp.w00);
-            atomicAdd(t + (int64_t)tp.i10 * C + c, g * tp.w10);
-            atomicAdd(t + (int64_t)tp.i01 * C + c, g * tp.w01);
-            atomicAdd(t + (int64_t)tp.i11 * C + c, g * tp.w11);
-        }
-    }
+    const TexGrad t{g_tex, g_mips, H, W, C, L};
+    float g[4];
+    for (int c = 0; c < C; ++c) g[c] = __ldg(g_out + p * C + c);
+    tex_scatter_point(t, __ldg(uv + 2 * p), __ldg(uv + 2 * p + 1), lod_of(uv_da, p, H, W, L), g);
 }
 
 static inline unsigned blocks_for(int64_t n) { return (unsigned)((n + 255) / 256); }

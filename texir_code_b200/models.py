@@ -184,6 +184,22 @@ class MaterialModel(HotPathMixin, nn.Module):
             roughness = roughness.reshape(*normal.shape[:-1], 1)
         return self.render(normal, albedo, roughness, points, cam_position, irr)
 
+    def _render_textured(self, normal, albedo, roughness, points, cam_position, irr, texc, texd, tex_a, tex_r):
+        """render() for materials that were fetched from textures: same result dict, but the render's backward kernel
+        scatters straight into the gradients of tex_a / tex_r (ops.shade_textured) instead of handing per-pixel
+        gradients to a separate scatter; falls back to the plain composition when the model is not `fused` or relights"""
+        if not getattr(self, "fused", True) or getattr(self, "relighting", False):
+            return self.render(normal, albedo, roughness, points, cam_position, irr)
+        lead = normal.shape[:-1]
+        n, p = normal.reshape(-1, 3), points.reshape(-1, 3)
+        shift_spec = draw_shift(n.shape[0], n.device)
+        rgb = ops.shade_textured(self._scene(), tex_a, tex_r, n, albedo.reshape(-1, 3), roughness.reshape(-1, 1), p,
+                                 cam_position, irr.reshape(-1, 3), shift_spec, texc, texd, num_spec=int(self.sample_l[1]),
+                                 max_mip_level=self.max_mip_level, mode_spec=self.sample_type[1],
+                                 eps=getattr(self, "brdf_eps", 1e-14), backward=getattr(self, "backward_mode", "stash"))
+        return {"rgb": rgb.reshape(*lead, 3), "albedo": albedo, "normal": normal.detach(),
+                "position": (points + 2e-2 * normal).detach()}
+
     def gbuffers(self, mvp: torch.Tensor, cam_position: torch.Tensor) -> dict:
         """mat_nvdiffrast.py:116-128: position / normal / texc / texd / mask of the 6 cube faces"""
         dev = self.scene.device
@@ -225,9 +241,11 @@ class MaterialModel(HotPathMixin, nn.Module):
         elif stage == 0:
             res = {"rgb": irr * albedo / np.pi, "albedo": albedo, "normal": normal, "position": pos + 1e-1 * normal}
         elif stage == 1:
-            res = self.render(normal, albedo.detach(), roughness_womipmap, pos + 1e-2 * normal, cam_position, irr)
+            res = self._render_textured(normal, albedo.detach(), roughness_womipmap, pos + 1e-2 * normal, cam_position, irr,
+                                        texc, None, None, self.materials_r)
         elif stage == 2:
-            res = self.render(normal, albedo, roughness, pos + 1e-2 * normal, cam_position, irr)
+            res = self._render_textured(normal, albedo, roughness, pos + 1e-2 * normal, cam_position, irr, texc, texd,
+                                        self.materials_a, self.materials_r)
         else:
             raise ValueError("stage must be -1, 0, 1 or 2")
         res.update({"empty_mask": mask, "roughness_womipmap": roughness_womipmap, "roughness": roughness})

@@ -242,6 +242,108 @@ def shade(scene: Scene, normal, albedo, roughness, points, cam_position, irr, sh
                         int(num_spec), int(num_diff), _lib.MODES[mode_spec], _lib.MODES[mode_diff], float(eps), backward)
 
 
+class _ShadeTextured(torch.autograd.Function):
+    """_Shade whose backward kernel accumulates straight into TEXTURE space: the per-pixel albedo / roughness values
+    come in detached, the gradients go out as gradients of the material textures (texir_shade_bwd_tex: the render
+    backward and the atomic scatter of dr.texture's backward in one launch, then the pyramid folds)."""
+
+    @staticmethod
+    def forward(ctx, scene, materials_a, materials_r, normal, albedo_px, rough_px, points, cam, irr, shift_spec,
+                shift_diff, texc, texd, levels_a, levels_r, N_spec, N_diff, mode_spec, mode_diff, eps, backward_mode):
+        dev = normal.device
+        P = int(normal.shape[0])
+        nrm, alb, pos = _f32c(normal), _f32c(albedo_px), _f32c(points)
+        rough = _f32c(rough_px).reshape(-1)
+        camc = _f32c(cam, dev).reshape(3)
+        irrc = _f32c(irr) if irr is not None else None
+        shs = _f32c(shift_spec, dev).reshape(P, 2)
+        shd = _f32c(shift_diff, dev).reshape(P, 2) if N_diff > 0 else None
+        need_a = materials_a is not None and materials_a.requires_grad
+        need_r = materials_r is not None and materials_r.requires_grad
+        stash = backward_mode == "stash"
+        rgb = torch.empty(P, 3, dtype=torch.float32, device=dev)
+        drgb = torch.empty(P, 3, dtype=torch.float32, device=dev) if (stash and need_r) else None
+        ediff = torch.empty(P, 3, dtype=torch.float32, device=dev) if (stash and N_diff > 0 and need_a) else None
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().texir_shade_fwd(scene.handle, _ptr(nrm), _ptr(alb), _ptr(rough), _ptr(pos), _ptr(camc),
+                                                   _ptr(irrc), _ptr(shs), _ptr(shd), P, N_spec, N_diff, mode_spec,
+                                                   mode_diff, eps, _ptr(rgb), _ptr(drgb), _ptr(ediff),
+                                                   _stream_ptr(dev)), "texir_shade_fwd")
+        ctx.scene = scene
+        ctx.cfg = (P, N_spec, N_diff, mode_spec, mode_diff, eps, levels_a, levels_r)
+        ctx.shape_a = tuple(materials_a.shape) if materials_a is not None else None
+        ctx.shape_r = tuple(materials_r.shape) if materials_r is not None else None
+        ctx.have = (drgb is not None, ediff is not None, irrc is not None, shd is not None, texd is not None)
+        saved = [nrm, alb, rough, pos, camc, shs, _f32c(texc).reshape(P, 2)]
+        for t in (irrc, shd, drgb, ediff, _f32c(texd).reshape(P, 4) if texd is not None else None):
+            if t is not None:
+                saved.append(t)
+        ctx.save_for_backward(*saved)
+        return rgb
+
+    @staticmethod
+    def backward(ctx, g_rgb):
+        saved = list(ctx.saved_tensors)
+        nrm, alb, rough, pos, camc, shs, uv = saved[:7]
+        rest = saved[7:]
+        have_drgb, have_ediff, have_irr, have_shd, have_da = ctx.have
+        irrc = rest.pop(0) if have_irr else None
+        shd = rest.pop(0) if have_shd else None
+        drgb = rest.pop(0) if have_drgb else None
+        ediff = rest.pop(0) if have_ediff else None
+        uv_da = rest.pop(0) if have_da else None
+        P, N_spec, N_diff, mode_spec, mode_diff, eps, La, Lr = ctx.cfg
+        dev = nrm.device
+        need = ctx.needs_input_grad  # (scene, materials_a, materials_r, ...)
+        lib = _lib.load()
+        g = _f32c(g_rgb).reshape(P, 3)
+
+        def target(shape, L, wanted):
+            if not wanted:
+                return None, None, 0, 0
+            H, W, C = shape
+            g_tex = torch.zeros(H, W, C, dtype=torch.float32, device=dev)
+            g_mips = torch.zeros(max(int(lib.texir_texture_mip_elems(H, W, C, L)), 1), dtype=torch.float32, device=dev)
+            return g_tex, g_mips, H, W
+
+        ga, gma, Ha, Wa = target(ctx.shape_a, La, need[1])
+        gr, gmr, Hr, Wr = target(ctx.shape_r, Lr, need[2])
+        if ga is None and gr is None:
+            return (None,) * 21
+        with torch.cuda.device(dev):
+            st = _stream_ptr(dev)
+            _lib.check(lib.texir_shade_bwd_tex(
+                ctx.scene.handle, _ptr(nrm), _ptr(alb), _ptr(rough), _ptr(pos), _ptr(camc), _ptr(irrc), _ptr(shs), _ptr(shd),
+                P, N_spec, N_diff, mode_spec, mode_diff, eps, _ptr(g), _ptr(drgb), _ptr(ediff), _ptr(uv), _ptr(uv_da),
+                _ptr(ga), _ptr(gma), Ha, Wa, La, _ptr(gr), _ptr(gmr), Hr, Wr, Lr, st), "texir_shade_bwd_tex")
+            if ga is not None and La > 0:
+                _lib.check(lib.texir_texture_mip_fold(_ptr(ga), _ptr(gma), Ha, Wa, 3, La, st), "texir_texture_mip_fold")
+            if gr is not None and Lr > 0:
+                _lib.check(lib.texir_texture_mip_fold(_ptr(gr), _ptr(gmr), Hr, Wr, 1, Lr, st), "texir_texture_mip_fold")
+        return (None, ga, gr) + (None,) * 18
+
+
+def shade_textured(scene: Scene, materials_a: Optional[torch.Tensor], materials_r: Optional[torch.Tensor], normal,
+                   albedo_px, rough_px, points, cam_position, irr, shift_spec, texc, texd=None, *, num_spec: int,
+                   albedo_mipmap: bool = True, rough_mipmap: bool = True, max_mip_level: Optional[int] = None,
+                   shift_diff=None, num_diff: int = 0, mode_spec: str = "importance", mode_diff: str = "uniform",
+                   eps: float = TINY_TINY_NUMBER, backward: str = "stash") -> torch.Tensor:
+    """Fused render whose gradients land in the material TEXTURES: albedo_px [P,3] / rough_px [P,1] are the values
+    fetched at texc [P,2] (texd [P,4] for the mip-mapped filter) from materials_a [Ha,Wa,3] / materials_r [Hr,Wr,1]
+    (pass None for a texture that must not receive a gradient, e.g. materials_a in the reference's stage 1); the
+    backward is ONE kernel that differentiates the render and scatters into both textures' gradients with atomics."""
+    _need_cuda("shade_textured", normal)
+    if backward not in ("stash", "recompute"):
+        raise ValueError("backward must be 'stash' or 'recompute'")
+    mip = texd is not None
+    La = mip_levels(int(materials_a.shape[0]), int(materials_a.shape[1]), max_mip_level) if (materials_a is not None and mip and albedo_mipmap) else 0
+    Lr = mip_levels(int(materials_r.shape[0]), int(materials_r.shape[1]), max_mip_level) if (materials_r is not None and mip and rough_mipmap) else 0
+    da = texd if (La > 0 or Lr > 0) else None  # a texture with 0 levels is scattered bilinearly whatever uv_da says
+    return _ShadeTextured.apply(scene, materials_a, materials_r, normal, albedo_px.detach(), rough_px.detach(), points,
+                                cam_position, irr, shift_spec, shift_diff, texc, da, La, Lr, int(num_spec), int(num_diff),
+                                _lib.MODES[mode_spec], _lib.MODES[mode_diff], float(eps), backward)
+
+
 # --------------------------------------------------------------------------------------------------
 # fused IrT batch
 # --------------------------------------------------------------------------------------------------
