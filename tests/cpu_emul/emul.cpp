@@ -189,7 +189,8 @@ void emul_shade(EmulScene* s, int kind, const float* nrm, const float* albedo, c
 
 // ---- IrT post-processing (texir_post.h): the two passes of k_pad_columns / k_pad_rows, texel by texel ----
 void emul_pad_texture(const float* img, int H, int W, int C, float* out, int32_t* index) {
-    std::vector<int> near((size_t)H * W), g((size_t)W);
+    std::vector<int> near((size_t)H * W);
+    std::vector<unsigned short> g((size_t)W), nr((size_t)W);
     for (int j = 0; j < W; ++j) {
         int last = -1;
         for (int i = 0; i < H; ++i) {
@@ -204,12 +205,12 @@ void emul_pad_texture(const float* img, int H, int W, int C, float* out, int32_t
         }
     }
     for (int i = 0; i < H; ++i) {
-        const int* nr = near.data() + (size_t)i * W;
-        const int maxl = pad_build_envelope(nr, W, i, g.data());
+        for (int x = 0; x < W; ++x) nr[x] = near[(size_t)i * W + x] < 0 ? kPadNone : (unsigned short)near[(size_t)i * W + x];
+        const int maxl = pad_build_envelope(nr.data(), W, i, g.data());
         for (int x = 0; x < W; ++x) {
             int sr = i, sc = x, rr = i, rc = x;
-            if (nr[x] != i && maxl >= 0) {
-                sc = pad_query_envelope(nr, g.data(), maxl, i, x);
+            if ((int)nr[x] != i && maxl >= 0) {
+                sc = pad_query_envelope(nr.data(), g.data(), maxl, i, x);
                 sr = nr[sc];
                 rr = pad_source_index(sr, H);
                 rc = pad_source_index(sc, W);

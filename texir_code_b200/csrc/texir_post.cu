@@ -29,32 +29,59 @@ using texir_host::finish_launch;
         if (e_ != cudaSuccess) return fail(std::string(#call) + ": " + cudaGetErrorString(e_), 2); \
     } while (0)
 
-__global__ void __launch_bounds__(128) k_pad_columns(const float* __restrict__ img, int H, int W, int C,
-                                                     int32_t* __restrict__ near_row) {
+// one thread per column; rows are taken eight at a time so that eight rows' loads are in flight per thread (only W
+// threads exist: the pass is latency bound, not bandwidth bound)
+__global__ void __launch_bounds__(32) k_pad_columns(const float* __restrict__ img, int H, int W, int C,
+                                                    int32_t* __restrict__ near_row) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= W) return;
     int last = -1;
-    for (int i = 0; i < H; ++i) {
-        if (!pad_texel_empty(img + ((int64_t)i * W + j) * C, C)) last = i;
-        near_row[(int64_t)i * W + j] = last;
+    for (int i0 = 0; i0 < H; i0 += 8) {
+        bool empty[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int i = i0 + k < H ? i0 + k : H - 1;
+            const float* px = img + ((int64_t)i * W + j) * C;
+            float s = __ldg(px);
+            for (int c = 1; c < C; ++c) s = __fadd_rn(s, __ldg(px + c));  // pad_texel_empty
+            empty[k] = s == 0.0f;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (i0 + k >= H) break;
+            if (!empty[k]) last = i0 + k;
+            near_row[(int64_t)(i0 + k) * W + j] = last;
+        }
     }
     int next = -1;
-    for (int i = H - 1; i >= 0; --i) {
-        const int up = near_row[(int64_t)i * W + j];
-        if (up == i) next = i;
-        near_row[(int64_t)i * W + j] = pad_pick_row(i, up, next);
+    for (int i0 = H - 1; i0 >= 0; i0 -= 8) {
+        int up[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) up[k] = near_row[(int64_t)(i0 - k >= 0 ? i0 - k : 0) * W + j];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int i = i0 - k;
+            if (i < 0) break;
+            if (up[k] == i) next = i;
+            near_row[(int64_t)i * W + j] = pad_pick_row(i, up[k], next);
+        }
     }
 }
 
-__global__ void __launch_bounds__(256) k_pad_rows(const float* __restrict__ img, int H, int W, int C,
-                                                  const int32_t* __restrict__ near_row, float* __restrict__ out,
-                                                  int32_t* __restrict__ index) {
-    extern __shared__ int sm_pad[];
-    int* nr = sm_pad;      // nearest non-empty row of every column, for this row
-    int* g = sm_pad + W;   // envelope: kept columns
+// one warp-sized CTA per row: the row's sites as 16-bit values in shared memory (4 bytes per column, so 14 rows are
+// resident per SM at W = 4096), lane 0 builds the envelope, all lanes query it
+__global__ void __launch_bounds__(64) k_pad_rows(const float* __restrict__ img, int H, int W, int C,
+                                                 const int32_t* __restrict__ near_row, float* __restrict__ out,
+                                                 int32_t* __restrict__ index) {
+    extern __shared__ unsigned short sm_pad[];
+    unsigned short* nr = sm_pad;      // nearest non-empty row of every column, for this row
+    unsigned short* g = sm_pad + W;   // envelope: kept columns
     __shared__ int s_maxl;
     const int i = blockIdx.x;
-    for (int x = threadIdx.x; x < W; x += blockDim.x) nr[x] = near_row[(int64_t)i * W + x];
+    for (int x = threadIdx.x; x < W; x += blockDim.x) {
+        const int r = near_row[(int64_t)i * W + x];
+        nr[x] = r < 0 ? kPadNone : (unsigned short)r;
+    }
     __syncthreads();
     if (threadIdx.x == 0) s_maxl = pad_build_envelope(nr, W, i, g);
     __syncthreads();
@@ -62,7 +89,7 @@ __global__ void __launch_bounds__(256) k_pad_rows(const float* __restrict__ img,
     for (int x = threadIdx.x; x < W; x += blockDim.x) {
         int sr = i, sc = x;        // nearest non-empty texel
         int rr = i, rc = x;        // texel the value is read from
-        if (nr[x] != i && maxl >= 0) {
+        if ((int)nr[x] != i && maxl >= 0) {
             sc = pad_query_envelope(nr, g, maxl, i, x);
             sr = nr[sc];
             rr = pad_source_index(sr, H);
@@ -175,14 +202,14 @@ int texir_pad_texture(const float* img, int H, int W, int C, float* out, int32_t
     if (H <= 0 || W <= 0 || C <= 0 || C > 4) return fail("texir_pad_texture: bad shape");
     if (!img || !out || !scratch) return fail("texir_pad_texture: NULL argument");
     if (img == out) return fail("texir_pad_texture: in-place padding is not supported");
-    const size_t smem = 2 * sizeof(int) * (size_t)W;
-    if (smem > 200 * 1024) return fail("texir_pad_texture: width above 25600 texels");
+    if (H >= 32768 || W >= 32768) return fail("texir_pad_texture: sides must be below 32768 texels");
+    const size_t smem = 2 * sizeof(unsigned short) * (size_t)W;
     texir_host::ScopedDevice guard(texir_host::device_of(out));
     if (smem > 48 * 1024)
         TXP_CUDA(cudaFuncSetAttribute(k_pad_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_pad_columns<<<(W + 127) / 128, 128, 0, (cudaStream_t)stream>>>(img, H, W, C, scratch);
+    k_pad_columns<<<(W + 31) / 32, 32, 0, (cudaStream_t)stream>>>(img, H, W, C, scratch);
     if (int rc = finish_launch("k_pad_columns")) return rc;
-    k_pad_rows<<<H, 256, smem, (cudaStream_t)stream>>>(img, H, W, C, scratch, out, index);
+    k_pad_rows<<<H, 64, smem, (cudaStream_t)stream>>>(img, H, W, C, scratch, out, index);
     return finish_launch("k_pad_rows");
 }
 

@@ -35,35 +35,38 @@ TX_HD int pad_pick_row(int i, int up, int down) {
     return (i - up) <= (down - i) ? up : down;
 }
 
-// squared distance of texel (i, x) to the site of column j, whose nearest non-empty row is rj
-TX_HD int64_t pad_dist2(int i, int x, int rj, int j) {
-    const int64_t dy = (int64_t)rj - i, dx = (int64_t)j - x;
+// squared distance of texel (i, x) to the site of column j, whose nearest non-empty row is rj (< 2^31 for sides < 32768)
+TX_HD int pad_dist2(int i, int x, int rj, int j) {
+    const int dy = rj - i, dx = j - x;
     return dy * dy + dx * dx;
 }
 
 // phase 2a: lower envelope of the row's sites, scipy's _VoronoiFT construction loop.  nr[j] = nearest non-empty
-// row of column j (or -1), g = stack of kept columns; returns the index of the last kept site (-1: none).
-TX_HD int pad_build_envelope(const int* nr, int W, int i, int* g) {
+// row of column j (kPadNone: the column has none), g = stack of kept columns; returns the index of the last kept site
+// (-1: none).  The dominance test is evaluated in float64 exactly as scipy evaluates it (every term is an integer
+// below 2^53, so the arithmetic is exact).
+constexpr unsigned short kPadNone = 0xFFFFu;
+TX_HD int pad_build_envelope(const unsigned short* nr, int W, int i, unsigned short* g) {
     int l = -1;
     for (int ii = 0; ii < W; ++ii) {
-        if (nr[ii] < 0) continue;
-        const int64_t dw = (int64_t)nr[ii] - i, wR = dw * dw;
+        if (nr[ii] == kPadNone) continue;
+        const double dw = (double)((int)nr[ii] - i), wR = dw * dw;
         while (l >= 1) {
             const int idx1 = g[l], idx2 = g[l - 1];
-            const int64_t a = idx1 - idx2, b = ii - idx1, c = a + b;
-            const int64_t du = (int64_t)nr[idx2] - i, dv = (int64_t)nr[idx1] - i;
-            const int64_t uR = du * du, vR = dv * dv;
-            if (c * vR - b * uR - a * wR - a * b * c <= 0) break;  // idx1 still owns part of the row
+            const double a = (double)(idx1 - idx2), b = (double)(ii - idx1), c = a + b;
+            const double du = (double)((int)nr[idx2] - i), dv = (double)((int)nr[idx1] - i);
+            const double uR = du * du, vR = dv * dv;
+            if (c * vR - b * uR - a * wR - a * b * c <= 0.0) break;  // idx1 still owns part of the row
             --l;
         }
-        g[++l] = ii;
+        g[++l] = (unsigned short)ii;
     }
     return l;
 }
 
 // phase 2b: scipy's query loop advances while the NEXT site is strictly nearer; along the envelope that
 // predicate holds for a prefix of the sites, so a binary search finds the same site for every x independently.
-TX_HD int pad_query_envelope(const int* nr, const int* g, int maxl, int i, int x) {
+TX_HD int pad_query_envelope(const unsigned short* nr, const unsigned short* g, int maxl, int i, int x) {
     int lo = 0, hi = maxl;
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
