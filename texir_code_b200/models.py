@@ -216,6 +216,9 @@ class MaterialModel(HotPathMixin, nn.Module):
     def forward(self, mvp, id, cam_position, stage=1):
         """mat_nvdiffrast.py:105-191, same arguments and result keys (rgb, albedo, normal, position, empty_mask,
         roughness_womipmap, roughness); stage -1 / 0 / 1 / 2 as in the reference."""
+        for name in ("materials_a", "materials_r", "irrt"):
+            if not hasattr(self, name):
+                raise ValueError("MaterialModel.forward needs %s (constructor: materials_a_res / materials_r_res / irrt)" % name)
         dev = self.scene.device
         cam_position = cam_position.to(dev)
         gb = self.gbuffers(mvp, cam_position)
