@@ -599,3 +599,42 @@ def test_material_optimisation_loop_recovers_textures(tx, gscene, cuda_device):
         losses.append(float(loss.detach()))
     assert losses[-1] < 0.6 * losses[0], (losses[0], losses[-1])
     assert set(mm.state_dict()) >= {"materials_a", "materials_r"}  # the reference's checkpoint keys
+
+
+def test_shared_first_descent_switch_changes_no_bit(cuda_device, tmp_path):
+    """TEXIR_FRONT=0 (every ray walks from the root) and the default (shared first descent) must give bit-identical
+    irradiance and render results; the switch is read once per process, hence two subprocesses"""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, %r)
+import texir_code_b200 as tx
+from texir_code_b200 import synth
+dev = torch.device('cuda:0')
+sc = synth.make_room_scene(60000, seed=666, clutter=16)
+tex = torch.from_numpy(synth.make_radiance_texture(512, seed=666))
+scene = tx.Scene(sc.vertices, sc.triangles, sc.triangle_uvs, device=dev)
+scene.set_texture(tex)
+pos, nrm = synth.sample_surface_points(sc, 3000, seed=3, seam_fraction=0.05)
+pos[:3] = [[0, 0, 0], [50, 0, 0], [3.99, 1.49, 2.99]]
+torch.manual_seed(1)
+sh = torch.rand(3000, 1, 2).to(dev)
+P = torch.from_numpy(pos).to(dev); N = torch.from_numpy(nrm).to(dev)
+E = tx.irradiance(scene, P, N, sh, 256)
+rough, albedo, irr, g = synth.make_materials(3000, seed=2)
+rgb = tx.shade(scene, N, torch.from_numpy(albedo).to(dev), torch.from_numpy(rough).to(dev), P, torch.tensor([0.1, 0.2, 0.3], device=dev),
+               torch.from_numpy(irr).to(dev), sh, num_spec=64)
+np.savez(sys.argv[1], E=E.cpu().numpy(), rgb=rgb.cpu().numpy())
+""" % root
+    outs = []
+    for flag in ("0", "1"):
+        path = str(tmp_path / ("front%s.npz" % flag))
+        env = dict(os.environ, TEXIR_FRONT=flag)
+        subprocess.run([sys.executable, "-c", code, path], check=True, env=env, timeout=600)
+        outs.append(np.load(path))
+    assert np.array_equal(outs[0]["E"].view(np.uint32), outs[1]["E"].view(np.uint32))
+    assert np.array_equal(outs[0]["rgb"].view(np.uint32), outs[1]["rgb"].view(np.uint32))
+    assert np.isfinite(outs[0]["E"]).all() and float(outs[0]["E"].sum()) > 0
