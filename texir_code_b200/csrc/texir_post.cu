@@ -10,9 +10,11 @@
 //                   source texel.  Two launches, a few ms for 4096^2; it runs once per generated texture.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/texir_b200.h"
@@ -240,15 +242,27 @@ int texir_hdr_write_host(const char* path, const uint8_t* rgbe_host, int H, int 
     if (W < 8 || W > 0x7fff) {  // run-length coding is not allowed: flat quadruplets
         out.insert(out.end(), rgbe_host, rgbe_host + (size_t)H * W * 4);
     } else {
-        std::vector<unsigned char> plane((size_t)W * 4);
-        for (int y = 0; y < H; ++y) {
-            const uint8_t* row = rgbe_host + (size_t)y * W * 4;
-            const unsigned char mark[4] = {2, 2, (unsigned char)(W >> 8), (unsigned char)(W & 0xFF)};
-            out.insert(out.end(), mark, mark + 4);
-            for (int x = 0; x < W; ++x)
-                for (int c = 0; c < 4; ++c) plane[(size_t)c * W + x] = row[4 * x + c];
-            for (int c = 0; c < 4; ++c) rle_plane(plane.data() + (size_t)c * W, W, out);
-        }
+        // scanlines are coded independently: bands of rows go to host threads, the pieces are appended in order
+        const int workers = (int)std::max(1u, std::min(std::min(std::thread::hardware_concurrency(), 16u), (unsigned)((H + 63) / 64)));
+        std::vector<std::vector<unsigned char>> piece((size_t)workers);
+        auto band = [&](int w) {
+            std::vector<unsigned char> plane((size_t)W * 4);
+            std::vector<unsigned char>& dst = piece[(size_t)w];
+            const int y0 = (int)((int64_t)H * w / workers), y1 = (int)((int64_t)H * (w + 1) / workers);
+            for (int y = y0; y < y1; ++y) {
+                const uint8_t* row = rgbe_host + (size_t)y * W * 4;
+                const unsigned char mark[4] = {2, 2, (unsigned char)(W >> 8), (unsigned char)(W & 0xFF)};
+                dst.insert(dst.end(), mark, mark + 4);
+                for (int x = 0; x < W; ++x)
+                    for (int c = 0; c < 4; ++c) plane[(size_t)c * W + x] = row[4 * x + c];
+                for (int c = 0; c < 4; ++c) rle_plane(plane.data() + (size_t)c * W, W, dst);
+            }
+        };
+        std::vector<std::thread> pool;
+        for (int w = 1; w < workers; ++w) pool.emplace_back(band, w);
+        band(0);
+        for (auto& t : pool) t.join();
+        for (const auto& pc : piece) out.insert(out.end(), pc.begin(), pc.end());
     }
     FILE* fp = fopen(path, "wb");
     if (!fp) return fail(std::string("texir_hdr_write_host: cannot create ") + path);
