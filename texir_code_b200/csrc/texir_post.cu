@@ -4,7 +4,7 @@
 // models/mat_nvdiffrast.py:73,89).  The run-length file format around the codec is host C++ at the end.
 //
 // Padding is an exact Euclidean feature transform in two passes over a [H,W] int32 scratch:
-//   k_pad_columns   one thread per column (coalesced across a warp): nearest non-empty row above / below
+//   k_pad_columns_a/b  one thread per (column, row segment), coalesced across a warp: nearest non-empty row above / below
 //   k_pad_rows      one CTA per row, the row's sites in shared memory: lower envelope (one thread; W steps of
 //                   integer work, ~0.1 ms for 4096), then every thread binary-searches its texels and copies the
 //                   source texel.  Two launches, a few ms for 4096^2; it runs once per generated texture.
@@ -31,18 +31,23 @@ using texir_host::finish_launch;
         if (e_ != cudaSuccess) return fail(std::string(#call) + ": " + cudaGetErrorString(e_), 2); \
     } while (0)
 
-// one thread per column; rows are taken eight at a time so that eight rows' loads are in flight per thread (only W
-// threads exist: the pass is latency bound, not bandwidth bound)
-__global__ void __launch_bounds__(32) k_pad_columns(const float* __restrict__ img, int H, int W, int C,
-                                                    int32_t* __restrict__ near_row) {
+// Column pass, split into row segments so that W x S threads work instead of W (blockIdx.y = segment):
+//   k_pad_columns_a  within the segment, downwards: nearest non-empty row at or above each texel (-1: none in the
+//                    segment so far); per (segment, column) the first and the last non-empty row of the segment
+//   k_pad_columns_b  carries those across segments and sweeps upwards: nearest of "above" and "below", ties -> above
+// Rows are taken eight at a time so that eight rows' loads are in flight per thread.
+__global__ void __launch_bounds__(32) k_pad_columns_a(const float* __restrict__ img, int H, int W, int C, int rows_per_seg,
+                                                      int32_t* __restrict__ near_row, int32_t* __restrict__ seg_first,
+                                                      int32_t* __restrict__ seg_last) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= W) return;
-    int last = -1;
-    for (int i0 = 0; i0 < H; i0 += 8) {
+    const int r0 = blockIdx.y * rows_per_seg, r1 = min(H, r0 + rows_per_seg);
+    int last = -1, first = -1;
+    for (int i0 = r0; i0 < r1; i0 += 8) {
         bool empty[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            const int i = i0 + k < H ? i0 + k : H - 1;
+            const int i = i0 + k < r1 ? i0 + k : r1 - 1;
             const float* px = img + ((int64_t)i * W + j) * C;
             float s = __ldg(px);
             for (int c = 1; c < C; ++c) s = __fadd_rn(s, __ldg(px + c));  // pad_texel_empty
@@ -50,22 +55,40 @@ __global__ void __launch_bounds__(32) k_pad_columns(const float* __restrict__ im
         }
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            if (i0 + k >= H) break;
-            if (!empty[k]) last = i0 + k;
+            if (i0 + k >= r1) break;
+            if (!empty[k]) {
+                last = i0 + k;
+                if (first < 0) first = last;
+            }
             near_row[(int64_t)(i0 + k) * W + j] = last;
         }
     }
-    int next = -1;
-    for (int i0 = H - 1; i0 >= 0; i0 -= 8) {
+    seg_first[(int64_t)blockIdx.y * W + j] = first;
+    seg_last[(int64_t)blockIdx.y * W + j] = last;
+}
+
+__global__ void __launch_bounds__(32) k_pad_columns_b(int H, int W, int rows_per_seg, int segs,
+                                                      const int32_t* __restrict__ seg_first,
+                                                      const int32_t* __restrict__ seg_last,
+                                                      int32_t* __restrict__ near_row) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= W) return;
+    const int seg = blockIdx.y;
+    const int r0 = seg * rows_per_seg, r1 = min(H, r0 + rows_per_seg);
+    int carry_up = -1, next = -1;
+    for (int s = seg - 1; s >= 0 && carry_up < 0; --s) carry_up = seg_last[(int64_t)s * W + j];
+    for (int s = seg + 1; s < segs && next < 0; ++s) next = seg_first[(int64_t)s * W + j];
+    for (int i0 = r1 - 1; i0 >= r0; i0 -= 8) {
         int up[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) up[k] = near_row[(int64_t)(i0 - k >= 0 ? i0 - k : 0) * W + j];
+        for (int k = 0; k < 8; ++k) up[k] = near_row[(int64_t)(i0 - k >= r0 ? i0 - k : r0) * W + j];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             const int i = i0 - k;
-            if (i < 0) break;
-            if (up[k] == i) next = i;
-            near_row[(int64_t)i * W + j] = pad_pick_row(i, up[k], next);
+            if (i < r0) break;
+            const int u = up[k] >= 0 ? up[k] : carry_up;
+            if (u == i) next = i;
+            near_row[(int64_t)i * W + j] = pad_pick_row(i, u, next);
         }
     }
 }
@@ -209,8 +232,20 @@ int texir_pad_texture(const float* img, int H, int W, int C, float* out, int32_t
     texir_host::ScopedDevice guard(texir_host::device_of(out));
     if (smem > 48 * 1024)
         TXP_CUDA(cudaFuncSetAttribute(k_pad_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_pad_columns<<<(W + 31) / 32, 32, 0, (cudaStream_t)stream>>>(img, H, W, C, scratch);
-    if (int rc = finish_launch("k_pad_columns")) return rc;
+    const int segs = std::max(1, std::min(32, (H + 63) / 64)), rows_per_seg = (H + segs - 1) / segs;
+    int32_t* seg_ends = nullptr;  // [2][segs][W]: first / last non-empty row of every (segment, column)
+    TXP_CUDA(cudaMallocAsync((void**)&seg_ends, 2 * sizeof(int32_t) * (size_t)segs * W, (cudaStream_t)stream));
+    const dim3 cgrid((W + 31) / 32, segs);
+    k_pad_columns_a<<<cgrid, 32, 0, (cudaStream_t)stream>>>(img, H, W, C, rows_per_seg, scratch, seg_ends,
+                                                            seg_ends + (size_t)segs * W);
+    int rc = finish_launch("k_pad_columns_a");
+    if (!rc) {
+        k_pad_columns_b<<<cgrid, 32, 0, (cudaStream_t)stream>>>(H, W, rows_per_seg, segs, seg_ends,
+                                                                seg_ends + (size_t)segs * W, scratch);
+        rc = finish_launch("k_pad_columns_b");
+    }
+    cudaFreeAsync(seg_ends, (cudaStream_t)stream);
+    if (rc) return rc;
     k_pad_rows<<<H, 64, smem, (cudaStream_t)stream>>>(img, H, W, C, scratch, out, index);
     return finish_launch("k_pad_rows");
 }

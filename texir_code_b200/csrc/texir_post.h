@@ -48,18 +48,28 @@ TX_HD int pad_dist2(int i, int x, int rj, int j) {
 constexpr unsigned short kPadNone = 0xFFFFu;
 TX_HD int pad_build_envelope(const unsigned short* nr, int W, int i, unsigned short* g) {
     int l = -1;
+    int i1 = 0, i2 = 0;        // the two topmost kept columns (g[l], g[l-1]) and their squared row distances,
+    double v1 = 0.0, v2 = 0.0;  // cached so that the common no-pop step touches no memory but nr[ii]
     for (int ii = 0; ii < W; ++ii) {
         if (nr[ii] == kPadNone) continue;
         const double dw = (double)((int)nr[ii] - i), wR = dw * dw;
         while (l >= 1) {
-            const int idx1 = g[l], idx2 = g[l - 1];
-            const double a = (double)(idx1 - idx2), b = (double)(ii - idx1), c = a + b;
-            const double du = (double)((int)nr[idx2] - i), dv = (double)((int)nr[idx1] - i);
-            const double uR = du * du, vR = dv * dv;
-            if (c * vR - b * uR - a * wR - a * b * c <= 0.0) break;  // idx1 still owns part of the row
+            const double a = (double)(i1 - i2), b = (double)(ii - i1), c = a + b;
+            if (c * v1 - b * v2 - a * wR - a * b * c <= 0.0) break;  // g[l] still owns part of the row
             --l;
+            i1 = i2;
+            v1 = v2;
+            if (l >= 1) {
+                i2 = g[l - 1];
+                const double du = (double)((int)nr[i2] - i);
+                v2 = du * du;
+            }
         }
         g[++l] = (unsigned short)ii;
+        i2 = i1;
+        v2 = v1;
+        i1 = ii;
+        v1 = wR;
     }
     return l;
 }
