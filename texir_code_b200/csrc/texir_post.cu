@@ -325,35 +325,50 @@ int texir_hdr_read_host(const char* path, uint8_t* rgbe_host, int H, int W) {
     } closer{fp};
     if (h != H || w != W) return fail("texir_hdr_read_host: size differs from texir_hdr_read_info");
     const std::string bad = std::string("texir_hdr_read_host: truncated or malformed pixel data in ") + path;
-    if (W < 8 || W > 0x7fff)
-        return fread(rgbe_host, 4, (size_t)H * W, fp) == (size_t)H * W ? 0 : fail(bad);
+    // the pixel data is read in one piece and parsed from memory (one fread instead of one per run)
+    const long at = ftell(fp);
+    if (at < 0 || fseek(fp, 0, SEEK_END) != 0) return fail(bad);
+    const long end = ftell(fp);
+    if (end < at || fseek(fp, at, SEEK_SET) != 0) return fail(bad);
+    std::vector<unsigned char> data((size_t)(end - at));
+    if (!data.empty() && fread(data.data(), 1, data.size(), fp) != data.size()) return fail(bad);
+    const unsigned char* q = data.data();
+    const unsigned char* const qe = q + data.size();
+    if (W < 8 || W > 0x7fff) {
+        if ((size_t)(qe - q) < (size_t)H * W * 4) return fail(bad);
+        memcpy(rgbe_host, q, (size_t)H * W * 4);
+        return 0;
+    }
     std::vector<unsigned char> plane((size_t)W * 4);
     for (int y = 0; y < H; ++y) {
         uint8_t* row = rgbe_host + (size_t)y * W * 4;
-        unsigned char mark[4];
-        if (fread(mark, 1, 4, fp) != 4) return fail(bad);
-        if (mark[0] != 2 || mark[1] != 2 || (mark[2] & 0x80)) {  // not run-length coded: the rest is flat
-            memcpy(row, mark, 4);
-            const size_t rest = (size_t)(H - y) * W - 1;
-            return fread(row + 4, 4, rest, fp) == rest ? 0 : fail(bad);
+        if (qe - q < 4) return fail(bad);
+        if (q[0] != 2 || q[1] != 2 || (q[2] & 0x80)) {  // not run-length coded: the rest is flat
+            const size_t rest = (size_t)(H - y) * W * 4;
+            if ((size_t)(qe - q) < rest) return fail(bad);
+            memcpy(row, q, rest);
+            return 0;
         }
-        if (((int)mark[2] << 8 | mark[3]) != W) return fail(bad);
+        if (((int)q[2] << 8 | q[3]) != W) return fail(bad);
+        q += 4;
         for (int c = 0; c < 4; ++c) {
             unsigned char* p = plane.data() + (size_t)c * W;
             int x = 0;
             while (x < W) {
-                unsigned char b[2];
-                if (fread(b, 1, 2, fp) != 2) return fail(bad);
-                if (b[0] > 128) {  // run
-                    const int n = b[0] - 128;
+                if (qe - q < 2) return fail(bad);
+                const unsigned char b0 = q[0], b1 = q[1];
+                q += 2;
+                if (b0 > 128) {  // run
+                    const int n = b0 - 128;
                     if (n > W - x) return fail(bad);
-                    memset(p + x, b[1], n);
+                    memset(p + x, b1, n);
                     x += n;
                 } else {  // literal bytes
-                    const int n = b[0];
-                    if (n == 0 || n > W - x) return fail(bad);
-                    p[x++] = b[1];
-                    if (n > 1 && fread(p + x, 1, n - 1, fp) != (size_t)(n - 1)) return fail(bad);
+                    const int n = b0;
+                    if (n == 0 || n > W - x || qe - q < n - 1) return fail(bad);
+                    p[x++] = b1;
+                    memcpy(p + x, q, (size_t)(n - 1));
+                    q += n - 1;
                     x += n - 1;
                 }
             }
