@@ -132,3 +132,47 @@ def test_irt_matches_reference(oracle, scene_golden):
     assert np.array_equal(E.numpy(), g["irt_E"])
     seam = np.all(g["irt_nrm"] == 0, axis=1)
     assert seam.any() and np.all(E.numpy()[seam] == 0)
+
+
+def test_uv_derivative_formula_vs_finite_differences(oracle):
+    """oracle.gbuffer_uv_da (the float64 ray-differential formula the G-buffer kernels are checked against) equals
+    central differences of the interpolated UVs along the ray differentials, on the pixels whose displaced rays stay on
+    the same triangle"""
+    from texir_code_b200 import synth
+    sc = synth.make_room_scene(3000, seed=666, clutter=6, tex_res=64, uv_kind="planar")
+    scene = oracle.OracleScene(sc.vertices, sc.triangles, brute=True)
+    res = 12
+    rays = synth.cube_map_rays(res, cam=(0.2, -0.1, 0.3)).astype(np.float64)
+    dd = synth.cube_map_ray_differentials(res).astype(np.float64)
+
+    def uv_of(r):
+        t, ids, bary = scene.cast_rays_np(r.astype(np.float32))
+        hit = ids != 0xFFFFFFFF
+        tri = np.where(hit, ids, 0).astype(np.int64)
+        v = sc.vertices.astype(np.float64)[sc.triangles[tri]]
+        # exact barycentrics of the float64 ray on the hit triangle's plane (the float32 ones are too coarse for a
+        # finite difference)
+        o, d = r[:, :3], r[:, 3:]
+        e1, e2 = v[:, 1] - v[:, 0], v[:, 2] - v[:, 0]
+        n = np.cross(e1, e2)
+        tt = np.einsum("ij,ij->i", n, v[:, 0] - o) / np.einsum("ij,ij->i", n, d)
+        x = o + tt[:, None] * d - v[:, 0]
+        nn = np.einsum("ij,ij->i", n, n)
+        b1 = np.einsum("ij,ij->i", np.cross(x, e2), n) / nn
+        b2 = np.einsum("ij,ij->i", np.cross(e1, x), n) / nn
+        tuv = np.asarray(sc.triangle_uvs, np.float64).reshape(-1, 3, 2)[tri]
+        uv = tuv[:, 0] * (1 - b1 - b2)[:, None] + tuv[:, 1] * b1[:, None] + tuv[:, 2] * b2[:, None]
+        return uv, ids, hit
+
+    uv0, ids0, hit0 = uv_of(rays)
+    an = oracle.gbuffer_uv_da(sc.vertices, sc.triangles, sc.triangle_uvs, rays, dd, ids0)
+    h = 1e-3
+    for k in range(2):
+        step = np.concatenate([np.zeros((len(rays), 3)), dd[:, 3 * k:3 * k + 3] * h], 1)
+        up, idp, _ = uv_of(rays + step)
+        um, idm, _ = uv_of(rays - step)
+        same = hit0 & (idp == ids0) & (idm == ids0)
+        assert same.mean() > 0.5
+        fd = (up - um) / (2 * h)
+        assert rel_l2(an[same][:, [k, 2 + k]], fd[same]) < 1e-5
+    assert np.all(an[~hit0] == 0)
