@@ -73,3 +73,16 @@ def test_mip_fetch_limits(emul, oracle):
     out, lod, L, _ = _emul_fetch(emul, tex, uv, huge, -1)
     assert np.all(lod == L)
     assert np.allclose(out, tex.reshape(-1, 3).mean(0)[None], rtol=1e-5)
+
+
+def test_level_of_detail_is_log2_of_the_footprint_major_axis(oracle):
+    """the closed form in texture_lod / mip_lod (l2b + sqrt(l2n)) is the largest eigenvalue of J J^T, J = d(s,t)/d(X,Y)
+    in texels: the squared length of the major axis of the pixel's footprint ellipse"""
+    rng = np.random.default_rng(4)
+    H, W, L = 256, 512, 8
+    da = (rng.normal(size=(2000, 4)) * np.exp(rng.uniform(-8, -2, (2000, 1)))).astype(np.float32)
+    lod = oracle.texture_lod(torch.from_numpy(da), H, W, L).numpy()
+    J = np.stack([np.stack([da[:, 0] * W, da[:, 1] * W], -1), np.stack([da[:, 2] * H, da[:, 3] * H], -1)], -2).astype(np.float64)
+    smax = np.linalg.svd(J, compute_uv=False)[:, 0]
+    ref = np.clip(np.log2(smax), 0, L)
+    assert np.max(np.abs(lod - ref)) < 1e-4
