@@ -176,3 +176,51 @@ def test_uv_derivative_formula_vs_finite_differences(oracle):
         fd = (up - um) / (2 * h)
         assert rel_l2(an[same][:, [k, 2 + k]], fd[same]) < 1e-5
     assert np.all(an[~hit0] == 0)
+
+
+def test_closest_hit_oracle_vs_float64_geometry(oracle):
+    """The closest-hit oracle (the one function whose parity against real Embree is unpinned) against an independent
+    float64 evaluation of the same geometry: same primitive wherever the two nearest candidates are not within 1e-6 of
+    each other, hit distance and barycentrics to float32 accuracy, misses agree away from edges"""
+    from texir_code_b200 import synth
+    sc = synth.make_room_scene(1500, seed=666, clutter=4, tex_res=32, uv_kind="planar")
+    scene = oracle.OracleScene(sc.vertices, sc.triangles, brute=True)
+    rng = np.random.default_rng(2)
+    R = 400
+    o = rng.uniform([-3.5, -1.2, -2.5], [3.5, 1.2, 2.5], size=(R, 3))
+    d = rng.normal(size=(R, 3))
+    rays = np.concatenate([o, d], 1).astype(np.float32)
+    t, ids, bary = scene.cast_rays_np(rays)
+    o64, d64 = rays[:, :3].astype(np.float64), rays[:, 3:].astype(np.float64)
+    v = sc.vertices.astype(np.float64)[sc.triangles]                              # [T,3,3]
+    e1, e2 = v[:, 1] - v[:, 0], v[:, 2] - v[:, 0]
+    # Moeller-Trumbore in float64 for every (ray, triangle)
+    pvec = np.cross(d64[:, None, :], e2[None])
+    det = np.einsum("rtj,tj->rt", pvec, e1)
+    tvec = o64[:, None, :] - v[None, :, 0]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        u = np.einsum("rtj,rtj->rt", tvec, pvec) / det
+        qvec = np.cross(tvec, e1[None])
+        w = np.einsum("rj,rtj->rt", d64, qvec) / det
+        tt = np.einsum("tj,rtj->rt", e2, qvec) / det
+    inside = (np.abs(det) > 0) & (u >= 0) & (w >= 0) & (u + w <= 1) & (tt > 0)
+    tt = np.where(inside, tt, np.inf)
+    order = np.argsort(tt, axis=1)
+    best, second = order[:, 0], order[:, 1]
+    tb = tt[np.arange(R), best]
+    ts = tt[np.arange(R), second]
+    hit64 = np.isfinite(tb)
+    margin = np.min(np.stack([u, w, 1 - u - w], -1)[np.arange(R), best], axis=-1)  # distance from the edges, barycentric
+    clear = hit64 & (margin > 1e-5) & ((ts - tb) > 1e-6 * np.maximum(tb, 1.0))
+    assert clear.mean() > 0.9
+    assert np.array_equal(ids[clear], best[clear].astype(np.uint32))
+    assert np.max(np.abs(t[clear] - tb[clear]) / tb[clear]) < 1e-5
+    ub, wb = u[np.arange(R), best], w[np.arange(R), best]
+    assert np.max(np.abs(bary[clear, 0] - ub[clear])) < 1e-4 and np.max(np.abs(bary[clear, 1] - wb[clear])) < 1e-4
+    with np.errstate(divide="ignore", invalid="ignore"):
+        t_raw = np.einsum("tj,rtj->rt", e2, qvec) / det
+    edge_dist = np.abs(np.minimum(np.minimum(u, w), 1 - u - w))                  # 0 on an edge of the triangle
+    near_edge = np.min(np.where((np.abs(det) > 0) & (t_raw > 0), edge_dist, np.inf), axis=1) < 1e-5
+    miss = ids == 0xFFFFFFFF
+    assert np.array_equal(miss[~near_edge], ~hit64[~near_edge])
+    assert np.all(np.isinf(t[miss])) and np.all(bary[miss] == 0)
