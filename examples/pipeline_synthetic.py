@@ -90,9 +90,11 @@ def main():
     opt = torch.optim.Adam([model.materials_a, model.materials_r], lr=2e-2)
     for stage in (0, 1, 2):                                                         # train_material.py's schedule
         losses = []
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
+        warm = min(3, args.steps - 1)                                               # first steps load kernels / grow pools
         for it in range(args.steps):
+            if it == warm:
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
             opt.zero_grad(set_to_none=True)
             torch.manual_seed(7)                                                    # same sample set as the target
             out = model(mvp, 0, cam, stage)
@@ -104,7 +106,7 @@ def main():
                 model.materials_a.clamp_(min=0.0)
             losses.append(float(loss.detach()))
         torch.cuda.synchronize()
-        ms = (time.perf_counter() - t0) * 1e3 / args.steps
+        ms = (time.perf_counter() - t0) * 1e3 / (args.steps - warm)
         print("stage %d: %d steps, %.2f ms/step, loss %.4f -> %.4f" % (stage, args.steps, ms, losses[0], losses[-1]))
 
 
