@@ -6,9 +6,15 @@
 
 Workload (BASELINE.json configs[1], SURVEY.md section 8d "C2"): IrT generation on the synthetic closed room,
 T = 2^20 triangles, 4096^2 HDR radiance texture, P = 1 048 576 texels, 2048 uniform samples per texel
--> 2 147 483 648 ray-samples per step per GPU.  A "step" is one pass of the fused kernel over all P texels
-(the reference walks them in 2048 batches of 512, models/tracer_o3d_irt.py:156-173).  Multi-GPU: every rank
-holds the scene and processes its own P texels (weak scaling, no data-path collective).
+-> 2 147 483 648 ray-samples per step.  A "step" is ONE pass over all P texels (the reference walks them in 2048
+batches of 512, models/tracer_o3d_irt.py:156-173).
+
+Multi-GPU (torchrun, one rank per GPU): the SAME job is split over the ranks (strong scaling): the texels are dealt out
+block-cyclically along a Morton curve, every rank's kernel stores its results into every rank's buffer over NVLink peer
+memory (the all-gather is the kernel's epilogue) and a flag barrier closes the step -- all inside the timed region.
+`mat_stage_sharded` is one stage-2 optimisation step of the Mat stage with the pixels split over the ranks and the
+single all-reduce of the texture gradients inside the timed region; `relight_sharded` the relighting forward.
+--tris / --tex select the larger scenes (configs[3]: 4194304 / 8192; configs[4]: 8388608 / 8192).
 
 One JSON line on stdout (rank 0); see the task contract for the keys.
 """
@@ -30,6 +36,7 @@ UNIT = "ray-samples/s"
 NUM_TRIS = 1 << 20
 TEX_RES = 4096
 SPP = 2048
+ISSUE_SLOTS_PER_S = 148 * 4 * 1.965e9   # warp-instruction issue slots of one B200 at its max SM clock
 
 
 def b_alg(num_tris: int) -> int:
@@ -49,15 +56,14 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic_bytes_per_launch(points: int, spp: int):
-    """dram bytes of the dominant kernel from the committed ncu --set full capture (profiles/traffic.json),
-    scaled per ray-sample to this launch; None if no capture has been committed"""
+def ncu_traffic(key: str):
+    """dram bytes per ray-sample of a kernel from the committed ncu --set full captures (profiles/traffic.json)"""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if not os.path.exists(p):
         return None
     try:
         d = json.load(open(p))
-        return float(d["dram_bytes_per_ray_sample"]) * points * spp
+        return float(d[key])
     except Exception:
         return None
 
@@ -117,7 +123,7 @@ class ClockSampler:
         return out
 
 
-def make_workload(seed_offset: int = 0):
+def make_workload():
     from texir_code_b200 import synth
     sc = synth.make_room_scene(NUM_TRIS, seed=666, tex_res=TEX_RES)
     tex = synth.make_radiance_texture(TEX_RES, seed=666)
@@ -130,7 +136,6 @@ def make_workload(seed_offset: int = 0):
 def cpu_reference_rate(sc, tex, points: int, spp: int, steps: int, warmup: int, threads: int):
     """ray-samples/s of the reference IrT loop body on the host: reference Python restated in torch
     (single torch thread, as the reference sets) + the C BVH closest hit on `threads` cores"""
-    import numpy as np
     import torch
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import texir_oracle as O
@@ -150,6 +155,12 @@ def cpu_reference_rate(sc, tex, points: int, spp: int, steps: int, warmup: int, 
     return points * spp * len(times) / total, total / len(times)
 
 
+def workload_text(P: int) -> str:
+    return ("IrT generation (BASELINE configs[1]): synthetic closed room, T=%d triangles, %d^2 fp32 radiance texture, "
+            "ONE job of P=%d texels x 2048 spp uniform per step, forward only (the reference's IrT stage has no "
+            "backward; the Mat-stage fwd+bwd is under 'mat_stage')" % (NUM_TRIS, TEX_RES, P))
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -160,11 +171,10 @@ def run_reference(args):
     rate, sec = cpu_reference_rate(sc, tex, points, SPP, args.steps, args.warmup, threads)
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "IrT generation, synthetic closed room, T=2^20 triangles, 4096^2 radiance texture, "
-                               "2048 spp uniform (BASELINE configs[1])",
-                   "step": "four 512-texel batches of the reference loop (bounded sample of the 1 048 576-texel job)"},
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_text(args.points),
+                   "step": "four 512-texel batches of the reference loop (bounded sample of the %d-texel job)" % args.points},
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": "2048 texels x 2048 spp per step; reference Python restated in torch (1 torch thread, "
                                    "as the reference sets) + C BVH closest hit on %d threads; NOT Embree" % threads},
@@ -178,11 +188,66 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------
+class Timer:
+    """CUDA-event timing on the current stream with a barrier + synchronize on both sides, max over ranks"""
+
+    def __init__(self, dev, world):
+        self.dev, self.world = dev, world
+
+    def barrier(self):
+        import torch
+        import torch.distributed as dist
+        if self.world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(self.dev)
+
+    def run(self, fn, steps: int, warmup: int, per_step: bool = False):
+        """-> (total ms of `steps` calls (max over ranks), [per-call ms on this rank])"""
+        import torch
+        import torch.distributed as dist
+        for _ in range(warmup):
+            fn()
+        self.barrier()
+        stream = torch.cuda.current_stream(self.dev)
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)] if per_step else []
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(steps):
+            if per_step:
+                ev[i][0].record(stream)
+            fn()
+            if per_step:
+                ev[i][1].record(stream)
+        e1.record(stream)
+        self.barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=self.dev)
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), [a.elapsed_time(b) for a, b in ev]
+
+
+def cube_mvps(dev):
+    """the six cube-face matrices of a camera at the origin, reference convention (datasets/dataset.py:402-469)"""
+    import torch
+    n_, f_ = 1e-4, 100.0
+    proj = torch.tensor([[1.0, 0, 0, 0], [0, 1.0, 0, 0], [0, 0, (f_ + n_) / (f_ - n_), -(2 * f_ * n_) / (f_ - n_)],
+                         [0, 0, 1.0, 0]])
+    faces = []
+    for fwd, up in (((1, 0, 0), (0, 1, 0)), ((-1, 0, 0), (0, 1, 0)), ((0, 1, 0), (0, 0, -1)), ((0, -1, 0), (0, 0, 1)),
+                    ((0, 0, 1), (0, 1, 0)), ((0, 0, -1), (0, 1, 0))):
+        fz, uy = torch.tensor(fwd, dtype=torch.float32), torch.tensor(up, dtype=torch.float32)
+        rx = torch.linalg.cross(uy, fz)
+        w2c = torch.eye(4)
+        w2c[:3, :3] = torch.stack([rx, uy, fz])          # camera at the origin looking along fwd
+        faces.append((proj @ w2c).t())
+    return torch.stack(faces).to(dev)
+
+
 def run_ours(args):
     import numpy as np
     import torch
     import torch.distributed as dist
-    from texir_code_b200 import launch_count, models, ops, synth
+    from texir_code_b200 import launch_count, models, ops, parallel, synth
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -194,88 +259,92 @@ def run_ours(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
+    timer = Timer(dev, world)
 
     P = args.points
     sc, tex = make_workload()
+    torch.cuda.synchronize(dev)
     t_build = time.perf_counter()
     tracer = models.TracerO3d(sc.vertices, sc.triangles, sc.triangle_uvs, torch.from_numpy(tex), sample_l=[SPP, 64],
                               device=dev, build_threads=max(1, (os.cpu_count() or 1) // world))
     tracer.scene.set_texture(tracer.texture)
+    torch.cuda.synchronize(dev)
     t_build = time.perf_counter() - t_build
     if args.bvh != 2:
         tracer.scene.set_bvh(args.bvh)
     info = tracer.scene.info()
-    # per-rank texel set (weak scaling: every rank has its own P texels)
-    pos, nrm = synth.sample_surface_points(sc, P, seed=666 + 1000 * rank)
-    torch.manual_seed(666 + rank)
+    # ONE texel set for the whole job, identical on every rank (seeded): rank r computes its share of it
+    pos, nrm = synth.sample_surface_points(sc, P, seed=666)
+    torch.manual_seed(666)
     shift = torch.rand(P, 1, 2)
     h_pos, h_nrm, h_shift = (torch.from_numpy(pos).pin_memory(), torch.from_numpy(nrm).pin_memory(), shift.pin_memory())
     h_out = torch.empty(P, 3).pin_memory()
     d_pos, d_nrm, d_shift = h_pos.to(dev), h_nrm.to(dev), h_shift.to(dev)
-    d_out = torch.empty(P, 3, device=dev)
-    stream = torch.cuda.current_stream(dev)
+    collective = "none"
+    if world > 1:
+        collective = args.collective
+        try:
+            job = parallel.ShardedIrradiance(tracer, P, collective=collective)
+        except Exception as exc:  # no peer mapping between these GPUs: the library collective does the same step
+            if collective != "peer":
+                raise
+            sys.stderr.write("peer memory unavailable (%s); using the NCCL formulation\n" % exc)
+            collective = "nccl"
+            job = parallel.ShardedIrradiance(tracer, P, collective="nccl")
+    else:
+        job = parallel.ShardedIrradiance(tracer, P)
 
     def step_resident():
-        ops.irradiance(tracer.scene, d_pos, d_nrm, d_shift, SPP, "uniform", out=d_out)
+        job(d_pos, d_nrm, d_shift)
 
     def step_e2e():
-        # the call a user makes: host buffers in, host buffer out (tracer.irradiance on freshly copied inputs)
+        # the call a user makes: host buffers in, host buffer out
         p = h_pos.to(dev, non_blocking=True)
         n = h_nrm.to(dev, non_blocking=True)
         s = h_shift.to(dev, non_blocking=True)
-        e = tracer.irradiance(p, n, s)
+        e = job(p, n, s)
         h_out.copy_(e, non_blocking=True)
 
     # ---- device-resident timing (value) ------------------------------------------------------------
     for _ in range(args.warmup):
         step_resident()
-    barrier()
+    timer.barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     n_launch0 = launch_count()
-    kernel_ms = []
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for a, b in ev:
-        a.record(stream)
-        step_resident()
-        b.record(stream)
-    e1.record(stream)
-    barrier()
+    elapsed_ms, _ = timer.run(step_resident, args.steps, 0)
     launches = launch_count() - n_launch0
     clocks = sampler.stop() if rank == 0 else {}
-    elapsed_ms = e0.elapsed_time(e1)
-    kernel_ms = [a.elapsed_time(b) for a, b in ev]
-    t = torch.tensor([elapsed_ms], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_ms = float(t.item())
-    value = world * P * SPP * args.steps / (elapsed_ms * 1e-3)
+    value = P * SPP * args.steps / (elapsed_ms * 1e-3)
+
+    # the dominant kernel alone (this rank's share), CUDA events around its launch on the launching stream
+    job.kernel_events = []
+    timer.run(step_resident, args.steps, 0)
+    torch.cuda.synchronize(dev)
+    kernel_ms = [a.elapsed_time(b) for a, b in job.kernel_events]
+    job.kernel_events = None
 
     # ---- end-to-end timing through the public API with host buffers --------------------------------
-    for _ in range(max(1, min(args.warmup, 2))):
-        step_e2e()
-    barrier()
-    e0.record(stream)
-    for _ in range(args.steps):
-        step_e2e()
-    e1.record(stream)
-    barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t.item())
-    e2e_value = world * P * SPP * args.steps / (e2e_ms * 1e-3)
+    e2e_ms, _ = timer.run(step_e2e, args.steps, max(1, min(args.warmup, 2)))
+    e2e_value = P * SPP * args.steps / (e2e_ms * 1e-3)
     h2d = (h_pos.numel() + h_nrm.numel() + h_shift.numel()) * 4
     d2h = h_out.numel() * 4
     checksum = float(h_out.double().sum().item())
+
+    # ---- the library formulation of the same collective, for comparison (N > 1, peer path only) -----
+    nccl_cmp = None
+    if world > 1 and collective == "peer":
+        job2 = parallel.ShardedIrradiance(tracer, P, collective="nccl")
+        ms2, _ = timer.run(lambda: job2(d_pos, d_nrm, d_shift), args.steps, 1)
+        same = bool(torch.equal(job2.result, job.result))
+        nccl_cmp = {"ms_per_step": ms2 / args.steps, "value": P * SPP * args.steps / (ms2 * 1e-3), "bit_identical_to_peer": same,
+                    "what": "zeroed [P,3] buffer + kernel + ONE NCCL all-reduce(sum) per step"}
+
+    extras = {}
+    if world > 1 and not args.no_mat:
+        extras["mat_stage_sharded"] = bench_mat_sharded(tracer.scene, sc, dev, args, tracer.texture, timer, rank, world)
+        extras["relight_sharded"] = bench_relight_sharded(tracer.scene, sc, dev, args, timer, rank, world)
 
     # ---- traversal work per ray (report nodes visited / triangles tested beside the roofline) ----
     trav = None
@@ -289,12 +358,11 @@ def run_ours(args):
         trav = {"nodes_per_ray": nv, "tris_per_ray": nt, "touched_bytes_per_ray": nv * node_b + nt * 52 + 48 + 64,
                 "hit_rate": torch.isfinite(st["t_hit"]).float().mean().item()}
 
-    # ---- material stage (C3 shape: 98 304 pixels, 256 spp importance, forward + backward) ----------
-    mat = None
-    if rank == 0 and not args.no_mat:
-        mat = bench_material_stage(tracer.scene, sc, dev, args, tracer.texture)
-
-    # ---- CPU baseline beside it (rank 0, N = 1 only) ------------------------------------------------
+    # ---- single-GPU extras: Mat stage (fwd+bwd), training steps, cold start, CPU baseline ------------
+    if world == 1 and not args.no_mat:
+        extras["mat_stage"] = bench_material_stage(tracer.scene, sc, dev, args, tracer.texture, timer)
+    if world == 1 and not args.no_cold:
+        extras["e2e_cold"] = bench_cold(sc, tex, dev, h_pos, h_nrm, h_shift, h_out, P)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         threads = os.cpu_count() or 1
@@ -307,25 +375,29 @@ def run_ours(args):
         peak, peak_src = measured_peak_gbs()
         balg = b_alg(NUM_TRIS)
         k_ms = statistics.mean(kernel_ms)
-        achieved = balg * P * SPP / (k_ms * 1e-3) / 1e9
+        rays_per_launch = (P // world) * SPP
+        achieved = balg * rays_per_launch / (k_ms * 1e-3) / 1e9
+        tr = ncu_traffic("dram_bytes_per_ray_sample")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {
-                "workload": "IrT generation (BASELINE configs[1]): synthetic closed room, T=%d triangles, %d^2 "
-                            "fp32 radiance texture, P=%d texels per GPU x 2048 spp uniform, forward only (the "
-                            "reference's IrT stage has no backward; the Mat-stage fwd+bwd is under 'mat_stage')"
-                            % (NUM_TRIS, TEX_RES, P),
-                "points_per_gpu": P, "spp": SPP, "triangles": NUM_TRIS, "texture": [TEX_RES, TEX_RES],
+                "workload": workload_text(P),
+                "points": P, "points_per_gpu": P // world, "spp": SPP, "triangles": NUM_TRIS, "texture": [TEX_RES, TEX_RES],
                 "bvh": "BVH%d" % info["bvh_kind"], "scene_bytes": info["device_bytes"],
                 "l2": "no flush: BVH + triangles + UVs + texture = %.0f MB resident, larger than the 126 MB L2"
                       % (info["device_bytes"] / 1e6),
-                "bvh_build_s": round(t_build, 2),
+                "scene_create_s": round(t_build, 3),
+                "sharding": "none" if world == 1 else "texels dealt out in 512-blocks along a Morton curve, block-cyclic over %d ranks" % world,
+                "collective": {"none": "none (one GPU)", "peer": "all-gather fused into the kernel epilogue (NVLink peer stores) + flag barrier, inside the timed step",
+                               "nccl": "one NCCL all-reduce(sum) of [P,3] per step, inside the timed step"}[collective],
             },
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic_bytes_per_launch(P, SPP), "peak_source": peak_src,
-                         "kernel": "k_irradiance_lean<4,FRONT> (QBVH2, shared first descent)" if info["bvh_kind"] == 2 else "k_irradiance<8>", "kernel_ms": k_ms, "alg_bytes_per_ray_sample": balg},
+                         "traffic": None if tr is None else tr * rays_per_launch, "peak_source": peak_src,
+                         "kernel": "k_irradiance_lean<4,FRONT> (QBVH2, shared first descent)" if info["bvh_kind"] == 2 else "k_irradiance<8>",
+                         "kernel_ms": k_ms, "alg_bytes_per_ray_sample": balg, "ray_samples_per_launch": rays_per_launch,
+                         "issue_frac_note": "see DESIGN.md section 3: the kernel is bound by instruction issue, not by HBM"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / args.steps, "checksum": checksum},
             "gpu_launches": launches,
@@ -335,107 +407,243 @@ def run_ours(args):
             line["traversal"] = trav
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        if mat is not None:
-            line["mat_stage"] = mat
+        if nccl_cmp is not None:
+            line["irt_nccl_formulation"] = nccl_cmp
+        line.update(extras)
         print_line(json.dumps(line))
+    job.close()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
     return 0
 
 
-def bench_material_stage(scene, sc, dev, args, texture):
-    """BASELINE configs[2] shape: 6x128^2 cube-map pixels, 256 importance samples, forward + backward"""
+def bench_cold(sc, tex, dev, h_pos, h_nrm, h_shift, h_out, P):
+    """one IrT from nothing, as the reference's runner does it once (trainer/generate_ir_texture.py:64-82): scene
+    creation (BVH build + upload), texture upload, H2D of the texels, the fused launch, D2H of the result"""
+    import torch
+    from texir_code_b200 import models
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    tr = models.TracerO3d(sc.vertices, sc.triangles, sc.triangle_uvs, torch.from_numpy(tex), sample_l=[SPP, 64], device=dev)
+    tr.scene.set_texture(tr.texture)
+    torch.cuda.synchronize(dev)
+    t1 = time.perf_counter()
+    e = tr.irradiance(h_pos.to(dev, non_blocking=True), h_nrm.to(dev, non_blocking=True), h_shift.to(dev, non_blocking=True))
+    h_out.copy_(e, non_blocking=True)
+    torch.cuda.synchronize(dev)
+    t2 = time.perf_counter()
+    inf = tr.scene.info()
+    tr.scene.close()
+    return {"total_s": t2 - t0, "scene_create_and_texture_s": t1 - t0, "irt_s": t2 - t1, "bvh_build_s": inf["build_seconds"],
+            "ray_samples_per_s": P * SPP / (t2 - t0), "what": "scene_create + set_texture + H2D + irradiance + D2H, wall clock"}
+
+
+def mat_inputs(scene, sc, dev):
     import numpy as np
     import torch
-    from texir_code_b200 import ops, synth
+    from texir_code_b200 import synth
     rays = synth.cube_map_rays(128)
     hit = scene.cast_rays(torch.from_numpy(rays).to(dev))
     pos, nrm = synth.gbuffer_from_hits(sc, rays, hit["t_hit"].cpu().numpy(),
                                        hit["primitive_ids"].cpu().numpy().view(np.uint32))
-    P, N = pos.shape[0], 256
+    P = pos.shape[0]
     rough, albedo, irr, g_rgb = synth.make_materials(P, seed=8)
+    return pos, nrm, rough, albedo, irr, g_rgb
+
+
+def bench_material_stage(scene, sc, dev, args, texture, timer):
+    """BASELINE configs[2] shape: 6x128^2 cube-map pixels, importance samples, forward + backward -- first-class:
+    >= 20 timed steps per leg, per-leg roofline on the algorithmic-bytes model (2 B_alg when the backward re-casts)
+    and the issue-slot fraction; then whole optimisation steps through MaterialModel.forward"""
+    import torch
+    from texir_code_b200 import launch_count, models, ops
+    pos, nrm, rough, albedo, irr, g_rgb = mat_inputs(scene, sc, dev)
+    P = pos.shape[0]
     torch.manual_seed(666)
     sh = torch.rand(P, 1, 2).to(dev)
     t = lambda x: torch.from_numpy(x).to(dev)
     nrm_d, pos_d, irr_d, g_d, cam = t(nrm), t(pos), t(irr), t(g_rgb), torch.zeros(3, device=dev)
-    out = {"pixels": P, "spp": N}
-    for mode, N in (("stash", 256), ("recompute", 256), ("stash_16spp", 16)):  # 16 spp = configs/syn.conf training
+    peak, _ = measured_peak_gbs()
+    balg = b_alg(NUM_TRIS)
+    steps = max(20, args.steps)
+    out = {"pixels": P, "timed_steps": steps}
+    for mode, N in (("stash", 256), ("recompute", 256), ("stash", 16), ("recompute", 16)):  # 16 spp = configs/syn.conf training
         a = t(albedo).requires_grad_(True)
         r = t(rough).requires_grad_(True)
 
         def step():
             a.grad = None
             r.grad = None
-            rgb = ops.shade(scene, nrm_d, a, r, pos_d, cam, irr_d, sh, num_spec=N, backward=mode.split("_")[0])
+            rgb = ops.shade(scene, nrm_d, a, r, pos_d, cam, irr_d, sh, num_spec=N, backward=mode)
             rgb.backward(g_d)
 
-        for _ in range(2):
-            step()
-        torch.cuda.synchronize(dev)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 5
-        e0.record()
-        for _ in range(reps):
-            step()
-        e1.record()
-        torch.cuda.synchronize(dev)
-        ms = e0.elapsed_time(e1) / reps
-        out["fwd_bwd_%s_ms" % mode] = ms
-        out["fwd_bwd_%s_ray_samples_per_s" % mode] = P * N / (ms * 1e-3)
-
-    def timed(fn, reps=5):
-        for _ in range(2):
-            fn()
-        torch.cuda.synchronize(dev)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(reps):
-            fn()
-        e1.record()
-        torch.cuda.synchronize(dev)
-        return e0.elapsed_time(e1) / reps
+        sampler = ClockSampler(dev.index)
+        sampler.start()
+        ms, _ = timer.run(step, steps, 3)
+        clocks = sampler.stop()
+        ms /= steps
+        rate = P * N / (ms * 1e-3)
+        casts = 2 if mode == "recompute" else 1   # ray casts per ray-sample: forward, + the backward's re-trace
+        leg = {"ms": ms, "ray_samples_per_s": rate, "spp": N,
+               "roofline": {"bound": "hbm", "achieved": rate * casts * balg / 1e9, "peak": peak, "unit": "GB/s",
+                            "frac": rate * casts * balg / 1e9 / peak, "alg_bytes_per_ray_sample": casts * balg,
+                            "traffic": ncu_traffic("shade_%s_dram_bytes_per_ray_sample" % mode)},
+               "clocks": clocks}
+        out["fwd_bwd_%s_%dspp" % (mode, N)] = leg
 
     # BASELINE configs[4] shape (relighting, forward only): 3072 uniform Monte-Carlo diffuse + 1024 importance
-    # specular samples per pixel = 4096 spp; and the reference's own default 1024 + 256 (test_relighting.conf)
+    # specular samples per pixel = 4096 spp; and the reference's own default 1024 + 256 (configs/test.conf:10)
     sh2 = torch.rand(P, 1, 2).to(dev)
     a0, r0 = t(albedo), t(rough)
     for tag, nd, ns in (("relight_3072_1024", 3072, 1024), ("relight_1024_256", 1024, 256)):
-        ms = timed(lambda: ops.shade(scene, nrm_d, a0, r0, pos_d, cam, None, sh, num_spec=ns, shift_diff=sh2,
-                                     num_diff=nd, mode_diff="uniform", eps=1e-6), reps=3)
+        ms, _ = timer.run(lambda: ops.shade(scene, nrm_d, a0, r0, pos_d, cam, None, sh, num_spec=ns, shift_diff=sh2,
+                                            num_diff=nd, mode_diff="uniform", eps=1e-6), 5, 2)
+        ms /= 5
         out[tag + "_ms"] = ms
         out[tag + "_ray_samples_per_s"] = P * (nd + ns) / (ms * 1e-3)
 
-    # one whole optimisation step of the Mat stage through the reference-signature call (stage 2): primary rays from
-    # the cube-face mvps -> G-buffer + UV derivatives -> mip-mapped fetches of materials_a (2048^2 x 3), materials_r
-    # (4096^2 x 1) and the IrT (1024^2 x 3) -> fused render (256 spp) -> backward into the two textures
-    from texir_code_b200 import models
-    n_, f_ = 1e-4, 100.0
-    proj = torch.tensor([[1.0, 0, 0, 0], [0, 1.0, 0, 0], [0, 0, (f_ + n_) / (f_ - n_), -(2 * f_ * n_) / (f_ - n_)],
-                         [0, 0, 1.0, 0]])
-    faces = []
-    for fwd, up in (((1, 0, 0), (0, 1, 0)), ((-1, 0, 0), (0, 1, 0)), ((0, 1, 0), (0, 0, -1)), ((0, -1, 0), (0, 0, 1)),
-                    ((0, 0, 1), (0, 1, 0)), ((0, 0, -1), (0, 1, 0))):
-        fz, uy = torch.tensor(fwd, dtype=torch.float32), torch.tensor(up, dtype=torch.float32)
-        rx = torch.linalg.cross(uy, fz)
-        w2c = torch.eye(4)
-        w2c[:3, :3] = torch.stack([rx, uy, fz])          # camera at the origin looking along fwd
-        faces.append((proj @ w2c).t())
-    mvp = torch.stack(faces).to(dev)
-    mm = models.MaterialModel(None, None, sc.triangle_uvs, texture, sample_l=[32, 256], scene=scene,
-                              materials_a_res=2048, materials_r_res=4096, cube_res=128,
-                              irrt=torch.rand(1024, 1024, 3) * 3.0, max_mip_level=13)
+    # whole optimisation steps of the Mat stage through the reference-signature call: G-buffer from the cube-face mvps
+    # -> fetches of materials_a (2048^2 x 3), materials_r (4096^2 x 1) and the IrT (1024^2 x 3) -> fused render ->
+    # backward into the two textures, at the training sample count (configs/syn.conf:24: 16) and the final-eval one (256)
+    mvp = cube_mvps(dev)
+    g_img = g_d.reshape(6, 128, 128, 3)
+    for stage in (1, 2):
+        for nspec in (16, 256):
+            mm = models.MaterialModel(None, None, sc.triangle_uvs, texture, sample_l=[32, nspec], scene=scene,
+                                      materials_a_res=2048, materials_r_res=4096, cube_res=128,
+                                      irrt=torch.rand(1024, 1024, 3) * 3.0, max_mip_level=13)
+            mm._warned_normals = True
+            if stage == 1:
+                mm.materials_a.requires_grad_(False)   # trainer/train_material.py:477-479
 
-    def train_step():
+            def train_step():
+                mm.zero_grad(set_to_none=True)
+                res = mm(mvp, 0, cam, stage)
+                res["rgb"].backward(g_img)
+                # (the optimiser would run here: the next step rebuilds the pyramids of the trainable textures)
+
+            train_step()
+            n0 = launch_count()
+            train_step()
+            per_step_launches = launch_count() - n0
+            reps = 50
+            torch.cuda.synchronize(dev)
+            w0 = time.perf_counter()
+            ms, _ = timer.run(train_step, reps, 3)
+            wall = (time.perf_counter() - w0) / (reps + 3) * 1e3
+            key = "train_step_stage%d_%dspp" % (stage, nspec)
+            out[key] = {"ms": ms / reps, "host_ms_per_step": wall, "launches": per_step_launches, "timed_steps": reps,
+                        "ray_samples_per_s": P * nspec / (ms / reps * 1e-3)}
+            if stage == 2 and nspec == 16:
+                out[key]["breakdown_ms"] = train_step_breakdown(mm, mvp, cam, g_img, dev)
+            del mm
+    out["train_step_what"] = ("MaterialModel.forward(mvp, id, cam, stage) + backward: G-buffer of 6x128^2 primary rays (1 launch), "
+                              "pyramids of the two material textures (2 launches each; the IrT's is cached), the four "
+                              "fetches (1 launch), fused render (1), ONE backward kernel into texture space, 1 fold per "
+                              "texture; 'launches' counts this library's kernels per step")
+    return out
+
+
+def train_step_breakdown(mm, mvp, cam, g_img, dev):
+    """CUDA-event split of one stage-2 step: G-buffer / pyramids+fetch+render (forward) / backward kernel + folds"""
+    import torch
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    acc = [0.0, 0.0, 0.0]
+    reps = 10
+    for _ in range(reps):
         mm.zero_grad(set_to_none=True)
-        res = mm(mvp, 0, cam, 2)
-        res["rgb"].backward(g_d.reshape(res["rgb"].shape))
+        torch.cuda.synchronize(dev)
+        ev[0].record()
+        gb = mm.gbuffers(mvp, cam)
+        ev[1].record()
+        normal, pos = gb["normal"].detach(), gb["position"].detach()
+        res, _, _ = mm._render_textured(normal, None, None, None, pos + 1e-2 * normal, cam, None, gb["texc"].reshape(-1, 2),
+                                        gb["texd"].reshape(-1, 4), 2)
+        ev[2].record()
+        res["rgb"].backward(g_img)
+        ev[3].record()
+        torch.cuda.synchronize(dev)
+        for k in range(3):
+            acc[k] += ev[k].elapsed_time(ev[k + 1])
+    return {"gbuffer": acc[0] / reps, "pyramids_fetch_render": acc[1] / reps, "backward_and_folds": acc[2] / reps}
 
-    ms = timed(train_step)
-    out["train_step_stage2_ms"] = ms
-    out["train_step_stage2_ray_samples_per_s"] = P * 256 / (ms * 1e-3)
-    out["train_step_stage2_what"] = ("MaterialModel.forward(mvp, id, cam, stage=2) + backward: G-buffer of 6x128^2 primary "
-                                     "rays, 4 texture fetches (3 mip-mapped: 2048^2x3, 4096^2x1, 1024^2x3), fused render "
-                                     "256 spp, gradient scatter + pyramid fold into materials_a / materials_r")
+
+def bench_mat_sharded(scene, sc, dev, args, texture, timer, rank, world):
+    """ONE stage-2 optimisation step of the Mat stage over all ranks: pixels dealt out in 128-blocks, every rank renders
+    and back-propagates its share, then the single all-reduce over the flat texture-gradient buffer -- all timed"""
+    import torch
+    import torch.distributed as dist
+    from texir_code_b200 import models, parallel
+    torch.manual_seed(4)
+    g_full = torch.randn(6, 128, 128, 3)
+    g_loc = parallel.local_pixels(g_full, rank, world, 6).to(dev)
+    mvp, cam = cube_mvps(dev), torch.zeros(3, device=dev)
+    out = {"pixels": 6 * 128 * 128, "pixels_per_gpu": 6 * 128 * 128 // world}
+    for nspec in (16, 256):
+        mm = models.MaterialModel(None, None, sc.triangle_uvs, texture, sample_l=[32, nspec], scene=scene,
+                                  materials_a_res=2048, materials_r_res=4096, cube_res=128,
+                                  irrt=torch.rand(1024, 1024, 3) * 3.0, max_mip_level=13, shard=(rank, world))
+        mm._warned_normals = True
+        params = [mm.materials_a, mm.materials_r]
+        parts = {"compute": 0.0, "allreduce": 0.0}
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+
+        def step(record=False):
+            mm.zero_grad(set_to_none=True)
+            if record:
+                ev[0].record()
+            res = mm(mvp, 0, cam, 2)
+            res["rgb"].backward(g_loc)
+            if record:
+                ev[1].record()
+            nbytes = parallel.allreduce_gradients(params)
+            if record:
+                ev[2].record()
+            return nbytes
+
+        nbytes = step()
+        reps = 30
+        ms, _ = timer.run(step, reps, 3)
+        for _ in range(5):
+            step(True)
+            torch.cuda.synchronize(dev)
+            parts["compute"] += ev[0].elapsed_time(ev[1]) / 5
+            parts["allreduce"] += ev[1].elapsed_time(ev[2]) / 5
+        t = torch.tensor([parts["compute"], parts["allreduce"]], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out["stage2_%dspp" % nspec] = {"ms_per_step": ms / reps, "ray_samples_per_s": 6 * 128 * 128 * nspec / (ms / reps * 1e-3),
+                                       "allreduce_bytes": nbytes, "compute_ms_max_rank": float(t[0]), "allreduce_ms_max_rank": float(t[1]),
+                                       "timed_steps": reps}
+        del mm
+    out["what"] = ("MaterialModel(shard=(rank, world)).forward(mvp, id, cam, 2) + backward on this rank's pixels, then ONE "
+                   "all-reduce(sum) over the flat buffer that holds both texture gradients (2048^2x3 + 4096^2x1 fp32), "
+                   "inside the timed step; the limiter at small sample counts is that dense all-reduce")
+    return out
+
+
+def bench_relight_sharded(scene, sc, dev, args, timer, rank, world):
+    """BASELINE configs[4] shape over all ranks: relighting forward (3072 uniform diffuse + 1024 importance specular
+    samples per pixel, models/test_nvdiffrast.py:275-295), pixels split in contiguous 512-aligned slices, one
+    all_gather of the colours inside the timed step"""
+    import torch
+    from texir_code_b200 import ops, parallel
+    pos, nrm, rough, albedo, irr, g_rgb = mat_inputs(scene, sc, dev)
+    P = pos.shape[0]
+    b, e = parallel.shard_bounds(P, rank, world, 512)
+    t = lambda x: torch.from_numpy(x[b:e]).to(dev)
+    torch.manual_seed(666)
+    sh = torch.rand(P, 1, 2)[b:e].to(dev)
+    sh2 = torch.rand(P, 1, 2)[b:e].to(dev)
+    nrm_d, pos_d, a0, r0, cam = t(nrm), t(pos), t(albedo), t(rough), torch.zeros(3, device=dev)
+    out = {"pixels": P}
+    for tag, nd, ns in (("3072_1024", 3072, 1024), ("1024_256", 1024, 256)):
+        def step():
+            rgb = ops.shade(scene, nrm_d, a0, r0, pos_d, cam, None, sh, num_spec=ns, shift_diff=sh2, num_diff=nd,
+                            mode_diff="uniform", eps=1e-6)
+            return parallel.gather_points(rgb, P, 512)
+        ms, _ = timer.run(step, 10, 2)
+        out[tag] = {"ms_per_step": ms / 10, "ray_samples_per_s": P * (nd + ns) / (ms / 10 * 1e-3)}
     return out
 
 
@@ -445,10 +653,13 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--points", type=int, default=1 << 20, help="texels per GPU (default: the full 1024^2 IrT)")
+    ap.add_argument("--points", type=int, default=1 << 20, help="texels of the IrT job (default: the full 1024^2 IrT)")
     ap.add_argument("--bvh", type=int, default=2, choices=[2, 8], help="BVH layout the kernels traverse")
+    ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
+                    help="multi-GPU IrT: results stored to every rank by the kernel (peer) or one NCCL all-reduce")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--no-mat", action="store_true", help="skip the material-stage fwd+bwd leg")
+    ap.add_argument("--no-mat", action="store_true", help="skip the material-stage legs")
+    ap.add_argument("--no-cold", action="store_true", help="skip the cold-start (scene creation included) leg")
     ap.add_argument("--tris", type=int, default=NUM_TRIS, help="triangles of the synthetic scene (configs[3]: 4194304)")
     ap.add_argument("--tex", type=int, default=TEX_RES, help="radiance texture resolution (configs[3]: 8192)")
     args = ap.parse_args()

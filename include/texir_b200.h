@@ -34,6 +34,10 @@ extern "C" {
 
 typedef struct texir_scene texir_scene;
 
+/* ranks of one node that can map each other's buffers (texir_peer_*), and the size of an exported buffer handle */
+#define TEXIR_MAX_PEERS 8
+#define TEXIR_PEER_HANDLE_BYTES 64
+
 /* sampling modes of generate_dir (utils/sample_util.py:115-143) */
 enum { TEXIR_MODE_UNIFORM = 0, TEXIR_MODE_COSINE = 1, TEXIR_MODE_IMPORTANCE = 2 };
 /* radiance texture source layouts */
@@ -98,6 +102,10 @@ TEXIR_API int texir_generate_dir_samples(const float* nrm, const float* rough, c
 TEXIR_API int texir_generate_dir_bwd(const float* nrm, const float* rough, const float* shift, int64_t P, int N,
                                      const float* g_out, float* g_rough, void* stream);
 
+/* diagnostics: s = sin(x), c = cos(x) for x [n] exactly as the kernels evaluate them inside generate_dir (variant 0) or
+ * as two separate library calls (variant 1); used to pin the direction arithmetic to the reference's torch-CUDA run */
+TEXIR_API int texir_debug_sincos(const float* x, int64_t n, int variant, float* s, float* c, void* stream);
+
 /* ---- query_irf: models/mat_nvdiffrast.py:292-320 / models/tracer_o3d_irt.py:240-269.
  * org [P,3] (one origin per point, the reference expands it), dir [P,N,3]; rad [P,N,3]. */
 TEXIR_API int texir_query_irf(const texir_scene* scene, const float* org, const float* dir, int64_t P, int N,
@@ -111,6 +119,15 @@ TEXIR_API int texir_query_irf(const texir_scene* scene, const float* org, const 
 TEXIR_API int texir_irradiance_fwd(const texir_scene* scene, const float* pos, const float* nrm,
                                    const float* shift, const int32_t* order, int64_t P, int N, int mode, float* E,
                                    void* stream);
+/* The same launch for ONE RANK'S SHARE of a multi-GPU IrT (the reference's loop models/tracer_o3d_irt.py:156-173
+ * has no multi-GPU form, the texels are independent).  pos / nrm / shift are the FULL [P_total,.] arrays, `order` lists
+ * the P point indices this rank computes, and every result is stored to slot order[i] of ALL n_peers buffers in
+ * E_peers_host (a HOST array of device pointers: this rank's own [P_total,3] buffer and the other ranks' buffers mapped
+ * with texir_peer_open) -- the all-gather is the kernel's epilogue, over NVLink peer stores.  Follow it with
+ * texir_peer_barrier before any rank reads its buffer. */
+TEXIR_API int texir_irradiance_fwd_peers(const texir_scene* scene, const float* pos, const float* nrm,
+                                         const float* shift, const int32_t* order, int64_t P, int N, int mode,
+                                         float* const* E_peers_host, int n_peers, void* stream);
 /* order [P] (int32, device): the points sorted along a 30-bit Morton curve over the scene box */
 TEXIR_API int texir_point_order(const texir_scene* scene, const float* pos, int64_t P, int32_t* order, void* stream);
 
@@ -137,6 +154,15 @@ TEXIR_API int texir_gbuffer(const texir_scene* scene, const float* rays, int64_t
 TEXIR_API int texir_gbuffer_mvp(const texir_scene* scene, const float* mvp, const float* cam, int V, int res, float* pos,
                                 float* nrm, float* uv, float* uv_da, uint32_t* prim, float* bary, float* mask,
                                 float* rays_out, void* stream);
+/* The same for one rank of a pixel-sharded Mat stage, and with the reference's texture-coordinate convention:
+ * rank `shard_rank` of `shard_world` takes the 128-pixel blocks b = shard_rank (mod shard_world) of every view and
+ * stores them compactly (outputs [V*res*res/shard_world, .]; res*res must be a multiple of 128*shard_world).
+ * flip_v != 0: uv = (u, 1 - v) and dv/dX, dv/dY negated -- pyredner.load_obj's flip_tex_coords=True default, which
+ * is what the reference's self.uvs hold (models/mat_nvdiffrast.py:194) and its dr.texture calls address with. */
+TEXIR_API int texir_gbuffer_mvp_shard(const texir_scene* scene, const float* mvp, const float* cam, int V, int res,
+                                      int shard_rank, int shard_world, int flip_v, float* pos, float* nrm, float* uv,
+                                      float* uv_da, uint32_t* prim, float* bary, float* mask, float* rays_out,
+                                      void* stream);
 /* screen-space derivatives of the interpolated UVs (the reference's texd = dr.interpolate(..., rast_db,
  * diff_attrs='all'), models/mat_nvdiffrast.py:128), as a ray differential on the hit triangle's plane.
  * ddir [R,6] = (d dir/dX, d dir/dY) per pixel, prim [R] from texir_gbuffer -> uv_da [R,4] =
@@ -177,6 +203,21 @@ TEXIR_API int texir_shade_bwd_tex(const texir_scene* scene, const float* nrm, co
                                   const float* ediff, const float* uv, const float* uv_da, float* g_tex_a,
                                   float* g_mips_a, int Ha, int Wa, int La, float* g_tex_r, float* g_mips_r, int Hr,
                                   int Wr, int Lr, void* stream);
+
+/* The whole backward of a Mat-stage step (models/mat_nvdiffrast.py:131-139,179-182 + the reference loss's direct terms
+ * on preds['albedo'] / ['roughness'] / ['roughness_womipmap'], models/loss.py:94,103,113) in ONE launch: as
+ * texir_shade_bwd_tex, plus per-pixel gradients of the fetched materials added before the scatter -- add_a [P,3] and
+ * add_r [P] through the mip-mapped transpose, add_rw [P] through the bilinear one (each nullable).  render_albedo = 0:
+ * the render saw albedo.detach() (stage 1); render_rough = 0: roughness entered detached; render_rough_bilinear = 1: the
+ * render saw roughness_womipmap (stage 1), so its roughness gradient takes the bilinear transpose. */
+TEXIR_API int texir_shade_bwd_mat(const texir_scene* scene, const float* nrm, const float* albedo, const float* rough,
+                                  const float* pos, const float* cam, const float* irr, const float* shift_spec,
+                                  const float* shift_diff, int64_t P, int N_spec, int N_diff, int mode_spec,
+                                  int mode_diff, float eps, const float* g_rgb, const float* drgb_drough,
+                                  const float* ediff, const float* uv, const float* uv_da, const float* add_a,
+                                  const float* add_r, const float* add_rw, int render_albedo, int render_rough,
+                                  int render_rough_bilinear, float* g_tex_a, float* g_mips_a, int Ha, int Wa, int La,
+                                  float* g_tex_r, float* g_mips_r, int Hr, int Wr, int Lr, void* stream);
 
 /* ---- stand-alone BRDF reductions with the reference's tensor signatures --------------------
  * specular_reflectance(lighting, h, n, v, l, roughness): mat_nvdiffrast.py:260-279.
@@ -226,6 +267,34 @@ TEXIR_API int texir_texture_scatter_mip(const float* g_out, int H, int W, int C,
                                         const float* uv_da, int64_t P, float* g_tex, float* g_mips, void* stream);
 /* ... and transpose of the build: g_mips folded down into g_tex, coarsest level first (g_mips is consumed) */
 TEXIR_API int texir_texture_mip_fold(float* g_tex, float* g_mips, int H, int W, int C, int levels, void* stream);
+
+/* The per-step forms of the three calls above (same values, fewer passes; csrc/texir_matstage.cu): the whole pyramid
+ * in two launches; the fold as one gather launch that writes the folded level 0 to `out` (out == g_tex: in place) and,
+ * with clear != 0, leaves g_tex / g_mips zeroed for the next step's scatter; and the four per-pixel fetches of a Mat-stage
+ * step (albedo and irradiance [P,3] mip-mapped, roughness [P] mip-mapped and bilinear; models/mat_nvdiffrast.py:131-139)
+ * in one launch, each output nullable. */
+TEXIR_API int texir_texture_mip_build_fast(const float* tex, int H, int W, int C, int levels, float* mips, void* stream);
+TEXIR_API int texir_texture_mip_fold_into(float* g_tex, float* g_mips, int H, int W, int C, int levels, float* out,
+                                          int clear, void* stream);
+TEXIR_API int texir_mat_fetch(const float* tex_a, const float* mips_a, int Ha, int Wa, int La, const float* tex_r,
+                              const float* mips_r, int Hr, int Wr, int Lr, const float* tex_i, const float* mips_i, int Hi,
+                              int Wi, int Li, const float* uv, const float* uv_da, int64_t P, float* albedo, float* rough,
+                              float* rough_womip, float* irr, void* stream);
+
+/* ---- peer memory of the multi-GPU path: one process per GPU; a rank exports a device buffer as a 64-byte
+ *      handle (CUDA IPC), the other ranks map it over NVLink / NVSwitch and kernels store into it directly.
+ * texir_peer_alloc: zeroed buffer on `device` + its handle (handle_out: TEXIR_PEER_HANDLE_BYTES, HOST memory);
+ * texir_peer_open: map another rank's buffer; _close / _free undo them.
+ * texir_peer_barrier: flags_host[r] = rank r's flag array (world + 1 uint32, from texir_peer_alloc, own or mapped):
+ * every rank stores `epoch` (monotonically increasing, > 0) into its slot of every array and waits until its own array
+ * holds `epoch` from everybody -- stream-ordered, so stores of earlier kernels on `stream` are visible to every rank
+ * after it.  The wait is bounded (about 4 s); on expiry slot [world] of the own array is set to `epoch`. */
+TEXIR_API int texir_peer_alloc(int device, int64_t bytes, void** dptr, unsigned char* handle_out);
+TEXIR_API int texir_peer_free(int device, void* dptr);
+TEXIR_API int texir_peer_open(int device, const unsigned char* handle, void** dptr);
+TEXIR_API int texir_peer_close(int device, void* dptr);
+TEXIR_API int texir_peer_barrier(uint32_t* const* flags_host, int rank, int world, uint32_t epoch, int device,
+                                 void* stream);
 
 /* ---- IrT post-processing ---------------------------------------------
  * padding_texture (tools/padding_texture.py:49-80): every empty texel (channel sum == 0) takes the value of

@@ -48,17 +48,22 @@ SIGNATURES = {
     "texir_generate_dir": (c_int, [_P, _P, _P, c_int64, c_int, c_int, _P, _P]),
     "texir_generate_dir_samples": (c_int, [_P, _P, _P, c_int64, c_int, c_int, _P, _P]),
     "texir_generate_dir_bwd": (c_int, [_P, _P, _P, c_int64, c_int, _P, _P, _P]),
+    "texir_debug_sincos": (c_int, [_P, c_int64, c_int, _P, _P, _P]),
     "texir_query_irf": (c_int, [_P, _P, _P, c_int64, c_int, _P, _P]),
     "texir_irradiance_fwd": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, c_int, _P, _P]),
+    "texir_irradiance_fwd_peers": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, c_int, _P, c_int, _P]),
     "texir_point_order": (c_int, [_P, _P, c_int64, _P, _P]),
     "texir_radiance_samples": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int, _P, _P, _P]),
     "texir_gbuffer": (c_int, [_P, _P, c_int64, _P, _P, _P, _P, _P, _P, _P]),
     "texir_gbuffer_mvp": (c_int, [_P, _P, _P, c_int, c_int] + [_P] * 9),
+    "texir_gbuffer_mvp_shard": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int] + [_P] * 9),
     "texir_gbuffer_uv_da": (c_int, [_P, _P, _P, _P, c_int64, _P, _P]),
     "texir_shade_fwd": (c_int, [_P] + [_P] * 8 + [c_int64, c_int, c_int, c_int, c_int, c_float, _P, _P, _P, _P]),
     "texir_shade_bwd": (c_int, [_P] + [_P] * 8 + [c_int64, c_int, c_int, c_int, c_int, c_float] + [_P] * 7),
     "texir_shade_bwd_tex": (c_int, [_P] + [_P] * 8 + [c_int64, c_int, c_int, c_int, c_int, c_float] + [_P] * 5
                             + [_P, _P, c_int, c_int, c_int, _P, _P, c_int, c_int, c_int, _P]),
+    "texir_shade_bwd_mat": (c_int, [_P] + [_P] * 8 + [c_int64, c_int, c_int, c_int, c_int, c_float] + [_P] * 8
+                            + [c_int, c_int, c_int] + [_P, _P, c_int, c_int, c_int, _P, _P, c_int, c_int, c_int, _P]),
     "texir_specular_reflectance": (c_int, [_P] * 6 + [c_int64, c_int, c_float, _P, _P]),
     "texir_specular_reflectance_bwd": (c_int, [_P] * 6 + [c_int64, c_int, c_float] + [_P] * 6),
     "texir_diffuse_reflectance": (c_int, [_P] * 4 + [c_int64, c_int, c_int, _P, _P]),
@@ -71,6 +76,14 @@ SIGNATURES = {
     "texir_texture_fetch_mip": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P, c_int64, _P, _P, _P]),
     "texir_texture_scatter_mip": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, c_int64, _P, _P, _P]),
     "texir_texture_mip_fold": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P]),
+    "texir_texture_mip_build_fast": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P]),
+    "texir_texture_mip_fold_into": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, c_int, _P]),
+    "texir_mat_fetch": (c_int, [_P, _P, c_int, c_int, c_int] * 3 + [_P, _P, c_int64, _P, _P, _P, _P, _P]),
+    "texir_peer_alloc": (c_int, [c_int, c_int64, POINTER(c_void_p), _P]),
+    "texir_peer_free": (c_int, [c_int, _P]),
+    "texir_peer_open": (c_int, [c_int, _P, POINTER(c_void_p)]),
+    "texir_peer_close": (c_int, [c_int, _P]),
+    "texir_peer_barrier": (c_int, [_P, c_int, c_int, ctypes.c_uint32, c_int, _P]),
     "texir_pad_texture": (c_int, [_P, c_int, c_int, c_int, _P, _P, _P, _P]),
     "texir_rgbe_encode": (c_int, [_P, c_int64, c_int, _P, _P]),
     "texir_rgbe_decode": (c_int, [_P, c_int64, c_int, _P, _P]),

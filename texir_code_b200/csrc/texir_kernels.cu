@@ -17,6 +17,7 @@
 #include "../../include/texir_b200.h"
 #include "bvh_build.h"
 #include "texir_host.h"
+#include "texir_scene.h"
 #include "texir_point.h"
 #include "texir_tex.h"
 
@@ -27,21 +28,6 @@ using namespace texir;
 // ------------------------------------------------------------------------------------------------
 static thread_local std::string g_err;
 static std::atomic<int64_t> g_launches{0};
-
-struct texir_scene {
-    SceneView view{};
-    texir_scene_info info{};
-    void* d_nodes2 = nullptr;
-    void* d_tris2 = nullptr;
-    void* d_qnodes2 = nullptr;
-    void* d_nodes8 = nullptr;
-    void* d_tris8 = nullptr;
-    void* d_uvs = nullptr;
-    void* d_slot_of_prim = nullptr;  // original primitive id -> BVH2 slot
-    void* d_tex = nullptr;
-    int64_t geom_bytes = 0, tex_bytes = 0;
-    float lo[3] = {0, 0, 0}, hi[3] = {1, 1, 1};  // scene box
-};
 
 #define TX_FAIL(msg)                 \
     do {                             \
@@ -141,6 +127,20 @@ __device__ __forceinline__ float group_sum(float v, int G) {
     for (int o = G >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
     return v;
 }
+// where a per-point result goes: the caller's buffer, or the same slot of that buffer on every rank (peer memory mapped
+// over NVLink): the all-gather of a sharded IrT is the kernel's own epilogue (texir_irradiance_fwd_peers)
+struct PeerOut {
+    float* p[TEXIR_MAX_PEERS];
+    int n;
+};
+__device__ __forceinline__ void store3_peers(const PeerOut& o, int64_t i, float x, float y, float z) {
+    for (int k = 0; k < o.n; ++k) {
+        float* E = o.p[k];
+        E[3 * i + 0] = x;
+        E[3 * i + 1] = y;
+        E[3 * i + 2] = z;
+    }
+}
 __host__ __device__ __forceinline__ int group_lanes(int N) {
     int g = 1;
     while (g < N && g < 32) g <<= 1;
@@ -235,6 +235,23 @@ __global__ void __launch_bounds__(128) k_generate_dir_bwd(const float* __restric
     }
     acc = group_sum(acc, 32);
     if (lane == 0) g_rough[p] = acc;
+}
+
+// diagnostics: the device's sine / cosine as generate_dir evaluates them (variant 0) or as two separate calls
+// (variant 1), for pinning them against the reference's torch-CUDA execution (profiles/discover_torch_cuda_rounding.py)
+__global__ void __launch_bounds__(256) k_debug_sincos(const float* __restrict__ x, int64_t n, int variant,
+                                                      float* __restrict__ s, float* __restrict__ c) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float a, b;
+    if (variant == 0) {
+        tx_sincos(x[i], &a, &b);
+    } else {
+        a = sinf(x[i]);
+        b = cosf(x[i]);
+    }
+    s[i] = a;
+    c[i] = b;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -393,7 +410,8 @@ template <int KIND>
 __global__ void __launch_bounds__(128) k_gbuffer_mvp(SceneView s, const float* __restrict__ mvp,
                                                      const float* __restrict__ cam, int res,
                                                      const uint32_t* __restrict__ slot_of_prim, GBufferOut g,
-                                                     float* __restrict__ rays_out) {
+                                                     float* __restrict__ rays_out, int shard_rank, int shard_world,
+                                                     int flip_v) {
     __shared__ double inv[16];
     __shared__ int ok;
     const int view = blockIdx.y;
@@ -418,9 +436,12 @@ __global__ void __launch_bounds__(128) k_gbuffer_mvp(SceneView s, const float* _
             for (int k = 0; k < 16; ++k) inv[k] /= det;
     }
     __syncthreads();
-    const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+    // block-cyclic pixel sharding (multi-GPU Mat stage): this rank takes the 128-pixel blocks b = rank (mod world) of
+    // every view and stores them compactly, view after view
+    const int pix = (blockIdx.x * shard_world + shard_rank) * blockDim.x + threadIdx.x;
     if (pix >= res * res) return;
-    const int64_t r = (int64_t)view * res * res + pix;
+    const int64_t r = shard_world > 1 ? ((int64_t)view * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x
+                                      : (int64_t)view * res * res + pix;
     const int row = pix / res, col = pix - row * res;
     const double x = ((double)col + 0.5) / (double)res * 2.0 - 1.0, y = ((double)row + 0.5) / (double)res * 2.0 - 1.0;
     // world_h = (x, y, 1, 1) @ inv
@@ -448,9 +469,17 @@ __global__ void __launch_bounds__(128) k_gbuffer_mvp(SceneView s, const float* _
         rays_out[6 * r + 3] = d.x; rays_out[6 * r + 4] = d.y; rays_out[6 * r + 5] = d.z;
     }
     const Hit h = gbuffer_pixel<KIND>(s, slot_of_prim, o, d, r, g);
-    if (g.uv_da)
-        reinterpret_cast<float4*>(g.uv_da)[r] =
-            s.tri_uvs ? gbuffer_uv_da(s, slot_of_prim, o, d, dd[0], dd[1], h.prim) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 da = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (g.uv_da && s.tri_uvs) da = gbuffer_uv_da(s, slot_of_prim, o, d, dd[0], dd[1], h.prim);
+    if (flip_v) {
+        // pyredner.load_obj(flip_tex_coords=True), the loader behind the reference's self.uvs (mat_nvdiffrast.py:194):
+        // the dr.texture calls address the material textures with v' = 1 - v, so dv'/dX = -dv/dX.  Uncovered pixels
+        // keep uv = 0 (dr.interpolate gives 0 where nothing was rasterised).
+        if (g.uv && h.prim != kInvalidId) g.uv[2 * r + 1] = 1.0f - g.uv[2 * r + 1];
+        da.z = -da.z;
+        da.w = -da.w;
+    }
+    if (g.uv_da) reinterpret_cast<float4*>(g.uv_da)[r] = da;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -463,7 +492,7 @@ template <int KIND>
 __global__ void __launch_bounds__(128, TX_IRR_MINB) k_irradiance(SceneView s, const float* __restrict__ pos,
                                                     const float* __restrict__ nrm, const float* __restrict__ shift,
                                                     const int32_t* __restrict__ order, int64_t P, int N, int mode,
-                                                    int G, int abits, float* __restrict__ E) {
+                                                    int G, int abits, PeerOut E) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int gl = lane & (G - 1);
@@ -475,11 +504,7 @@ __global__ void __launch_bounds__(128, TX_IRR_MINB) k_irradiance(SceneView s, co
     irradiance_lane<KIND>(s, load3(nrm, p), load3(pos, p), __ldg(shift + 2 * p + 0), __ldg(shift + 2 * p + 1), N, mode,
                           gl, G, abits, acc);
     float ax = group_sum(acc[0], G), ay = group_sum(acc[1], G), az = group_sum(acc[2], G);
-    if (live && gl == 0) {
-        E[3 * p + 0] = irradiance_finish(ax, N);
-        E[3 * p + 1] = irradiance_finish(ay, N);
-        E[3 * p + 2] = irradiance_finish(az, N);
-    }
+    if (live && gl == 0) store3_peers(E, p, irradiance_finish(ax, N), irradiance_finish(ay, N), irradiance_finish(az, N));
 }
 
 // Occupancy-tuned IrT kernel for G == 32 (N >= 32): measured on B200 the traversal is latency bound (ncu:
@@ -500,7 +525,7 @@ __global__ void __launch_bounds__(128, TX_LEAN_MINB) k_irradiance_lean(SceneView
                                                              const float* __restrict__ nrm,
                                                              const float* __restrict__ shift,
                                                              const int32_t* __restrict__ order, int64_t P, int N,
-                                                             int mode, int abits, float* __restrict__ E) {
+                                                             int mode, int abits, PeerOut E) {
     __shared__ IrtPointSmem sm_pt[4];
     __shared__ float sm_acc[3][128];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -557,11 +582,7 @@ __global__ void __launch_bounds__(128, TX_LEAN_MINB) k_irradiance_lean(SceneView
     }
     float ax = group_sum(sm_acc[0][threadIdx.x], 32), ay = group_sum(sm_acc[1][threadIdx.x], 32),
           az = group_sum(sm_acc[2][threadIdx.x], 32);
-    if (live && lane == 0) {
-        E[3 * p + 0] = irradiance_finish(ax, N);
-        E[3 * p + 1] = irradiance_finish(ay, N);
-        E[3 * p + 2] = irradiance_finish(az, N);
-    }
+    if (live && lane == 0) store3_peers(E, p, irradiance_finish(ax, N), irradiance_finish(ay, N), irradiance_finish(az, N));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -594,6 +615,16 @@ struct ShadeArgs {
     const float* uv;
     const float* uv_da;
     TexGrad ga, gr;
+    // texir_shade_bwd_mat: the whole Mat-stage backward in this one launch.  Direct gradients of the fetched per-pixel
+    // materials (what the reference's loss puts on preds['albedo'] / ['roughness'] / ['roughness_womipmap'],
+    // models/loss.py:94,103,113) are added to the render's before the scatter: add_a [P,3] and add_r [P] go through the
+    // mip-mapped transpose, add_rw [P] through the bilinear one.  render_albedo = 0: the render saw albedo.detach()
+    // (stage 1, mat_nvdiffrast.py:179); render_rough_bilinear = 1: it saw roughness_womipmap (stage 1).
+    const float* add_a;
+    const float* add_r;
+    const float* add_rw;
+    int render_albedo, render_rough_bilinear;
+    int no_render_rough;  // roughness entered the render detached: only the direct terms reach materials_r
 };
 
 // gradient of one pixel's albedo / roughness, written per pixel and / or scattered into the material textures' gradients
@@ -609,10 +640,30 @@ __device__ __forceinline__ void shade_emit_material_grads(const ShadeArgs& a, in
         const float u = __ldg(a.uv + 2 * p), v = __ldg(a.uv + 2 * p + 1);
         float4 da = make_float4(0.f, 0.f, 0.f, 0.f);
         if (a.uv_da) da = __ldg(reinterpret_cast<const float4*>(a.uv_da) + p);
-        if (have_a && a.ga.tex)
-            tex_scatter_point(a.ga, u, v, mip_lod(da.x, da.y, da.z, da.w, a.ga.H, a.ga.W, a.ga.L), ga);
-        if (have_r && a.gr.tex)
-            tex_scatter_point(a.gr, u, v, mip_lod(da.x, da.y, da.z, da.w, a.gr.H, a.gr.W, a.gr.L), &gr);
+        if (a.ga.tex) {
+            float t[3] = {0.f, 0.f, 0.f};
+            if (have_a && a.render_albedo) { t[0] = ga[0]; t[1] = ga[1]; t[2] = ga[2]; }
+            if (a.add_a) {
+                t[0] += __ldg(a.add_a + 3 * p + 0);
+                t[1] += __ldg(a.add_a + 3 * p + 1);
+                t[2] += __ldg(a.add_a + 3 * p + 2);
+            }
+            if (t[0] != 0.f || t[1] != 0.f || t[2] != 0.f)  // adding zeros changes nothing: skip the 24 atomics
+                tex_scatter_point(a.ga, u, v, mip_lod(da.x, da.y, da.z, da.w, a.ga.H, a.ga.W, a.ga.L), t);
+        }
+        if (a.gr.tex) {
+            float r_mip = a.add_r ? __ldg(a.add_r + p) : 0.f, r_bil = a.add_rw ? __ldg(a.add_rw + p) : 0.f;
+            if (have_r) {
+                if (a.render_rough_bilinear) r_bil += gr; else r_mip += gr;
+            }
+            if (r_mip != 0.f) tex_scatter_point(a.gr, u, v, mip_lod(da.x, da.y, da.z, da.w, a.gr.H, a.gr.W, a.gr.L), &r_mip);
+            if (r_bil != 0.f) {
+                MipLod m0;
+                m0.level0 = m0.level1 = 0;
+                m0.frac = 0.f;
+                tex_scatter_point(a.gr, u, v, m0, &r_bil);
+            }
+        }
     }
 }
 
@@ -646,7 +697,7 @@ __device__ __forceinline__ void shade_epilogue(const ShadeArgs& a, int64_t p, fl
     } else {
         V3 g = load3(a.g_rgb, p);
         const float ga[3] = {g.x * dfac[0], g.y * dfac[1], g.z * dfac[2]};
-        shade_emit_material_grads(a, p, ga, (g.x * dx + g.y * dy + g.z * dz) * inv_ns, true, true);
+        shade_emit_material_grads(a, p, ga, (g.x * dx + g.y * dy + g.z * dz) * inv_ns, true, !a.no_render_rough);
         if (a.g_irr) {
             V3 al = load3(a.albedo, p);
             bool lit = a.N_diff == 0;
@@ -823,7 +874,7 @@ __global__ void __launch_bounds__(256) k_shade_bwd_stash(ShadeArgs a) {
     int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= a.P) return;
     V3 g = load3(a.g_rgb, p);
-    const bool want_a = a.g_albedo || a.ga.tex, want_r = a.g_rough || a.gr.tex;
+    const bool want_a = a.g_albedo || (a.ga.tex && a.render_albedo), want_r = (a.g_rough || a.gr.tex) && !a.no_render_rough;
     float ga[3] = {0.f, 0.f, 0.f}, gr = 0.f;
     if (want_a) {
         V3 fac;
@@ -1326,6 +1377,13 @@ int texir_generate_dir(const float* nrm, const float* rough, const float* shift,
     return finish_launch("k_generate_dir");
 }
 
+int texir_debug_sincos(const float* x, int64_t n, int variant, float* s, float* c, void* stream) {
+    if (n <= 0 || !x || !s || !c) TX_FAIL("texir_debug_sincos: bad argument");
+    DeviceGuard guard(device_of(s));
+    k_debug_sincos<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(x, n, variant, s, c);
+    return finish_launch("k_debug_sincos");
+}
+
 int texir_generate_dir_samples(const float* nrm, const float* rough, const float* samples, int64_t P, int N, int mode,
                                float* out, void* stream) {
     if (check_pn("texir_generate_dir_samples", P, N) || check_mode("texir_generate_dir_samples", mode)) return 1;
@@ -1466,19 +1524,37 @@ int texir_gbuffer(const texir_scene* sc, const float* rays, int64_t R, float* po
     return finish_launch("k_gbuffer");
 }
 
-int texir_gbuffer_mvp(const texir_scene* sc, const float* mvp, const float* cam, int V, int res, float* pos, float* nrm,
-                      float* uv, float* uv_da, uint32_t* prim, float* bary, float* mask, float* rays_out, void* stream) {
-    if (!sc) TX_FAIL("texir_gbuffer_mvp: NULL scene");
-    if (V < 0 || res <= 0 || res > 16384 || V > 65535) TX_FAIL("texir_gbuffer_mvp: bad view count or resolution");
+static int gbuffer_mvp_impl(const char* fn, const texir_scene* sc, const float* mvp, const float* cam, int V, int res,
+                            int shard_rank, int shard_world, int flip_v, float* pos, float* nrm, float* uv, float* uv_da,
+                            uint32_t* prim, float* bary, float* mask, float* rays_out, void* stream) {
+    if (!sc) TX_FAIL(std::string(fn) + ": NULL scene");
+    if (V < 0 || res <= 0 || res > 16384 || V > 65535) TX_FAIL(std::string(fn) + ": bad view count or resolution");
     if (V == 0) return 0;
-    if (!mvp || !cam) TX_FAIL("texir_gbuffer_mvp: NULL mvp / cam");
-    if ((uv || uv_da) && !sc->view.tri_uvs) TX_FAIL("texir_gbuffer_mvp: uv requested but the scene has no triangle uvs");
+    if (!mvp || !cam) TX_FAIL(std::string(fn) + ": NULL mvp / cam");
+    if ((uv || uv_da) && !sc->view.tri_uvs) TX_FAIL(std::string(fn) + ": uv requested but the scene has no triangle uvs");
+    if (shard_world < 1 || shard_rank < 0 || shard_rank >= shard_world) TX_FAIL(std::string(fn) + ": bad shard");
+    const int64_t blocks = ((int64_t)res * res + 127) / 128;
+    if (shard_world > 1 && (((int64_t)res * res) % 128 != 0 || blocks % shard_world != 0))
+        TX_FAIL(std::string(fn) + ": res*res must be a multiple of 128 * world for a sharded G-buffer");
     DeviceGuard guard(sc->info.device);
     GBufferOut g{pos, nrm, uv, prim, bary, mask, uv_da};
-    dim3 grid(grid_for((int64_t)res * res, 128), (unsigned)V);
+    dim3 grid((unsigned)(blocks / shard_world), (unsigned)V);
     k_gbuffer_mvp<4><<<grid, 128, 0, (cudaStream_t)stream>>>(sc->view, mvp, cam, res, (const uint32_t*)sc->d_slot_of_prim, g,
-                                                             rays_out);
+                                                             rays_out, shard_rank, shard_world, flip_v);
     return finish_launch("k_gbuffer_mvp");
+}
+
+int texir_gbuffer_mvp(const texir_scene* sc, const float* mvp, const float* cam, int V, int res, float* pos, float* nrm,
+                      float* uv, float* uv_da, uint32_t* prim, float* bary, float* mask, float* rays_out, void* stream) {
+    return gbuffer_mvp_impl("texir_gbuffer_mvp", sc, mvp, cam, V, res, 0, 1, 0, pos, nrm, uv, uv_da, prim, bary, mask,
+                            rays_out, stream);
+}
+
+int texir_gbuffer_mvp_shard(const texir_scene* sc, const float* mvp, const float* cam, int V, int res, int shard_rank,
+                            int shard_world, int flip_v, float* pos, float* nrm, float* uv, float* uv_da, uint32_t* prim,
+                            float* bary, float* mask, float* rays_out, void* stream) {
+    return gbuffer_mvp_impl("texir_gbuffer_mvp_shard", sc, mvp, cam, V, res, shard_rank, shard_world, flip_v, pos, nrm, uv,
+                            uv_da, prim, bary, mask, rays_out, stream);
 }
 
 int texir_gbuffer_uv_da(const texir_scene* sc, const float* rays, const float* ddir, const uint32_t* prim, int64_t R,
@@ -1494,34 +1570,54 @@ int texir_gbuffer_uv_da(const texir_scene* sc, const float* rays, const float* d
     return finish_launch("k_gbuffer_uv_da");
 }
 
-int texir_irradiance_fwd(const texir_scene* sc, const float* pos, const float* nrm, const float* shift,
-                         const int32_t* order, int64_t P, int N, int mode, float* E, void* stream) {
-    if (check_scene_tex("texir_irradiance_fwd", sc) || check_pn("texir_irradiance_fwd", P, N) ||
-        check_mode("texir_irradiance_fwd", mode))
-        return 1;
-    if (mode == TEXIR_MODE_IMPORTANCE) TX_FAIL("texir_irradiance_fwd: importance mode needs roughness; use uniform/cosine");
+static int irradiance_launch(const char* fn, const texir_scene* sc, const float* pos, const float* nrm, const float* shift,
+                             const int32_t* order, int64_t P, int N, int mode, const PeerOut& E, void* stream) {
+    if (check_scene_tex(fn, sc) || check_pn(fn, P, N) || check_mode(fn, mode)) return 1;
+    if (mode == TEXIR_MODE_IMPORTANCE) TX_FAIL(std::string(fn) + ": importance mode needs roughness; use uniform/cosine");
     if (P == 0) return 0;
-    if (!pos || !nrm || !shift || !E) TX_FAIL("texir_irradiance_fwd: NULL argument");
+    if (!pos || !nrm || !shift) TX_FAIL(std::string(fn) + ": NULL argument");
+    for (int k = 0; k < E.n; ++k)
+        if (!E.p[k]) TX_FAIL(std::string(fn) + ": NULL output");
     DeviceGuard guard(sc->info.device);
     const int G = group_lanes(N), ab = patch_bits(N);
     const int64_t warps = (P + (32 / G) - 1) / (32 / G);
     unsigned g = grid_for(warps * 32, 128);
+    cudaStream_t st = (cudaStream_t)stream;
     if (sc->info.bvh_kind == TEXIR_BVH8)
-        k_irradiance<8><<<g, 128, 0, (cudaStream_t)stream>>>(sc->view, pos, nrm, shift, order, P, N, mode, G, ab, E);
+        k_irradiance<8><<<g, 128, 0, st>>>(sc->view, pos, nrm, shift, order, P, N, mode, G, ab, E);
     else if (stream_mode() == 3 && G == 32 && use_qnodes())
         if (use_front())
-            k_irradiance_lean<4, true><<<g, 128, 0, (cudaStream_t)stream>>>(sc->view, pos, nrm, shift, order, P, N, mode, ab, E);
+            k_irradiance_lean<4, true><<<g, 128, 0, st>>>(sc->view, pos, nrm, shift, order, P, N, mode, ab, E);
         else
-            k_irradiance_lean<4><<<g, 128, 0, (cudaStream_t)stream>>>(sc->view, pos, nrm, shift, order, P, N, mode, ab, E);
+            k_irradiance_lean<4><<<g, 128, 0, st>>>(sc->view, pos, nrm, shift, order, P, N, mode, ab, E);
     else if (stream_mode() == 3 && G == 32)
-        k_irradiance_lean<3><<<g, 128, 0, (cudaStream_t)stream>>>(sc->view, pos, nrm, shift, order, P, N, mode, ab, E);
+        k_irradiance_lean<3><<<g, 128, 0, st>>>(sc->view, pos, nrm, shift, order, P, N, mode, ab, E);
     else if (stream_mode() >= 2 && use_qnodes())
-        k_irradiance<4><<<g, 128, 0, (cudaStream_t)stream>>>(sc->view, pos, nrm, shift, order, P, N, mode, G, ab, E);
+        k_irradiance<4><<<g, 128, 0, st>>>(sc->view, pos, nrm, shift, order, P, N, mode, G, ab, E);
     else if (stream_mode() >= 2)
-        k_irradiance<3><<<g, 128, 0, (cudaStream_t)stream>>>(sc->view, pos, nrm, shift, order, P, N, mode, G, ab, E);
+        k_irradiance<3><<<g, 128, 0, st>>>(sc->view, pos, nrm, shift, order, P, N, mode, G, ab, E);
     else
-        k_irradiance<2><<<g, 128, 0, (cudaStream_t)stream>>>(sc->view, pos, nrm, shift, order, P, N, mode, G, ab, E);
+        k_irradiance<2><<<g, 128, 0, st>>>(sc->view, pos, nrm, shift, order, P, N, mode, G, ab, E);
     return finish_launch("k_irradiance");
+}
+
+int texir_irradiance_fwd(const texir_scene* sc, const float* pos, const float* nrm, const float* shift,
+                         const int32_t* order, int64_t P, int N, int mode, float* E, void* stream) {
+    PeerOut o{};
+    o.p[0] = E;
+    o.n = 1;
+    return irradiance_launch("texir_irradiance_fwd", sc, pos, nrm, shift, order, P, N, mode, o, stream);
+}
+
+int texir_irradiance_fwd_peers(const texir_scene* sc, const float* pos, const float* nrm, const float* shift,
+                               const int32_t* order, int64_t P, int N, int mode, float* const* E_peers_host,
+                               int n_peers, void* stream) {
+    if (!E_peers_host || n_peers <= 0 || n_peers > TEXIR_MAX_PEERS) TX_FAIL("texir_irradiance_fwd_peers: bad peer list");
+    if (!order) TX_FAIL("texir_irradiance_fwd_peers: order (this rank's point list) is required");
+    PeerOut o{};
+    for (int k = 0; k < n_peers; ++k) o.p[k] = E_peers_host[k];
+    o.n = n_peers;
+    return irradiance_launch("texir_irradiance_fwd_peers", sc, pos, nrm, shift, order, P, N, mode, o, stream);
 }
 
 static int shade_common(const char* fn, const texir_scene* sc, ShadeArgs& a) {
@@ -1598,7 +1694,7 @@ static int shade_bwd_impl(const char* fn, const texir_scene* sc, ShadeArgs& a, v
     }
     DeviceGuard guard(sc->info.device);
     // rays are needed only for a gradient whose forward stash is missing
-    const bool want_r = a.g_rough || a.gr.tex, want_a = a.g_albedo || a.ga.tex;
+    const bool want_r = (a.g_rough || a.gr.tex) && !a.no_render_rough, want_a = a.g_albedo || (a.ga.tex && a.render_albedo);
     const bool need_rays = (want_r && !a.drgb_drough) || (want_a && a.N_diff > 0 && !a.ediff);
     if (!need_rays) {
         k_shade_bwd_stash<<<grid_for(a.P, 256), 256, 0, (cudaStream_t)stream>>>(a);
@@ -1607,12 +1703,13 @@ static int shade_bwd_impl(const char* fn, const texir_scene* sc, ShadeArgs& a, v
     return launch_shade<true>(sc, a, stream);
 }
 
-int texir_shade_bwd_tex(const texir_scene* sc, const float* nrm, const float* albedo, const float* rough,
+int texir_shade_bwd_mat(const texir_scene* sc, const float* nrm, const float* albedo, const float* rough,
                         const float* pos, const float* cam, const float* irr, const float* shift_spec,
                         const float* shift_diff, int64_t P, int N_spec, int N_diff, int mode_spec, int mode_diff,
                         float eps, const float* g_rgb, const float* drgb_drough, const float* ediff, const float* uv,
-                        const float* uv_da, float* g_tex_a, float* g_mips_a, int Ha, int Wa, int La, float* g_tex_r,
-                        float* g_mips_r, int Hr, int Wr, int Lr, void* stream) {
+                        const float* uv_da, const float* add_a, const float* add_r, const float* add_rw,
+                        int render_albedo, int render_rough, int render_rough_bilinear, float* g_tex_a, float* g_mips_a,
+                        int Ha, int Wa, int La, float* g_tex_r, float* g_mips_r, int Hr, int Wr, int Lr, void* stream) {
     ShadeArgs a{};
     a.nrm = nrm; a.albedo = albedo; a.rough = rough; a.pos = pos; a.cam = cam; a.irr = irr;
     a.shift_spec = shift_spec; a.shift_diff = shift_diff;
@@ -1623,13 +1720,30 @@ int texir_shade_bwd_tex(const texir_scene* sc, const float* nrm, const float* al
     a.uv = uv; a.uv_da = uv_da;
     a.ga = TexGrad{g_tex_a, g_mips_a, Ha, Wa, 3, La};
     a.gr = TexGrad{g_tex_r, g_mips_r, Hr, Wr, 1, Lr};
-    if (!uv) TX_FAIL("texir_shade_bwd_tex: uv is NULL");
-    if (!g_tex_a && !g_tex_r) TX_FAIL("texir_shade_bwd_tex: no gradient texture given");
+    a.add_a = add_a; a.add_r = add_r; a.add_rw = add_rw;
+    a.render_albedo = render_albedo; a.render_rough_bilinear = render_rough_bilinear;
+    a.no_render_rough = !render_rough;
+    const char* fn = "texir_shade_bwd_mat";
+    if (!uv) TX_FAIL(std::string(fn) + ": uv is NULL");
+    if (!g_tex_a && !g_tex_r) TX_FAIL(std::string(fn) + ": no gradient texture given");
+    if ((add_a && !g_tex_a) || ((add_r || add_rw) && !g_tex_r)) TX_FAIL(std::string(fn) + ": direct gradient without its texture");
     if ((g_tex_a && (Ha <= 0 || Wa <= 0 || La < 0 || La != mip_level_count(Ha, Wa, La) || (La > 0 && !g_mips_a))) ||
         (g_tex_r && (Hr <= 0 || Wr <= 0 || Lr < 0 || Lr != mip_level_count(Hr, Wr, Lr) || (Lr > 0 && !g_mips_r))))
-        TX_FAIL("texir_shade_bwd_tex: bad gradient-texture shape / level count");
-    if (!uv_da && (La > 0 || Lr > 0)) TX_FAIL("texir_shade_bwd_tex: mip levels given without uv_da");
-    return shade_bwd_impl("texir_shade_bwd_tex", sc, a, stream);
+        TX_FAIL(std::string(fn) + ": bad gradient-texture shape / level count");
+    if (!uv_da && (La > 0 || Lr > 0)) TX_FAIL(std::string(fn) + ": mip levels given without uv_da");
+    return shade_bwd_impl(fn, sc, a, stream);
+}
+
+int texir_shade_bwd_tex(const texir_scene* sc, const float* nrm, const float* albedo, const float* rough,
+                        const float* pos, const float* cam, const float* irr, const float* shift_spec,
+                        const float* shift_diff, int64_t P, int N_spec, int N_diff, int mode_spec, int mode_diff,
+                        float eps, const float* g_rgb, const float* drgb_drough, const float* ediff, const float* uv,
+                        const float* uv_da, float* g_tex_a, float* g_mips_a, int Ha, int Wa, int La, float* g_tex_r,
+                        float* g_mips_r, int Hr, int Wr, int Lr, void* stream) {
+    return texir_shade_bwd_mat(sc, nrm, albedo, rough, pos, cam, irr, shift_spec, shift_diff, P, N_spec, N_diff, mode_spec,
+                               mode_diff, eps, g_rgb, drgb_drough, ediff, uv, uv_da, nullptr, nullptr, nullptr,
+                               g_tex_a != nullptr, g_tex_r != nullptr, 0, g_tex_a, g_mips_a, Ha, Wa, La, g_tex_r, g_mips_r, Hr, Wr,
+                               Lr, stream);
 }
 
 int texir_shade_bwd(const texir_scene* sc, const float* nrm, const float* albedo, const float* rough,

@@ -39,6 +39,11 @@ class HotPathMixin:
         sc.set_texture(self.texture)
         return sc
 
+    def _draw_shift(self, b: int, device) -> torch.Tensor:
+        """the Cranley-Patterson shift of one generate_dir call: torch.rand(b, 1, 2) on the CPU generator, as the
+        reference draws it (utils/sample_util.py:102)"""
+        return draw_shift(b, device)
+
     # -- reference methods ------------------------------------------------------------------------
     def query_irf(self, points, directions, num_sample):
         """mat_nvdiffrast.py:292 -- points [P,N,3], directions [P,N,1,3] -> [P,N,3] (CUDA)"""
@@ -68,8 +73,8 @@ class HotPathMixin:
         if getattr(self, "fused", True):
             b, dev = normal.shape[0], normal.device
             # RNG order of the reference: the diffuse generate_dir (if any) draws first
-            shift_diff = draw_shift(b, dev) if relight else None
-            shift_spec = draw_shift(b, dev)
+            shift_diff = self._draw_shift(b, dev) if relight else None
+            shift_spec = self._draw_shift(b, dev)
             rgb = ops.shade(self._scene(), normal, albedo, roughness, points, cam_position, irr, shift_spec,
                             num_spec=n_spec, shift_diff=shift_diff, num_diff=n_diff if relight else 0,
                             mode_spec=self.sample_type[1], mode_diff=self.sample_type[0], eps=eps,
@@ -143,7 +148,7 @@ class MaterialModel(HotPathMixin, nn.Module):
                  brdf_eps: float = 1e-14, device=None, materials_a_res: int = 0, materials_r_res: int = 0,
                  fused: bool = True, backward_mode: str = "stash", cube_res: int = 128, irrt=None,
                  max_mip_level: Optional[int] = 13, hdr_exposure: float = 5.0, vertex_normals=None,
-                 scene: Optional[Scene] = None):
+                 scene: Optional[Scene] = None, flip_tex_coords: bool = True, shard=None):
         super().__init__()
         # `scene`: share an already built Scene (BVH + uploads) instead of building another one from the arrays
         self.scene = scene if scene is not None else Scene(vertices, triangles, triangle_uvs, device=device)
@@ -158,6 +163,16 @@ class MaterialModel(HotPathMixin, nn.Module):
         self.cube_res = int(cube_res)
         self.max_mip_level = max_mip_level      # get_mip_level(8192) = 13, mat_nvdiffrast.py:65
         self.hdr_exposure = float(hdr_exposure)
+        # The reference addresses materials_a / materials_r / irrt through self.uvs, which pyredner.load_obj delivers
+        # with flip_tex_coords=True (v' = 1 - v; mat_nvdiffrast.py:194,128-139), while the Open3D ray caster keeps the
+        # OBJ's raw v against a vertically flipped radiance texture (:89-90).  `scene` holds the raw per-corner UVs, so
+        # the texture fetches of forward() see (u, 1 - v); irt.hdr is loaded unflipped (:73) for the same reason.
+        self.flip_tex_coords = bool(flip_tex_coords)
+        # (rank, world): render only this rank's pixels (parallel.local_pixels gives the matching slice of an image);
+        # forward() then returns flat [P_local, C] tensors and parallel.allreduce_gradients completes the step
+        self.shard = None if shard is None else (int(shard[0]), int(shard[1]))
+        self.mat_ws = ops.MatWorkspace()
+        self._warned_normals = False
         dev = self.scene.device
         # trainable material textures, same names / initial values as mat_nvdiffrast.py:68-69
         if materials_a_res > 0:
@@ -170,6 +185,16 @@ class MaterialModel(HotPathMixin, nn.Module):
             self.normals = nn.Parameter(torch.as_tensor(vertex_normals, dtype=torch.float32).to(dev), requires_grad=False)
             self.triangles = nn.Parameter(torch.as_tensor(np.asarray(triangles), dtype=torch.int64).to(dev),
                                           requires_grad=False)
+
+    def _draw_shift(self, b: int, device) -> torch.Tensor:
+        """sharded model: every rank draws the shift of ALL 6 * cube_res^2 pixels (so the CPU generator advances as on one
+        GPU and a pixel gets the same shift whatever the world size) and keeps its own pixels'"""
+        total = 6 * self.cube_res * self.cube_res
+        if self.shard is None or self.shard[1] == 1 or b * self.shard[1] != total:
+            return draw_shift(b, device)
+        from .parallel import local_pixels
+        full = torch.rand(total, 1, 2)
+        return local_pixels(full.reshape(6, -1, 2), self.shard[0], self.shard[1], 6).reshape(-1, 1, 2).to(device)
 
     def forward_gbuffer(self, normal, points, cam_position, irr, albedo=None, roughness=None, texc=None, texd=None):
         """G-buffer in, shaded colour out.  Materials come either as per-pixel tensors or, given texc [P,2] (and texd
@@ -184,26 +209,40 @@ class MaterialModel(HotPathMixin, nn.Module):
             roughness = roughness.reshape(*normal.shape[:-1], 1)
         return self.render(normal, albedo, roughness, points, cam_position, irr)
 
-    def _render_textured(self, normal, albedo, roughness, points, cam_position, irr, texc, texd, tex_a, tex_r):
-        """render() for materials that were fetched from textures: same result dict, but the render's backward kernel
-        scatters straight into the gradients of tex_a / tex_r (ops.shade_textured) instead of handing per-pixel
-        gradients to a separate scatter; falls back to the plain composition when the model is not `fused` or relights"""
-        if not getattr(self, "fused", True) or getattr(self, "relighting", False):
-            return self.render(normal, albedo, roughness, points, cam_position, irr)
+    def _render_textured(self, normal, albedo, roughness, roughness_womipmap, points, cam_position, irr, texc, texd, stage):
+        """stages 1 and 2 of forward(): the result dict of render() plus roughness / roughness_womipmap.  Fused: one
+        autograd node does the four fetches, the render and -- in its backward -- the scatter of every output's gradient
+        into the material textures (ops.mat_stage).  Not fused (or relighting): the reference's own composition."""
         lead = normal.shape[:-1]
+        if albedo is not None:
+            if stage == 1:
+                res = self.render(normal, albedo.detach(), roughness_womipmap, points, cam_position, irr)
+            else:
+                res = self.render(normal, albedo, roughness, points, cam_position, irr)
+            return res, roughness, roughness_womipmap
         n, p = normal.reshape(-1, 3), points.reshape(-1, 3)
-        shift_spec = draw_shift(n.shape[0], n.device)
-        rgb = ops.shade_textured(self._scene(), tex_a, tex_r, n, albedo.reshape(-1, 3), roughness.reshape(-1, 1), p,
-                                 cam_position, irr.reshape(-1, 3), shift_spec, texc, texd, num_spec=int(self.sample_l[1]),
-                                 max_mip_level=self.max_mip_level, mode_spec=self.sample_type[1],
-                                 eps=getattr(self, "brdf_eps", 1e-14), backward=getattr(self, "backward_mode", "stash"))
-        return {"rgb": rgb.reshape(*lead, 3), "albedo": albedo, "normal": normal.detach(),
-                "position": (points + 2e-2 * normal).detach()}
+        shift_spec = self._draw_shift(n.shape[0], n.device)
+        rgb, alb, rough, rough_w, _ = ops.mat_stage(
+            self._scene(), self.mat_ws, self.materials_a, self.materials_r, self.irrt, n, p, cam_position, texc, texd,
+            shift_spec, stage=stage, num_spec=int(self.sample_l[1]), max_mip_level=self.max_mip_level,
+            mode_spec=self.sample_type[1], eps=getattr(self, "brdf_eps", 1e-14),
+            backward=getattr(self, "backward_mode", "stash"))
+        alb = alb.reshape(*lead, 3)
+        res = {"rgb": rgb.reshape(*lead, 3), "albedo": alb.detach() if stage == 1 else alb, "normal": normal.detach(),
+               "position": (points + 2e-2 * normal).detach()}
+        return res, rough.reshape(*lead, 1), rough_w.reshape(*lead, 1)
 
     def gbuffers(self, mvp: torch.Tensor, cam_position: torch.Tensor) -> dict:
         """mat_nvdiffrast.py:116-128: position / normal / texc / texd / mask of the 6 cube faces"""
         dev = self.scene.device
-        gb = ops.gbuffer_mvp(self._scene(), mvp.to(dev), cam_position.to(dev), self.cube_res)
+        gb = ops.gbuffer_mvp(self._scene(), mvp.to(dev), cam_position.to(dev), self.cube_res, shard=self.shard,
+                             flip_v=self.flip_tex_coords)
+        if not hasattr(self, "normals") and not self._warned_normals:
+            import warnings
+            warnings.warn("MaterialModel was built without vertex_normals: the G-buffer normal is the geometric face normal "
+                          "turned towards the camera, whereas the reference interpolates the OBJ's vertex normals "
+                          "(mat_nvdiffrast.py:120); pass vertex_normals= for meshes with smooth shading normals")
+            self._warned_normals = True
         if hasattr(self, "normals"):
             tri = self.triangles[gb["primitive_ids"].long().clamp_(min=0) % self.triangles.shape[0]]
             b = gb["primitive_uvs"]
@@ -225,11 +264,16 @@ class MaterialModel(HotPathMixin, nn.Module):
         normal, pos, mask = gb["normal"].detach(), gb["position"].detach(), gb["mask"]
         shp = normal.shape[:-1]
         texc, texd = gb["texc"].reshape(-1, 2), gb["texd"].reshape(-1, 4)
-        mip = dict(filter_mode="linear-mipmap-linear", max_mip_level=self.max_mip_level)
-        albedo = ops.texture_fetch(self.materials_a, texc, texd, **mip).reshape(*shp, 3)
-        roughness_womipmap = ops.texture_fetch(self.materials_r, texc, None, "linear").reshape(*shp, 1)
-        roughness = ops.texture_fetch(self.materials_r, texc, texd, **mip).reshape(*shp, 1)
-        irr = ops.texture_fetch(self.irrt, texc, texd, **mip).reshape(*shp, 3)
+        fused = getattr(self, "fused", True) and not getattr(self, "relighting", False)
+        if stage in (1, 2) and fused:
+            # fetches, render and the texture-space backward are ONE autograd node (ops.mat_stage)
+            albedo = roughness = roughness_womipmap = irr = None
+        else:
+            mip = dict(filter_mode="linear-mipmap-linear", max_mip_level=self.max_mip_level)
+            albedo = ops.texture_fetch(self.materials_a, texc, texd, **mip).reshape(*shp, 3)
+            roughness_womipmap = ops.texture_fetch(self.materials_r, texc, None, "linear").reshape(*shp, 1)
+            roughness = ops.texture_fetch(self.materials_r, texc, texd, **mip).reshape(*shp, 1)
+            irr = ops.texture_fetch(self.irrt, texc, texd, **mip).reshape(*shp, 3)
         if stage == -1:
             # "a simple trick to locate the light source": only texels brighter than 0.5 (before exposure) emit
             source = self.texture
@@ -243,16 +287,24 @@ class MaterialModel(HotPathMixin, nn.Module):
                 self.texture = source
         elif stage == 0:
             res = {"rgb": irr * albedo / np.pi, "albedo": albedo, "normal": normal, "position": pos + 1e-1 * normal}
-        elif stage == 1:
-            res = self._render_textured(normal, albedo.detach(), roughness_womipmap, pos + 1e-2 * normal, cam_position, irr,
-                                        texc, None, None, self.materials_r)
-        elif stage == 2:
-            res = self._render_textured(normal, albedo, roughness, pos + 1e-2 * normal, cam_position, irr, texc, texd,
-                                        self.materials_a, self.materials_r)
+        elif stage in (1, 2):
+            res, roughness, roughness_womipmap = self._render_textured(normal, albedo, roughness, roughness_womipmap,
+                                                                       pos + 1e-2 * normal, cam_position, irr, texc, texd,
+                                                                       stage)
         else:
             raise ValueError("stage must be -1, 0, 1 or 2")
         res.update({"empty_mask": mask, "roughness_womipmap": roughness_womipmap, "roughness": roughness})
         return res
+
+
+def _seam_mask(index_texture, device) -> torch.Tensor:
+    """tracer_o3d_irt.py:138,177: texels whose index entry sums to zero -- summed in the array's OWN dtype, like the
+    reference's numpy does (the index texture is a 16-bit PNG, so the sum wraps modulo 65536 there too)"""
+    if isinstance(index_texture, torch.Tensor):
+        idx = index_texture
+        return ((idx[..., 0] + idx[..., 1] + idx[..., 2]) == 0).to(device)
+    idx = np.asarray(index_texture)
+    return torch.from_numpy(np.ascontiguousarray((idx[:, :, 0] + idx[:, :, 1] + idx[:, :, 2]) == 0)).to(device)
 
 
 class TracerO3d(nn.Module):
@@ -270,6 +322,34 @@ class TracerO3d(nn.Module):
         self.texture = texture if isinstance(texture, torch.Tensor) else torch.from_numpy(np.asarray(texture))
         self.sample_l = list(sample_l)
         self.sample_type = list(sample_type)
+        self.position_texture = None    # set by calcute_position_normal_texture, read by forward()
+        self.normal_texture = None
+        self.index_texture = None
+
+    def calcute_position_normal_texture(self, position_normal_list, index_texture):
+        """tracer_o3d_irt.py:115-142 (the reference's spelling): every texel of the index texture [H,W,3] = (row, col,
+        view) in units of 1/50000 of the panorama picks its position and normal from that view's [h,w,6]
+        position-normal panorama; texels whose entry is all zero (seams) get zeros.  Same integer arithmetic as the
+        reference's numpy, done on the device."""
+        dev = self.scene.device
+        idx = torch.as_tensor(np.asarray(index_texture).astype(np.int64), device=dev)
+        H, W = idx.shape[:2]
+        pos = torch.zeros(H, W, 3, dtype=torch.float32, device=dev)
+        nrm = torch.zeros(H, W, 3, dtype=torch.float32, device=dev)
+        for view in torch.unique(idx[..., 2]).tolist():
+            pano = torch.as_tensor(position_normal_list[view], dtype=torch.float32, device=dev)
+            h, w = pano.shape[:2]
+            sel = idx[..., 2] == view
+            # (index / 50000 * size).astype(int): float64 division, truncation, then np.clip
+            col = (idx[..., 1][sel].double() / 50000 * w).long().clamp_(0, w - 1)
+            row = (idx[..., 0][sel].double() / 50000 * h).long().clamp_(0, h - 1)
+            pos[sel] = pano[row, col, 0:3]
+            nrm[sel] = pano[row, col, 3:6]
+        seam = _seam_mask(index_texture, dev)
+        pos[seam] = 0.0
+        nrm[seam] = 0.0
+        self.position_texture, self.normal_texture, self.index_texture = pos, nrm, index_texture
+        return pos, nrm
 
     def query_irf(self, points, directions, num_sample):
         """tracer_o3d_irt.py:240"""
@@ -287,10 +367,19 @@ class TracerO3d(nn.Module):
             raise ValueError("IrT sampling must be 'uniform' or 'cosine'")
         return ops.irradiance(self.scene, position, normal, shift, int(self.sample_l[0]), mode)
 
-    def forward(self, position_texture: torch.Tensor, normal_texture: torch.Tensor, index_texture=None,
-                shift: Optional[torch.Tensor] = None):
+    def forward(self, position_texture: Optional[torch.Tensor] = None, normal_texture: Optional[torch.Tensor] = None,
+                index_texture=None, shift: Optional[torch.Tensor] = None):
         """position_texture, normal_texture [H,W,3] (CUDA) -> irradiance texture [H,W,3]; texels whose
-        index-texture entry is all zero (seams) are zeroed (tracer_o3d_irt.py:176-178)."""
+        index-texture entry is all zero (seams) are zeroed (tracer_o3d_irt.py:176-178).  Called without arguments
+        like the reference's runner does (trainer/generate_ir_texture.py:77: ``self.model()``) it uses the textures
+        calcute_position_normal_texture() left on the model."""
+        if position_texture is None or normal_texture is None:
+            if self.position_texture is None or self.normal_texture is None:
+                raise ValueError("TracerO3d.forward(): no position / normal textures -- pass them, or call "
+                                 "calcute_position_normal_texture(position_normal_list, index_texture) first")
+            position_texture, normal_texture = self.position_texture, self.normal_texture
+            if index_texture is None:
+                index_texture = self.index_texture
         shp = position_texture.shape
         pos = position_texture.reshape(-1, 3)
         nrm = normal_texture.reshape(-1, 3)
@@ -298,7 +387,5 @@ class TracerO3d(nn.Module):
             raise AssertionError("texel count must be a multiple of 512 (tracer_o3d_irt.py:161)")
         irr = self.irradiance(pos, nrm, shift).reshape(shp)
         if index_texture is not None:
-            idx = torch.as_tensor(index_texture, device=irr.device)
-            seam = (idx[..., 0] + idx[..., 1] + idx[..., 2]) == 0
-            irr = irr.masked_fill(seam.unsqueeze(-1), 0.0)
+            irr = irr.masked_fill(_seam_mask(index_texture, irr.device).unsqueeze(-1), 0.0)
         return irr

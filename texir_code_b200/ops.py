@@ -161,6 +161,16 @@ def diffuse_reflectance(lighting, l, n, albedo, sample_type: str = "uniform"):
 # --------------------------------------------------------------------------------------------------
 # fused render
 # --------------------------------------------------------------------------------------------------
+def _check_recompute_texture(ctx, casts_rays: bool) -> None:
+    """a backward that re-casts the rays must find the radiance texture of its forward pass: set_texture repacks in place
+    (stage -1 swaps self.texture and swaps it back, mat_nvdiffrast.py:143-150), so a texture replaced in between would
+    silently give the gradients of another scene"""
+    if casts_rays and ctx.scene.texture_key() != ctx.tex_key:
+        raise _lib.TexirError("backward='recompute' re-traces the rays against the scene's radiance texture, which has been "
+                              "replaced since the forward pass; use backward='stash' or restore the texture first")
+
+
+
 class _Shade(torch.autograd.Function):
     """rgb = albedo * dfac + (1/N) sum_i L_i w_i(roughness).  backward='stash': the forward kernel also
     emits d rgb / d roughness by forward-mode differentiation (roughness is the only non-trivial
@@ -190,6 +200,7 @@ class _Shade(torch.autograd.Function):
                                                    mode_diff, eps, _ptr(rgb), _ptr(drgb), _ptr(ediff),
                                                    _stream_ptr(dev)), "texir_shade_fwd")
         ctx.scene = scene
+        ctx.tex_key = scene.texture_key()
         ctx.cfg = (P, N_spec, N_diff, mode_spec, mode_diff, eps)
         ctx.shapes = (albedo.shape, roughness.shape, None if irr is None else irr.shape)
         ctx.have = (drgb is not None, ediff is not None, irrc is not None, shd is not None)
@@ -213,6 +224,7 @@ class _Shade(torch.autograd.Function):
         P, N_spec, N_diff, mode_spec, mode_diff, eps = ctx.cfg
         dev = nrm.device
         need = ctx.needs_input_grad  # (scene, normal, albedo, roughness, points, cam, irr, ...)
+        _check_recompute_texture(ctx, (need[3] and drgb is None) or (need[2] and N_diff > 0 and ediff is None))
         g = _f32c(g_rgb).reshape(P, 3)
         g_alb = torch.empty(P, 3, dtype=torch.float32, device=dev) if need[2] else None
         g_rough = torch.empty(P, dtype=torch.float32, device=dev) if need[3] else None
@@ -270,6 +282,7 @@ class _ShadeTextured(torch.autograd.Function):
                                                    mode_diff, eps, _ptr(rgb), _ptr(drgb), _ptr(ediff),
                                                    _stream_ptr(dev)), "texir_shade_fwd")
         ctx.scene = scene
+        ctx.tex_key = scene.texture_key()
         ctx.cfg = (P, N_spec, N_diff, mode_spec, mode_diff, eps, levels_a, levels_r)
         ctx.shape_a = tuple(materials_a.shape) if materials_a is not None else None
         ctx.shape_r = tuple(materials_r.shape) if materials_r is not None else None
@@ -295,6 +308,7 @@ class _ShadeTextured(torch.autograd.Function):
         P, N_spec, N_diff, mode_spec, mode_diff, eps, La, Lr = ctx.cfg
         dev = nrm.device
         need = ctx.needs_input_grad  # (scene, materials_a, materials_r, ...)
+        _check_recompute_texture(ctx, (need[2] and drgb is None) or (need[1] and N_diff > 0 and ediff is None))
         lib = _lib.load()
         g = _f32c(g_rgb).reshape(P, 3)
 
@@ -345,6 +359,161 @@ def shade_textured(scene: Scene, materials_a: Optional[torch.Tensor], materials_
 
 
 # --------------------------------------------------------------------------------------------------
+# the whole Mat-stage step as ONE autograd node (fetch -> render -> texture-space backward)
+# --------------------------------------------------------------------------------------------------
+class MatWorkspace:
+    """Buffers a Mat-stage step re-uses from one optimiser step to the next (one per model and device):
+
+      * the mip pyramids of materials_a / materials_r / irrt: storage re-used from step to step; the trainable
+        textures' pyramids are rebuilt every step (two launches each), the frozen IrT's only when the tensor changed;
+      * the texture-space scatter targets of the backward kernel (level 0 + pyramid per material texture).  They are
+        zeroed once; the fold kernel that consumes them leaves them zeroed again, so no step pays for a memset of the
+        150 MiB they occupy at the reference's texture sizes (2048^2 x 3 and 4096^2 x 1, mat_nvdiffrast.py:68-69).
+    """
+
+    def __init__(self):
+        self._pyr = {}       # name -> (key, mips, L)
+        self._scatter = {}   # name -> (shape key, level-0 buffer, pyramid buffer)
+        self.dirty = False   # a backward died between the scatter and the fold: re-zero before the next use
+
+    def pyramid(self, name: str, tex: torch.Tensor, max_mip_level: Optional[int]):
+        key = (tex.data_ptr(), tex._version, tuple(tex.shape), max_mip_level)
+        hit = self._pyr.get(name)
+        # a trainable texture is rebuilt on every step (its optimiser updates it in between, possibly through .data,
+        # which no version counter sees); a frozen one (the IrT, requires_grad=False) only when it was replaced
+        if hit is not None and hit[0] == key and not tex.requires_grad:
+            return hit[1], hit[2]
+        H, W, C = (int(x) for x in tex.shape)
+        L = mip_levels(H, W, max_mip_level)
+        lib = _lib.load()
+        n = max(int(lib.texir_texture_mip_elems(H, W, C, L)), 1)
+        mips = hit[1] if (hit is not None and hit[1].numel() == n and hit[1].device == tex.device) else \
+            torch.empty(n, dtype=torch.float32, device=tex.device)
+        t = _f32c(tex)
+        with torch.cuda.device(tex.device):
+            _lib.check(lib.texir_texture_mip_build_fast(_ptr(t), H, W, C, L, _ptr(mips), _stream_ptr(tex.device)),
+                       "texir_texture_mip_build_fast")
+        self._pyr[name] = (key, mips, L)
+        return mips, L
+
+    def scatter_target(self, name: str, shape, L: int, dev):
+        H, W, C = shape
+        key = (H, W, C, L, str(dev))
+        hit = self._scatter.get(name)
+        if hit is None or hit[0] != key or self.dirty:
+            n = max(int(_lib.load().texir_texture_mip_elems(H, W, C, L)), 1)
+            hit = (key, torch.zeros(H, W, C, dtype=torch.float32, device=dev), torch.zeros(n, dtype=torch.float32, device=dev))
+            self._scatter[name] = hit
+        return hit[1], hit[2]
+
+
+class _MatStage(torch.autograd.Function):
+    """(materials_a, materials_r) -> (rgb, albedo, roughness, roughness_womipmap, irr) per pixel: the four dr.texture
+    fetches of models/mat_nvdiffrast.py:131-139, the fused render of :179-182, and ONE backward kernel that takes the
+    gradients of all outputs and accumulates into the two textures' gradients (texir_shade_bwd_mat), then one fold
+    launch per texture."""
+
+    @staticmethod
+    def forward(ctx, materials_a, materials_r, ws, scene, irrt, normal, points, cam, texc, texd, shift_spec, stage,
+                N_spec, mode_spec, eps, backward_mode, max_mip_level):
+        dev = normal.device
+        P = int(normal.shape[0])
+        lib = _lib.load()
+        nrm, pos = _f32c(normal), _f32c(points)
+        camc = _f32c(cam, dev).reshape(3)
+        uv, da = _f32c(texc).reshape(P, 2), _f32c(texd).reshape(P, 4)
+        shs = _f32c(shift_spec, dev).reshape(P, 2)
+        ta, tr, ti = _f32c(materials_a), _f32c(materials_r), _f32c(irrt)
+        ma, La = ws.pyramid("a", materials_a, max_mip_level)
+        mr, Lr = ws.pyramid("r", materials_r, max_mip_level)
+        mi, Li = ws.pyramid("i", irrt, max_mip_level)
+        f32 = dict(dtype=torch.float32, device=dev)
+        albedo, irr = torch.empty(P, 3, **f32), torch.empty(P, 3, **f32)
+        rough, rough_w = torch.empty(P, **f32), torch.empty(P, **f32)
+        (Ha, Wa, _), (Hr, Wr, _), (Hi, Wi, _) = ta.shape, tr.shape, ti.shape
+        need_a = bool(materials_a.requires_grad) and stage == 2
+        need_r = bool(materials_r.requires_grad)
+        stash = backward_mode == "stash"
+        rgb = torch.empty(P, 3, **f32)
+        drgb = torch.empty(P, 3, **f32) if (stash and need_r) else None
+        rough_in = rough_w if stage == 1 else rough
+        with torch.cuda.device(dev):
+            st = _stream_ptr(dev)
+            _lib.check(lib.texir_mat_fetch(_ptr(ta), _ptr(ma), Ha, Wa, La, _ptr(tr), _ptr(mr), Hr, Wr, Lr, _ptr(ti), _ptr(mi),
+                                           Hi, Wi, Li, _ptr(uv), _ptr(da), P, _ptr(albedo), _ptr(rough), _ptr(rough_w),
+                                           _ptr(irr), st), "texir_mat_fetch")
+            _lib.check(lib.texir_shade_fwd(scene.handle, _ptr(nrm), _ptr(albedo), _ptr(rough_in), _ptr(pos), _ptr(camc),
+                                           _ptr(irr), _ptr(shs), None, P, N_spec, 0, mode_spec, _lib.MODE_UNIFORM, eps,
+                                           _ptr(rgb), _ptr(drgb), None, st), "texir_shade_fwd")
+        ctx.ws, ctx.scene = ws, scene
+        ctx.tex_key = scene.texture_key()
+        ctx.cfg = (P, N_spec, mode_spec, eps, stage, La, Lr, (int(Ha), int(Wa)), (int(Hr), int(Wr)), need_a)
+        ctx.have_drgb = drgb is not None
+        saved = [nrm, albedo, rough_in, pos, camc, irr, shs, uv, da] + ([drgb] if drgb is not None else [])
+        ctx.save_for_backward(*saved)
+        ctx.mark_non_differentiable(irr)
+        return rgb, albedo, rough.unsqueeze(-1), rough_w.unsqueeze(-1), irr
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_albedo, g_rough, g_rough_w, _g_irr):
+        saved = list(ctx.saved_tensors)
+        nrm, albedo, rough_in, pos, camc, irr, shs, uv, da = saved[:9]
+        drgb = saved[9] if ctx.have_drgb else None
+        P, N_spec, mode_spec, eps, stage, La, Lr, (Ha, Wa), (Hr, Wr), render_a = ctx.cfg
+        dev = nrm.device
+        need_a, need_r = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        need_a = need_a and (render_a or g_albedo is not None)   # stage 1: the render saw albedo.detach()
+        if not need_a and not need_r:
+            return (None,) * 17
+        _check_recompute_texture(ctx, need_r and drgb is None)
+        lib, ws = _lib.load(), ctx.ws
+        g = _f32c(g_rgb).reshape(P, 3) if g_rgb is not None else torch.zeros(P, 3, dtype=torch.float32, device=dev)
+        add_a = _f32c(g_albedo).reshape(P, 3) if (g_albedo is not None and need_a) else None
+        add_r = _f32c(g_rough).reshape(P) if (g_rough is not None and need_r) else None
+        add_rw = _f32c(g_rough_w).reshape(P) if (g_rough_w is not None and need_r) else None
+        sa, sma = ws.scatter_target("a", (Ha, Wa, 3), La, dev) if need_a else (None, None)
+        sr, smr = ws.scatter_target("r", (Hr, Wr, 1), Lr, dev) if need_r else (None, None)
+        n_a, n_r = (Ha * Wa * 3 if need_a else 0), (Hr * Wr if need_r else 0)
+        flat = torch.empty(n_a + n_r, dtype=torch.float32, device=dev)  # ONE buffer: a single all-reduce covers both
+        out_a = flat[:n_a].view(Ha, Wa, 3) if need_a else None
+        out_r = flat[n_a:].view(Hr, Wr, 1) if need_r else None
+        ws.dirty = True
+        with torch.cuda.device(dev):
+            st = _stream_ptr(dev)
+            _lib.check(lib.texir_shade_bwd_mat(
+                ctx.scene.handle, _ptr(nrm), _ptr(albedo), _ptr(rough_in), _ptr(pos), _ptr(camc), _ptr(irr), _ptr(shs), None,
+                P, N_spec, 0, mode_spec, _lib.MODE_UNIFORM, eps, _ptr(g), _ptr(drgb), None, _ptr(uv), _ptr(da),
+                _ptr(add_a), _ptr(add_r), _ptr(add_rw), int(bool(render_a and need_a)), int(bool(need_r)),
+                int(stage == 1), _ptr(sa), _ptr(sma), Ha, Wa, La if need_a else 0, _ptr(sr), _ptr(smr), Hr, Wr,
+                Lr if need_r else 0, st), "texir_shade_bwd_mat")
+            if need_a:
+                _lib.check(lib.texir_texture_mip_fold_into(_ptr(sa), _ptr(sma), Ha, Wa, 3, La, _ptr(out_a), 1, st),
+                           "texir_texture_mip_fold_into")
+            if need_r:
+                _lib.check(lib.texir_texture_mip_fold_into(_ptr(sr), _ptr(smr), Hr, Wr, 1, Lr, _ptr(out_r), 1, st),
+                           "texir_texture_mip_fold_into")
+        ws.dirty = False
+        return (out_a, out_r) + (None,) * 15
+
+
+def mat_stage(scene: Scene, ws: MatWorkspace, materials_a, materials_r, irrt, normal, points, cam_position, texc, texd,
+              shift_spec, *, stage: int, num_spec: int, max_mip_level: Optional[int] = None,
+              mode_spec: str = "importance", eps: float = TINY_TINY_NUMBER, backward: str = "stash"):
+    """One Mat-stage step on flat per-pixel G-buffer tensors (normal, points [P,3]; texc [P,2]; texd [P,4]):
+    -> (rgb [P,3], albedo [P,3], roughness [P,1], roughness_womipmap [P,1], irr [P,3]) exactly as
+    MaterialModel.forward computes them for stage 1 (render(albedo.detach(), roughness_womipmap)) or stage 2
+    (render(albedo, roughness)), models/mat_nvdiffrast.py:131-139,179-182.  Gradients of every output reach
+    materials_a / materials_r through ONE backward kernel + one fold per texture."""
+    _need_cuda("mat_stage", normal)
+    if stage not in (1, 2):
+        raise ValueError("mat_stage covers the ray-traced stages 1 and 2")
+    if backward not in ("stash", "recompute"):
+        raise ValueError("backward must be 'stash' or 'recompute'")
+    return _MatStage.apply(materials_a, materials_r, ws, scene, irrt, normal, points, cam_position, texc, texd, shift_spec,
+                           int(stage), int(num_spec), _lib.MODES[mode_spec], float(eps), backward, max_mip_level)
+
+
+# --------------------------------------------------------------------------------------------------
 # fused IrT batch
 # --------------------------------------------------------------------------------------------------
 def point_order(scene: Scene, position: torch.Tensor) -> torch.Tensor:
@@ -361,22 +530,45 @@ def point_order(scene: Scene, position: torch.Tensor) -> torch.Tensor:
 
 
 def irradiance(scene: Scene, position: torch.Tensor, normal: torch.Tensor, shift: torch.Tensor, num_samples: int,
-               mode: str = "uniform", out: Optional[torch.Tensor] = None, coherent: bool = True) -> torch.Tensor:
+               mode: str = "uniform", out: Optional[torch.Tensor] = None, coherent: bool = True,
+               order: Optional[torch.Tensor] = None) -> torch.Tensor:
     """E[p] = sum_i L_i clamp(n.l_i,0,1) 2 pi / N for P points in one launch (tracer_o3d_irt.py:168-171);
     position, normal [P,3], shift [P,1,2] or [P,2] -> [P,3].  coherent=True lets warps take the points in Morton
-    order (texir_point_order); the values do not depend on it."""
+    order (texir_point_order); the values do not depend on it.  order (int32, device): compute only the listed
+    points (rows of `out` that are not listed are left untouched)."""
     _need_cuda("irradiance", position)
     dev = position.device
     P = int(position.shape[0])
     pos, nrm = _f32c(position), _f32c(normal)
     sh = _f32c(shift, dev).reshape(P, 2)
     E = out if out is not None else torch.empty(P, 3, dtype=torch.float32, device=dev)
-    order = point_order(scene, pos) if (coherent and P > 4096) else None
+    if order is None:
+        order = point_order(scene, pos) if (coherent and P > 4096) else None
+        count = P
+    else:
+        order = order.to(device=dev, dtype=torch.int32).contiguous()
+        count = int(order.numel())
     with torch.cuda.device(dev):
-        _lib.check(_lib.load().texir_irradiance_fwd(scene.handle, _ptr(pos), _ptr(nrm), _ptr(sh), _ptr(order), P,
+        _lib.check(_lib.load().texir_irradiance_fwd(scene.handle, _ptr(pos), _ptr(nrm), _ptr(sh), _ptr(order), count,
                                                     int(num_samples), _lib.MODES[mode], _ptr(E), _stream_ptr(dev)),
                    "texir_irradiance_fwd")
     return E
+
+
+def irradiance_peers(scene: Scene, position: torch.Tensor, normal: torch.Tensor, shift: torch.Tensor,
+                     order: torch.Tensor, num_samples: int, mode: str, peer_ptrs, num_peers: int) -> None:
+    """this rank's share (`order`: int32 point indices) of a multi-GPU IrT; every result row is stored into ALL the
+    [P,3] buffers of peer_ptrs (ctypes array of device pointers, parallel.PeerBuffer.ptr_array) by the kernel itself"""
+    _need_cuda("irradiance_peers", position)
+    dev = position.device
+    P = int(position.shape[0])
+    pos, nrm = _f32c(position), _f32c(normal)
+    sh = _f32c(shift, dev).reshape(P, 2)
+    order = order.to(device=dev, dtype=torch.int32).contiguous()
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().texir_irradiance_fwd_peers(scene.handle, _ptr(pos), _ptr(nrm), _ptr(sh), _ptr(order),
+                                                          int(order.numel()), int(num_samples), _lib.MODES[mode], peer_ptrs,
+                                                          int(num_peers), _stream_ptr(dev)), "texir_irradiance_fwd_peers")
 
 
 def radiance_samples(scene: Scene, position: torch.Tensor, normal: torch.Tensor, shift: torch.Tensor,
@@ -438,17 +630,23 @@ def gbuffer(scene: Scene, rays: torch.Tensor, offset: float = 0.0,
     return out
 
 
-def gbuffer_mvp(scene: Scene, mvp: torch.Tensor, cam_position: torch.Tensor, res: int, return_rays: bool = False
-                ) -> dict:
+def gbuffer_mvp(scene: Scene, mvp: torch.Tensor, cam_position: torch.Tensor, res: int, return_rays: bool = False,
+                shard=None, flip_v: bool = False) -> dict:
     """The G-buffer of the views the reference rasterises, straight from its camera matrices and in one launch
     (mat_nvdiffrast.py:116-128): mvp [V,4,4] (clip = [v,1] @ mvp[i]), cam_position [3] -> dict(position, normal
-    [V,res,res,3], texc [..,2], texd [..,4], primitive_ids, primitive_uvs, mask [..,1]) (+ rays [..,6])."""
+    [V,res,res,3], texc [..,2], texd [..,4], primitive_ids, primitive_uvs, mask [..,1]) (+ rays [..,6]).
+    shard = (rank, world): only this rank's pixels (128-pixel blocks rank, rank + world, ... of every view, see
+    parallel.local_pixels), flat [V*res*res/world, .].  flip_v: texc = (u, 1 - v) and dv/dX, dv/dY negated, the
+    convention of the reference's self.uvs (pyredner.load_obj flips v by default, mat_nvdiffrast.py:194)."""
     _need_cuda("gbuffer_mvp", mvp)
     dev = mvp.device
     m = _f32c(mvp).reshape(-1, 4, 4)
     cam = _f32c(cam_position, dev).reshape(3)
     V, res = int(m.shape[0]), int(res)
-    R = V * res * res
+    rank, world = (0, 1) if shard is None else (int(shard[0]), int(shard[1]))
+    if world > 1 and (res * res) % (128 * world) != 0:
+        raise ValueError("a sharded G-buffer needs res*res to be a multiple of 128 * world")
+    R = V * res * res // world
     f32 = dict(dtype=torch.float32, device=dev)
     pos, nrm, bary = torch.empty(R, 3, **f32), torch.empty(R, 3, **f32), torch.empty(R, 2, **f32)
     uv = torch.empty(R, 2, **f32) if scene.has_uvs else None
@@ -457,10 +655,10 @@ def gbuffer_mvp(scene: Scene, mvp: torch.Tensor, cam_position: torch.Tensor, res
     mask = torch.empty(R, **f32)
     rays = torch.empty(R, 6, **f32) if return_rays else None
     with torch.cuda.device(dev):
-        _lib.check(_lib.load().texir_gbuffer_mvp(scene.handle, _ptr(m), _ptr(cam), V, res, _ptr(pos), _ptr(nrm), _ptr(uv),
-                                                 _ptr(texd), _ptr(prim), _ptr(bary), _ptr(mask), _ptr(rays),
-                                                 _stream_ptr(dev)), "texir_gbuffer_mvp")
-    shape = (V, res, res)
+        _lib.check(_lib.load().texir_gbuffer_mvp_shard(scene.handle, _ptr(m), _ptr(cam), V, res, rank, world, int(flip_v),
+                                                       _ptr(pos), _ptr(nrm), _ptr(uv), _ptr(texd), _ptr(prim), _ptr(bary),
+                                                       _ptr(mask), _ptr(rays), _stream_ptr(dev)), "texir_gbuffer_mvp_shard")
+    shape = (V, res, res) if world == 1 else (R,)
     out = {"position": pos.reshape(shape + (3,)), "normal": nrm.reshape(shape + (3,)),
            "primitive_ids": prim.reshape(shape), "primitive_uvs": bary.reshape(shape + (2,)),
            "mask": mask.reshape(shape + (1,))}

@@ -134,6 +134,10 @@ class Scene:
         self._tex_ref = texture  # keeps data_ptr from being recycled by another tensor
         self.tex_hw = (H, W)
 
+    def texture_key(self):
+        """identity of the radiance texture that is resident now (what a ray-recomputing backward must find again)"""
+        return self._tex_key
+
     # -- closest hit ------------------------------------------------------------------------------
     def cast_rays(self, rays: torch.Tensor, normals: bool = False, stats: bool = False):
         """rays [...,6] float32 (origin, direction) -> dict of CUDA tensors shaped like rays[...,0]:
