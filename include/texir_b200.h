@@ -44,6 +44,8 @@ enum { TEXIR_MODE_UNIFORM = 0, TEXIR_MODE_COSINE = 1, TEXIR_MODE_IMPORTANCE = 2 
 enum { TEXIR_TEX_CHW = 0 /* [3,H,W], the reference's self.texture[0] */, TEXIR_TEX_HWC = 1 /* [H,W,3] */ };
 /* BVH layout a scene's kernels traverse */
 enum { TEXIR_BVH2 = 2, TEXIR_BVH8 = 8 };
+/* who builds the tree: AUTO = the device for scenes of >= 4096 triangles (environment TEXIR_BUILDER=1 / 2 forces host / device) */
+enum { TEXIR_BUILDER_AUTO = 0, TEXIR_BUILDER_HOST = 1, TEXIR_BUILDER_DEVICE = 2 };
 
 typedef struct texir_scene_info {
     int64_t num_tris;
@@ -53,8 +55,10 @@ typedef struct texir_scene_info {
     int32_t bvh_kind;       /* TEXIR_BVH2 or TEXIR_BVH8 */
     int32_t device;
     double sah2, sah8;
-    double build_seconds;
+    double build_seconds;   /* wall time of texir_scene_create: build + uploads */
     int64_t device_bytes;   /* HBM held by the scene (BVHs + triangles + uvs + texture) */
+    int32_t builder;        /* TEXIR_BUILDER_HOST or TEXIR_BUILDER_DEVICE: who built the resident tree */
+    int32_t reserved;
 } texir_scene_info;
 
 TEXIR_API const char* texir_last_error(void);
@@ -65,10 +69,17 @@ TEXIR_API int64_t texir_launch_count(void);
 /* ---- scene: replaces o3d.t.geometry.RaycastingScene() + add_triangles + self.triangle_uvs
  *      (models/mat_nvdiffrast.py:87,97-101; models/tracer_o3d_irt.py:75,85-89) ------------------
  * verts_host [nv,3] f32, tris_host [nt,3] i32, tri_uvs_host [3*nt,2] f64 (np.asarray(mesh.triangle_uvs),
- * may be NULL for a pure cast_rays scene).  Builds the BVHs on the host (build_threads <= 0: all
- * cores) and uploads them to `device`. */
+ * may be NULL for a pure cast_rays scene).  Builds the BVH -- on `device` itself for scenes of >= 4096 triangles,
+ * else on the host (build_threads <= 0: all cores) -- and keeps it resident there. */
 TEXIR_API int texir_scene_create(const float* verts_host, int64_t nv, const int32_t* tris_host, int64_t nt,
                                  const double* tri_uvs_host, int device, int build_threads, texir_scene** out);
+/* The same with the builder chosen explicitly (TEXIR_BUILDER_*).  Both builders run the same binned-SAH algorithm with
+ * the same arithmetic and produce the same tree (node boxes, splits, leaf contents); the device one (csrc/
+ * bvh_build_gpu.cu: level-synchronous, a CTA or a warp per node) takes milliseconds where the host one takes most of a
+ * second.  The 8-wide layout is built lazily, on the host, by the first texir_scene_set_bvh(scene, TEXIR_BVH8). */
+TEXIR_API int texir_scene_create_ex(const float* verts_host, int64_t nv, const int32_t* tris_host, int64_t nt,
+                                    const double* tri_uvs_host, int device, int build_threads, int builder,
+                                    texir_scene** out);
 TEXIR_API int texir_scene_destroy(texir_scene* scene);
 TEXIR_API int texir_scene_get_info(const texir_scene* scene, texir_scene_info* info);
 TEXIR_API int texir_scene_set_bvh(texir_scene* scene, int bvh_kind);

@@ -47,9 +47,48 @@ cands = {
 print("torch.norm(dim=-1) on CUDA:")
 for k, v in cands.items():
     print("   %-34s %.6f" % (k, rate(v, ref)))
-# contiguous (non-expanded) input: same kernel?
-ref2 = torch.norm(x, dim=-1)
-print("   expanded vs contiguous input agree: %.6f" % rate(ref, ref2))
+# contiguous (non-expanded) input -- what norm_axis(torch.cross(...)) and F.normalize(cam - p) see: another reduction
+# schedule (two lanes share the three elements), so possibly another summation order
+def norm_cands(X, Y, Z):
+    return {
+        "sqrt((x*x+y*y)+z*z)": torch.sqrt((X * X + Y * Y) + Z * Z),
+        "sqrt((x*x+z*z)+y*y)": torch.sqrt((X * X + Z * Z) + Y * Y),
+        "sqrt(x*x+(y*y+z*z))": torch.sqrt(X * X + (Y * Y + Z * Z)),
+        "sqrt(fma(z,z,fma(y,y,x*x)))": torch.sqrt(fma(Z, Z, fma(Y, Y, X * X))),
+        "sqrt(fma(z,z,x*x)+y*y)": torch.sqrt(fma(Z, Z, X * X) + Y * Y),
+        "sqrt(fma(y,y,fma(z,z,x*x)))": torch.sqrt(fma(Y, Y, fma(Z, Z, X * X))),
+        "sqrt(fma(y,y,x*x)+z*z)": torch.sqrt(fma(Y, Y, X * X) + Z * Z),
+        "sqrt(fma(x,x,z*z)+y*y)": torch.sqrt(fma(X, X, Z * Z) + Y * Y),
+    }
+for shape in ((n, 3), (512, 16, 3), (512, 2048, 3), (98304, 16, 3), (98304, 3), (512, 3)):
+    xs = torch.randn(*shape, device=dev)
+    r2 = torch.norm(xs, dim=-1, keepdim=True).reshape(-1)
+    f = xs.reshape(-1, 3)
+    print("torch.norm(dim=-1) on CUDA, CONTIGUOUS input %s:" % (shape,))
+    for k, v in norm_cands(f[:, 0], f[:, 1], f[:, 2]).items():
+        print("   %-34s %.6f" % (k, rate(v, r2)))
+    if len(shape) == 2:
+        fn = torch.nn.functional.normalize(xs, eps=1e-4)
+        for k, v in norm_cands(f[:, 0], f[:, 1], f[:, 2]).items():
+            print("   F.normalize == x / max(%s, eps): %.6f" % (k, rate(f / torch.clamp(v, min=1e-4).unsqueeze(-1), fn)))
+for shape in ((512, 16, 3), (512, 2048, 3), (98304, 16, 3)):
+    xs = torch.randn(shape[0], 3, device=dev).unsqueeze(1).expand(*shape)
+    r2 = torch.norm(xs, dim=-1, keepdim=True).reshape(-1)
+    f = xs.reshape(-1, 3)
+    print("torch.norm(dim=-1) on CUDA, EXPANDED input %s:" % (shape,))
+    for k, v in norm_cands(f[:, 0], f[:, 1], f[:, 2]).items():
+        print("   %-34s %.6f" % (k, rate(v, r2)))
+
+# torch.sum(a * b, dim=-1, keepdim=True): vdh = sum(h * view.unsqueeze(1)), ndl = sum(n.unsqueeze(1) * l) ...
+for shape in ((512, 2048, 3), (98304, 16, 3), (98304, 1, 3)):
+    hh = torch.randn(*shape, device=dev)
+    vv = torch.randn(shape[0], 3, device=dev)
+    prod = hh * vv.unsqueeze(1)
+    r = torch.sum(prod, dim=-1, keepdim=True).reshape(-1)
+    f = prod.reshape(-1, 3)
+    p0, p1, p2 = f[:, 0], f[:, 1], f[:, 2]
+    print("torch.sum(h * v.unsqueeze(1), dim=-1) on CUDA %s:  (p0+p1)+p2 %.6f   (p0+p2)+p1 %.6f   p0+(p1+p2) %.6f" % (
+        shape, rate((p0 + p1) + p2, r), rate((p0 + p2) + p1, r), rate(p0 + (p1 + p2), r)))
 
 a, b = torch.randn(n, 3, device=dev), torch.randn(n, 3, device=dev)
 refc = torch.cross(a, b, dim=-1)

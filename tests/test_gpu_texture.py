@@ -183,28 +183,30 @@ def test_material_model_forward_reference_signature(tx, oracle, cuda_device, sce
     assert grads[0] == (True, False)       # lambertian initialisation: albedo only
     assert grads[1] == (False, True)       # albedo detached, un-mip-mapped roughness
     assert grads[2] == (True, True)
-    # stage 2 on the oracle: same G-buffer, torch restatement of dr.texture, reference render restatement
+    # stage 2 on the oracle: same G-buffer, torch restatement of dr.texture, reference render restatement -- executed
+    # like the reference executes it: everything on the CUDA device except query_irf (host), mat_nvdiffrast.py:294
     P = 6 * res * res
+    dv = cuda_device
     texc, texd = gb["texc"].reshape(P, 2).cpu(), gb["texd"].reshape(P, 4).cpu()
     ta = mm.materials_a.detach().cpu().clone().requires_grad_(True)
     tr = mm.materials_r.detach().cpu().clone().requires_grad_(True)
-    a = oracle.texture_mipmap_linear(ta, texc, texd, 13)
-    r = oracle.texture_mipmap_linear(tr, texc, texd, 13)
-    irr = oracle.texture_mipmap_linear(torch.from_numpy(irrt), texc, texd, 13)
-    nrm, pos = gb["normal"].reshape(P, 3).cpu(), gb["position"].reshape(P, 3).cpu()
+    a = oracle.texture_mipmap_linear(ta, texc, texd, 13).to(dv)          # the fetch restatement runs on the host ...
+    r = oracle.texture_mipmap_linear(tr, texc, texd, 13).to(dv)
+    irr = oracle.texture_mipmap_linear(torch.from_numpy(irrt), texc, texd, 13).to(dv)
+    nrm, pos = gb["normal"].reshape(P, 3), gb["position"].reshape(P, 3)  # ... the render where the reference runs it
     torch.manual_seed(666)
-    shift = torch.rand(P, 1, 2)
+    shift = torch.rand(P, 1, 2).to(dv)
     ref = oracle.render(oracle.OracleScene(g["vertices"], g["triangles"]), g["triangle_uvs"], torch.from_numpy(g["texture"]),
-                        [16, 16], ["uniform", "importance"], nrm, a, r, pos + 1e-2 * nrm, cam, irr, shift_spec=shift)
-    g_rgb = torch.from_numpy(rng.normal(size=(P, 3)).astype(np.float32))
+                        [16, 16], ["uniform", "importance"], nrm, a, r, pos + 1e-2 * nrm, cam.to(dv), irr, shift_spec=shift)
+    g_rgb = torch.from_numpy(rng.normal(size=(P, 3)).astype(np.float32)).to(dv)
     (ref["rgb"] * g_rgb).sum().backward()
     mm.zero_grad()
     torch.manual_seed(666)
     out = mm(mvp.to(cuda_device), 0, cam, 2)
-    (out["rgb"].reshape(P, 3) * g_rgb.to(cuda_device)).sum().backward()
-    assert rel_l2(out["rgb"].detach().cpu().numpy().reshape(P, 3), ref["rgb"].detach().numpy()) < 1e-4
-    assert rel_l2(mm.materials_a.grad.cpu().numpy(), ta.grad.numpy()) < 1e-3
-    assert rel_l2(mm.materials_r.grad.cpu().numpy(), tr.grad.numpy()) < 1e-3
+    (out["rgb"].reshape(P, 3) * g_rgb).sum().backward()
+    assert rel_l2(out["rgb"].detach().cpu().numpy().reshape(P, 3), ref["rgb"].detach().cpu().numpy()) < 1e-4
+    assert rel_l2(mm.materials_a.grad.cpu().numpy(), ta.grad.cpu().numpy()) < 1e-3
+    assert rel_l2(mm.materials_r.grad.cpu().numpy(), tr.grad.cpu().numpy()) < 1e-3
 
 
 def test_gbuffer_mvp_one_launch_equals_rays_plus_gbuffer(tx, cuda_device, scene_golden):

@@ -17,6 +17,8 @@ MODE_UNIFORM, MODE_COSINE, MODE_IMPORTANCE = 0, 1, 2
 MODES = {"uniform": MODE_UNIFORM, "cosine": MODE_COSINE, "importance": MODE_IMPORTANCE}
 TEX_CHW, TEX_HWC = 0, 1
 BVH2, BVH8 = 2, 8
+BUILDER_AUTO, BUILDER_HOST, BUILDER_DEVICE = 0, 1, 2
+BUILDERS = {"auto": 0, "host": 1, "device": 2}
 
 
 class TexirError(RuntimeError):
@@ -29,6 +31,7 @@ class SceneInfo(Structure):
         ("depth2", c_int32), ("depth8", c_int32), ("tex_h", c_int32), ("tex_w", c_int32),
         ("bvh_kind", c_int32), ("device", c_int32),
         ("sah2", c_double), ("sah8", c_double), ("build_seconds", c_double), ("device_bytes", c_int64),
+        ("builder", c_int32), ("reserved", c_int32),
     ]
 
 
@@ -39,6 +42,7 @@ SIGNATURES = {
     "texir_version": (c_int, []),
     "texir_launch_count": (c_int64, []),
     "texir_scene_create": (c_int, [_P, c_int64, _P, c_int64, _P, c_int, c_int, POINTER(c_void_p)]),
+    "texir_scene_create_ex": (c_int, [_P, c_int64, _P, c_int64, _P, c_int, c_int, c_int, POINTER(c_void_p)]),
     "texir_scene_destroy": (c_int, [_P]),
     "texir_scene_get_info": (c_int, [_P, POINTER(SceneInfo)]),
     "texir_scene_set_bvh": (c_int, [_P, c_int]),

@@ -8,6 +8,8 @@
 #include <cfloat>
 #include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 
@@ -555,7 +557,7 @@ void build8(const Builder& B, float pad, HostBVH& out) {
 }  // namespace
 
 bool build_bvh(const float* verts, int64_t nv, const int32_t* tris, int64_t nt, int threads, HostBVH& out,
-               std::string& err) {
+               std::string& err, bool want8) {
     auto t0 = std::chrono::steady_clock::now();
     if (nt <= 0 || nv <= 0 || !verts || !tris) {
         err = "build_bvh: empty mesh";
@@ -601,7 +603,9 @@ bool build_bvh(const float* verts, int64_t nv, const int32_t* tris, int64_t nt, 
     }
     if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
     threads = std::min(threads, 64);
+    auto tp0 = std::chrono::steady_clock::now();
     B.build(threads);
+    auto tp1 = std::chrono::steady_clock::now();
     // boxes are padded by 1e-5 of the scene diagonal plus 4 ulp of the largest coordinate: larger
     // than any rounding in the slab tests or in the triangle test's edge decisions
     double dx = (double)scene.hi[0] - scene.lo[0], dy = (double)scene.hi[1] - scene.lo[1],
@@ -612,13 +616,21 @@ bool build_bvh(const float* verts, int64_t nv, const int32_t* tris, int64_t nt, 
     float pad = (float)(1e-5 * diag + 4.8e-7 * maxc);
     if (!(pad > 0.f)) pad = 1e-7f;
     flatten2(B, pad, /*top_depth=*/10, out);
+    auto tp2 = std::chrono::steady_clock::now();
     quantise2(out);
-    build8(B, pad, out);
+    auto tp3 = std::chrono::steady_clock::now();
+    if (want8) build8(B, pad, out);
+    auto tp4 = std::chrono::steady_clock::now();
+    if (getenv("TEXIR_BUILD_TIMING")) {
+        auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+        fprintf(stderr, "bvh build: prims %.1f ms, tree %.1f ms, flatten %.1f ms, quantise %.1f ms, bvh8 %.1f ms\n",
+                ms(t0, tp0), ms(tp0, tp1), ms(tp1, tp2), ms(tp2, tp3), ms(tp3, tp4));
+    }
     if (out.depth2 > kStackSize - 2) {
         err = "build_bvh: BVH2 deeper than the traversal stack";
         return false;
     }
-    if (out.depth8 > kStack8 - 2) {
+    if (want8 && out.depth8 > kStack8 - 2) {
         err = "build_bvh: BVH8 deeper than the traversal stack";
         return false;
     }

@@ -29,7 +29,27 @@ struct HostBVH {
 };
 
 // verts: [nv][3] float32, tris: [nt][3] int32.  Returns false and fills err on bad input.
+// want8 = false skips the 8-wide layout (it is only walked after texir_scene_set_bvh(scene, 8)).
 bool build_bvh(const float* verts, int64_t nv, const int32_t* tris, int64_t nt, int threads, HostBVH& out,
-               std::string& err);
+               std::string& err, bool want8 = true);
+
+// The same binned-SAH tree built on the current CUDA device (bvh_build_gpu.cu): the BVH2 / QBVH2 node arrays, the
+// slot-ordered triangle records and the primitive -> slot map, all device memory owned by the caller on success.
+// Inputs are HOST arrays (they are uploaded).  Returns false with `err` set when the mesh is invalid or the tree
+// cannot be built on the device (deeper than the traversal stack, whole scene in one leaf): the host builder then
+// decides.
+struct DeviceBVH {
+    void* d_nodes2 = nullptr;        // float4 [4 * num_nodes]
+    void* d_qnodes2 = nullptr;       // uint4  [2 * num_nodes]
+    void* d_tris2 = nullptr;         // float4 [3 * nt]
+    void* d_slot_of_prim = nullptr;  // uint32 [nt]
+    int64_t num_nodes = 0;
+    int depth = 0;
+    double sah = 0.0, seconds = 0.0;
+    float qmin[3], qstep[3];
+    float scene_lo[3], scene_hi[3];
+};
+bool build_bvh_device(const float* verts_host, int64_t nv, const int32_t* tris_host, int64_t nt, void* stream, DeviceBVH& out,
+                      std::string& err);
 
 }  // namespace texir

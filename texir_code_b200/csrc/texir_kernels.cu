@@ -8,6 +8,7 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -763,14 +764,17 @@ struct ShadePointSmem {
 #ifndef TX_SHADE_LEAN_MINB
 #define TX_SHADE_LEAN_MINB 10
 #endif
-template <int KIND, bool TANGENT, bool FRONT = false>
+// G = lanes per point: 32 (N >= 32), or 16 with two points per warp (the reference trains at 16 specular samples,
+// configs/syn.conf:24)
+template <int KIND, bool TANGENT, bool FRONT = false, int G = 32>
 __global__ void __launch_bounds__(128, TX_SHADE_LEAN_MINB) k_shade_lean(SceneView s, ShadeArgs a) {
-    __shared__ ShadePointSmem sm_pt[4];
+    constexpr int PTS = 128 / G;  // points per CTA
+    __shared__ ShadePointSmem sm_pt[PTS];
     __shared__ float sm_acc[TANGENT ? 9 : 6][128];
-    __shared__ uint4 sm_front[FRONT ? 4 : 1][FRONT ? kMaxFront : 1];  // shared first descent, see k_irradiance_lean
-    __shared__ int sm_front_n[4], sm_front_start[4];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, tid = threadIdx.x;
-    int64_t p = (int64_t)blockIdx.x * 4 + wid;
+    __shared__ uint4 sm_front[FRONT ? PTS : 1][FRONT ? kMaxFront : 1];  // shared first descent, see k_irradiance_lean
+    __shared__ int sm_front_n[PTS], sm_front_start[PTS];
+    const int lane = threadIdx.x & (G - 1), wid = threadIdx.x / G, tid = threadIdx.x;  // lane within the point's group
+    int64_t p = (int64_t)blockIdx.x * PTS + wid;
     const bool live = p < a.P;
     if (!live) p = a.P - 1;
     const V3 o = load3(a.pos, p);
@@ -802,7 +806,7 @@ __global__ void __launch_bounds__(128, TX_SHADE_LEAN_MINB) k_shade_lean(SceneVie
     {  // specular samples
         const int ab = a.a_spec, N = a.N_spec, M = (N + (1 << ab) - 1) >> ab;
         for (int c = 0; c < (1 << ab); ++c)
-            for (int j = lane; j < M; j += 32) {
+            for (int j = lane; j < M; j += G) {
                 const uint32_t i = ((uint32_t)j << ab) + (uint32_t)c;
                 if (i >= (uint32_t)N) continue;
                 V3 l;
@@ -838,7 +842,7 @@ __global__ void __launch_bounds__(128, TX_SHADE_LEAN_MINB) k_shade_lean(SceneVie
     if (a.N_diff > 0) {  // Monte-Carlo diffuse (relighting)
         const int ab = a.a_diff, N = a.N_diff, M = (N + (1 << ab) - 1) >> ab;
         for (int c = 0; c < (1 << ab); ++c)
-            for (int j = lane; j < M; j += 32) {
+            for (int j = lane; j < M; j += G) {
                 const uint32_t i = ((uint32_t)j << ab) + (uint32_t)c;
                 if (i >= (uint32_t)N) continue;
                 V3 d;
@@ -866,7 +870,7 @@ __global__ void __launch_bounds__(128, TX_SHADE_LEAN_MINB) k_shade_lean(SceneVie
         lo.diff[k] = sm_acc[3 + k][tid];
         lo.dspec[k] = TANGENT ? sm_acc[TANGENT ? 6 + k : 0][tid] : 0.f;
     }
-    shade_reduce_store<TANGENT>(a, lo, p, live, lane, 32);
+    shade_reduce_store<TANGENT>(a, lo, p, live, lane, G);
 }
 
 // backward from the forward-mode stash: no rays
@@ -1186,16 +1190,61 @@ int texir_scene_destroy(texir_scene* sc) {
     return 0;
 }
 
-int texir_scene_create(const float* verts_host, int64_t nv, const int32_t* tris_host, int64_t nt,
-                       const double* tri_uvs_host, int device, int build_threads, texir_scene** out) {
+// uploads a host-built tree (all of it, or only the 8-wide layout when `only8`)
+static int upload_host_bvh(texir_scene* sc, const HostBVH& bvh, int64_t nt, bool only8) {
+    int rc = 0;
+    int64_t bytes = 0;
+    if (!only8) {
+        std::vector<uint32_t> slot_of_prim((size_t)nt, 0u);
+        for (size_t s = 0; s < bvh.prim2.size(); ++s) slot_of_prim[bvh.prim2[s]] = (uint32_t)s;
+        if ((rc = upload(bvh.nodes2, &sc->d_nodes2, &bytes)) || (rc = upload(bvh.tris2, &sc->d_tris2, &bytes)) ||
+            (rc = upload(bvh.qnodes2, &sc->d_qnodes2, &bytes)) || (rc = upload(slot_of_prim, &sc->d_slot_of_prim, &bytes)))
+            return rc;
+        sc->view.nodes2 = (const float4*)sc->d_nodes2;
+        sc->view.tris2 = (const float4*)sc->d_tris2;
+        sc->view.qnodes2 = (const uint4*)sc->d_qnodes2;
+        for (int a = 0; a < 3; ++a) {
+            sc->view.qmin[a] = bvh.qmin[a];
+            sc->view.qstep[a] = bvh.qstep[a];
+            sc->lo[a] = bvh.scene_lo[a];
+            sc->hi[a] = bvh.scene_hi[a];
+        }
+        sc->info.num_nodes2 = (int64_t)bvh.nodes2.size() / 4;
+        sc->info.depth2 = bvh.depth2;
+        sc->info.sah2 = bvh.sah2;
+    }
+    if (!bvh.nodes8.empty()) {
+        if ((rc = upload(bvh.nodes8, &sc->d_nodes8, &bytes)) || (rc = upload(bvh.tris8, &sc->d_tris8, &bytes))) return rc;
+        sc->view.nodes8 = (const uint4*)sc->d_nodes8;
+        sc->view.tris8 = (const float4*)sc->d_tris8;
+        sc->info.num_nodes8 = (int64_t)bvh.nodes8.size() / 5;
+        sc->info.depth8 = bvh.depth8;
+        sc->info.sah8 = bvh.sah8;
+    }
+    sc->geom_bytes += bytes;
+    return 0;
+}
+
+int texir_scene_create_ex(const float* verts_host, int64_t nv, const int32_t* tris_host, int64_t nt,
+                          const double* tri_uvs_host, int device, int build_threads, int builder, texir_scene** out) {
     if (!out) TX_FAIL("texir_scene_create: out is NULL");
     *out = nullptr;
+    if (nt <= 0 || nv <= 0 || !verts_host || !tris_host) TX_FAIL("build_bvh: empty mesh");
+    if (builder != TEXIR_BUILDER_AUTO && builder != TEXIR_BUILDER_HOST && builder != TEXIR_BUILDER_DEVICE)
+        TX_FAIL("texir_scene_create: unknown builder");
+    if (builder == TEXIR_BUILDER_AUTO) {
+        const int env = env_int("TEXIR_BUILDER", 0);  // 1 = host, 2 = device
+        builder = env == 1 ? TEXIR_BUILDER_HOST : (env == 2 || nt >= 4096) ? TEXIR_BUILDER_DEVICE : TEXIR_BUILDER_HOST;
+    }
+    const auto t0 = std::chrono::steady_clock::now();
     HostBVH bvh;
     std::string err;
-    try {
-        if (!build_bvh(verts_host, nv, tris_host, nt, build_threads, bvh, err)) TX_FAIL(err);
-    } catch (const std::exception& e) {
-        TX_FAIL(std::string("texir_scene_create: ") + e.what());
+    if (builder == TEXIR_BUILDER_HOST) {  // before any CUDA call: argument errors are reported on a box without a GPU too
+        try {
+            if (!build_bvh(verts_host, nv, tris_host, nt, build_threads, bvh, err, /*want8=*/false)) TX_FAIL(err);
+        } catch (const std::exception& e) {
+            TX_FAIL(std::string("texir_scene_create: ") + e.what());
+        }
     }
     int ndev = 0;
     TX_CUDA(cudaGetDeviceCount(&ndev));
@@ -1204,52 +1253,79 @@ int texir_scene_create(const float* verts_host, int64_t nv, const int32_t* tris_
     if (!guard.ok) TX_FAIL("texir_scene_create: cannot select device");
     texir_scene* sc = new texir_scene();
     sc->info.device = device;
-    int rc = 0;
-    int64_t bytes = 0;
-    std::vector<uint32_t> slot_of_prim((size_t)nt, 0u);
-    for (size_t s = 0; s < bvh.prim2.size(); ++s) slot_of_prim[bvh.prim2[s]] = (uint32_t)s;
-    std::vector<double> uvs;
-    if (tri_uvs_host) uvs.assign(tri_uvs_host, tri_uvs_host + 6 * (size_t)nt);
-    if ((rc = upload(bvh.nodes2, &sc->d_nodes2, &bytes)) || (rc = upload(bvh.tris2, &sc->d_tris2, &bytes)) ||
-        (rc = upload(bvh.qnodes2, &sc->d_qnodes2, &bytes)) ||
-        (rc = upload(bvh.nodes8, &sc->d_nodes8, &bytes)) ||
-        (rc = upload(bvh.tris8, &sc->d_tris8, &bytes)) ||
-        (rc = upload(slot_of_prim, &sc->d_slot_of_prim, &bytes)) || (rc = upload(uvs, &sc->d_uvs, &bytes))) {
+    auto bail = [&](int rc) {
         std::string keep = g_err;
         texir_scene_destroy(sc);
         g_err = keep;
         return rc;
+    };
+    if (builder == TEXIR_BUILDER_DEVICE) {
+        DeviceBVH d;
+        if (build_bvh_device(verts_host, nv, tris_host, nt, nullptr, d, err)) {
+            sc->d_nodes2 = d.d_nodes2;
+            sc->d_qnodes2 = d.d_qnodes2;
+            sc->d_tris2 = d.d_tris2;
+            sc->d_slot_of_prim = d.d_slot_of_prim;
+            sc->view.nodes2 = (const float4*)sc->d_nodes2;
+            sc->view.tris2 = (const float4*)sc->d_tris2;
+            sc->view.qnodes2 = (const uint4*)sc->d_qnodes2;
+            for (int a = 0; a < 3; ++a) {
+                sc->view.qmin[a] = d.qmin[a];
+                sc->view.qstep[a] = d.qstep[a];
+                sc->lo[a] = d.scene_lo[a];
+                sc->hi[a] = d.scene_hi[a];
+            }
+            sc->info.num_nodes2 = d.num_nodes;
+            sc->info.depth2 = d.depth;
+            sc->info.sah2 = d.sah;
+            sc->geom_bytes += d.num_nodes * 96 + nt * 52;
+        } else if (err.rfind("build_bvh:", 0) == 0) {  // invalid mesh: the host builder would say the same
+            g_err = err;
+            return bail(1);
+        } else {  // a tree the device builder does not take (too deep, one-leaf scene): the host builder's case
+            cudaGetLastError();
+            builder = TEXIR_BUILDER_HOST;
+            try {
+                if (!build_bvh(verts_host, nv, tris_host, nt, build_threads, bvh, err, false)) {
+                    g_err = err;
+                    return bail(1);
+                }
+            } catch (const std::exception& e) {
+                g_err = std::string("texir_scene_create: ") + e.what();
+                return bail(1);
+            }
+        }
     }
-    sc->geom_bytes = bytes;
-    for (int a = 0; a < 3; ++a) {
-        sc->lo[a] = bvh.scene_lo[a];
-        sc->hi[a] = bvh.scene_hi[a];
+    if (builder == TEXIR_BUILDER_HOST)
+        if (int rc = upload_host_bvh(sc, bvh, nt, false)) return bail(rc);
+    sc->builder = builder;
+    if (tri_uvs_host) {
+        const size_t bytes = 6 * (size_t)nt * sizeof(double);
+        if (cudaMalloc(&sc->d_uvs, bytes) != cudaSuccess || cudaMemcpy(sc->d_uvs, tri_uvs_host, bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
+            g_err = "texir_scene_create: uploading triangle_uvs failed";
+            cudaGetLastError();
+            return bail(2);
+        }
+        sc->geom_bytes += (int64_t)bytes;
     }
-    sc->view.nodes2 = (const float4*)sc->d_nodes2;
-    sc->view.tris2 = (const float4*)sc->d_tris2;
-    sc->view.qnodes2 = (const uint4*)sc->d_qnodes2;
-    for (int a = 0; a < 3; ++a) {
-        sc->view.qmin[a] = bvh.qmin[a];
-        sc->view.qstep[a] = bvh.qstep[a];
-    }
-    sc->view.nodes8 = (const uint4*)sc->d_nodes8;
-    sc->view.tris8 = (const float4*)sc->d_tris8;
+    sc->h_verts.assign(verts_host, verts_host + 3 * (size_t)nv);
+    sc->h_tris.assign(tris_host, tris_host + 3 * (size_t)nt);
     sc->view.tri_uvs = tri_uvs_host ? (const double*)sc->d_uvs : nullptr;
     sc->view.tex = nullptr;
     sc->view.tex_w = sc->view.tex_h = 0;
     sc->view.num_tris = (uint32_t)nt;
     sc->info.num_tris = nt;
-    sc->info.num_nodes2 = (int64_t)bvh.nodes2.size() / 4;
-    sc->info.num_nodes8 = (int64_t)bvh.nodes8.size() / 5;
-    sc->info.depth2 = bvh.depth2;
-    sc->info.depth8 = bvh.depth8;
-    sc->info.sah2 = bvh.sah2;
-    sc->info.sah8 = bvh.sah8;
-    sc->info.build_seconds = bvh.build_seconds;
+    sc->info.build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     sc->info.bvh_kind = TEXIR_BVH2;  // measured on B200: 2.1x faster than the compressed BVH8 on this path
-    sc->info.device_bytes = bytes;
+    sc->info.builder = builder;
+    sc->info.device_bytes = sc->geom_bytes;
     *out = sc;
     return 0;
+}
+
+int texir_scene_create(const float* verts_host, int64_t nv, const int32_t* tris_host, int64_t nt,
+                       const double* tri_uvs_host, int device, int build_threads, texir_scene** out) {
+    return texir_scene_create_ex(verts_host, nv, tris_host, nt, tri_uvs_host, device, build_threads, TEXIR_BUILDER_AUTO, out);
 }
 
 int texir_scene_get_info(const texir_scene* sc, texir_scene_info* info) {
@@ -1264,6 +1340,21 @@ int texir_scene_get_info(const texir_scene* sc, texir_scene_info* info) {
 int texir_scene_set_bvh(texir_scene* sc, int kind) {
     if (!sc) TX_FAIL("texir_scene_set_bvh: NULL scene");
     if (kind != TEXIR_BVH2 && kind != TEXIR_BVH8) TX_FAIL("texir_scene_set_bvh: kind must be 2 or 8");
+    if (kind == TEXIR_BVH8 && !sc->d_nodes8) {
+        // the 8-wide layout is a measured-and-rejected alternative: built (on the host, from the same binary tree
+        // algorithm) only when somebody asks for it
+        HostBVH bvh;
+        std::string err;
+        try {
+            if (!build_bvh(sc->h_verts.data(), (int64_t)sc->h_verts.size() / 3, sc->h_tris.data(), (int64_t)sc->h_tris.size() / 3, 0,
+                           bvh, err, /*want8=*/true))
+                TX_FAIL(err);
+        } catch (const std::exception& e) {
+            TX_FAIL(std::string("texir_scene_set_bvh: ") + e.what());
+        }
+        DeviceGuard guard(sc->info.device);
+        if (int rc = upload_host_bvh(sc, bvh, sc->info.num_tris, /*only8=*/true)) return rc;
+    }
     sc->info.bvh_kind = kind;
     return 0;
 }
@@ -1651,19 +1742,25 @@ template <bool TANGENT>
 static int launch_shade(const texir_scene* sc, const ShadeArgs& a, void* stream) {
     const int64_t warps = (a.P + (32 / a.G) - 1) / (32 / a.G);
     unsigned g = grid_for(warps * 32, 128);
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool lean = stream_mode() == 3 && use_qnodes() && sc->info.bvh_kind != TEXIR_BVH8;
     if (sc->info.bvh_kind == TEXIR_BVH8)
-        k_shade<8, TANGENT><<<g, 128, 0, (cudaStream_t)stream>>>(sc->view, a);
-    else if (stream_mode() == 3 && a.G == 32 && use_qnodes())
+        k_shade<8, TANGENT><<<g, 128, 0, st>>>(sc->view, a);
+    else if (lean && a.G == 32)
         if (use_front())
-            k_shade_lean<4, TANGENT, true><<<g, 128, 0, (cudaStream_t)stream>>>(sc->view, a);
+            k_shade_lean<4, TANGENT, true><<<g, 128, 0, st>>>(sc->view, a);
         else
-            k_shade_lean<4, TANGENT><<<g, 128, 0, (cudaStream_t)stream>>>(sc->view, a);
+            k_shade_lean<4, TANGENT><<<g, 128, 0, st>>>(sc->view, a);
+    else if (lean && a.G == 16 && (a.N_diff == 0 || group_lanes(a.N_diff) == 16) && group_lanes(a.N_spec) == 16)
+        // 16 rays per point do not amortise the shared first descent (measured: 501 us with it, 483 us without, for
+        // 98 304 pixels x 16 spp), so the two-points-per-warp kernel walks every ray from the root
+        k_shade_lean<4, TANGENT, false, 16><<<g, 128, 0, st>>>(sc->view, a);
     else if (stream_mode() >= 2 && use_qnodes())
-        k_shade<4, TANGENT><<<g, 128, 0, (cudaStream_t)stream>>>(sc->view, a);
+        k_shade<4, TANGENT><<<g, 128, 0, st>>>(sc->view, a);
     else if (stream_mode() >= 2)
-        k_shade<3, TANGENT><<<g, 128, 0, (cudaStream_t)stream>>>(sc->view, a);
+        k_shade<3, TANGENT><<<g, 128, 0, st>>>(sc->view, a);
     else
-        k_shade<2, TANGENT><<<g, 128, 0, (cudaStream_t)stream>>>(sc->view, a);
+        k_shade<2, TANGENT><<<g, 128, 0, st>>>(sc->view, a);
     return finish_launch("k_shade");
 }
 

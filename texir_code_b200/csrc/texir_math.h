@@ -80,13 +80,30 @@ TX_HD V3 v3(float x, float y, float z) {
 TX_HD V3 rn_scale(V3 a, float s) { return v3(tx_mul(a.x, s), tx_mul(a.y, s), tx_mul(a.z, s)); }
 TX_HD V3 rn_add(V3 a, V3 b) { return v3(tx_add(a.x, b.x), tx_add(a.y, b.y), tx_add(a.z, b.z)); }
 TX_HD V3 rn_sub(V3 a, V3 b) { return v3(tx_sub(a.x, b.x), tx_sub(a.y, b.y), tx_sub(a.z, b.z)); }
-// torch.sum(a*b, dim=-1) over 3 elements: product kernel, then (p0 + p1) + p2
+// Reductions over the last dimension (three elements).  The reference executes them with torch ON THE CUDA DEVICE, whose
+// reduction kernel sums a CONTIGUOUS row as (e0 + e2) + e1 (two lanes share the row: lane 0 takes elements 0 and 2) and a
+// row of a BROADCAST (expanded, stride-0) tensor as (e0 + e1) + e2, every product rounded separately -- measured on
+// B200 with torch 2.11: 100 % bit-equal on 4e5 vectors for each of the two cases, every other order <= 95 %
+// (profiles/discover_torch_cuda_rounding.py, profiles/r02_torch_cuda_rounding.txt).  The DEVICE code follows that.
+// torch on the CPU (where tests/golden were generated) accumulates acc = fma(x_i, x_i, acc) for the norm and sums a
+// dot product in order; the HOST build of this header (tests/cpu_emul) keeps those forms so that the emulation stays
+// bit-equal to the CPU goldens.
+#ifdef __CUDA_ARCH__
+// torch.sum(a * b, dim=-1) of a contiguous product tensor
+TX_HD float rn_dot(V3 a, V3 b) {
+    return tx_add(tx_add(tx_mul(a.x, b.x), tx_mul(a.z, b.z)), tx_mul(a.y, b.y));
+}
+// torch.norm(x, dim=-1) of a contiguous tensor: norm_axis(torch.cross(..)), F.normalize(cam - p)
+TX_HD float rn_norm(V3 a) { return tx_sqrt(tx_add(tx_add(tx_mul(a.x, a.x), tx_mul(a.z, a.z)), tx_mul(a.y, a.y))); }
+// torch.norm(x, dim=-1) of an expanded tensor: norm_axis(normals.unsqueeze(1).expand(b, N, 3)), sample_util.py:80,89
+TX_HD float rn_norm_bcast(V3 a) { return tx_sqrt(tx_add(tx_add(tx_mul(a.x, a.x), tx_mul(a.y, a.y)), tx_mul(a.z, a.z))); }
+#else
 TX_HD float rn_dot(V3 a, V3 b) {
     return tx_add(tx_add(tx_mul(a.x, b.x), tx_mul(a.y, b.y)), tx_mul(a.z, b.z));
 }
-// torch.norm(x, dim=-1) on CPU accumulates acc = fma(x_i, x_i, acc): sqrt(fma(z,z, fma(y,y, x*x)))
-// (measured against torch 2.11 CPU: 100 % bit-equal on 2e5 random vectors; the plain sum is 89 %)
 TX_HD float rn_norm(V3 a) { return tx_sqrt(tx_fma(a.z, a.z, tx_fma(a.y, a.y, tx_mul(a.x, a.x)))); }
+TX_HD float rn_norm_bcast(V3 a) { return rn_norm(a); }
+#endif
 // torch.cross on CPU: c.x = fma(a.y, b.z, -(a.z*b.y))  (100 % bit-equal; the unfused form is 75 %)
 TX_HD V3 rn_cross(V3 a, V3 b) {
     return v3(tx_fma(a.y, b.z, -tx_mul(a.z, b.y)),
@@ -96,6 +113,10 @@ TX_HD V3 rn_cross(V3 a, V3 b) {
 // norm_axis(x) = x / (norm(x) + 1e-6), utils/sample_util.py:86-87
 TX_HD V3 rn_norm_axis(V3 a) {
     float d = tx_add(rn_norm(a), kTiny);
+    return v3(tx_div(a.x, d), tx_div(a.y, d), tx_div(a.z, d));
+}
+TX_HD V3 rn_norm_axis_bcast(V3 a) {
+    float d = tx_add(rn_norm_bcast(a), kTiny);
     return v3(tx_div(a.x, d), tx_div(a.y, d), tx_div(a.z, d));
 }
 
@@ -144,7 +165,7 @@ struct Frame {
 TX_HD Frame make_frame(V3 nraw) {
     Frame f;
     V3 xa = (fabsf(nraw.x) > 0.99f) ? v3(0.f, 1.f, 0.f) : v3(1.f, 0.f, 0.f);
-    f.n = rn_norm_axis(nraw);
+    f.n = rn_norm_axis_bcast(nraw);
     f.u = rn_norm_axis(rn_cross(xa, f.n));
     f.v = rn_norm_axis(rn_cross(f.n, f.u));
     return f;

@@ -5,9 +5,9 @@
 //
 //   k_mip_build_tile   levels 1..5 of a pyramid from one read of level 0 (a CTA owns a 32x32 tile, shared memory)
 //   k_mip_build_tail   levels 6..L by one CTA (at most 128x128 texels are left)
-//   k_mip_fold_tile    transpose of the build as a GATHER: every level-0 texel evaluates its own chain
-//                      g0 + w (g1 + w (g2 + ...)) coarsest first, the part above level 5 once per tile; optionally
-//                      writes to a separate output and leaves the scatter buffers zeroed for the next step
+//   k_mip_fold_gather  transpose of the build as a GATHER: every level-0 texel evaluates its own chain
+//                      g0 + w (g1 + w (g2 + ...)) coarsest first, one streaming pass; optionally writes to a separate
+//                      output and leaves the scatter buffers zeroed for the next step
 //   k_mat_fetch        albedo (mip), roughness (mip), roughness (bilinear) and irradiance (mip) of a pixel in one pass
 #include <cuda_runtime.h>
 
@@ -36,44 +36,108 @@ __device__ __forceinline__ float box4(float a, float b, float c, float d) {
     return acc * 0.25f;
 }
 
+// A CTA of 64 threads owns a 32x32 tile of level 0; thread (tx4, ty4) of the 8x8 thread grid owns a 4x4 block of it.
+// Levels 1 and 2 of a block stay in the owner's registers; levels 3 and 4 are 2x2 averages across threads, fetched
+// with warp shuffles in the operand order of box4 (lane = ty4 * 8 + tx4, so the partners sit at lane ^ 1 and lane ^ 8,
+// then ^ 2 and ^ 16); level 5 joins the two warps through shared memory.  No other synchronisation, every load and
+// store of level 0 is a 128-bit access.
 template <int C>
-__global__ void __launch_bounds__(256) k_mip_build_tile(const float* __restrict__ tex, int H, int W, int nl,
-                                                        float* __restrict__ mips) {
-    __shared__ float bufA[kTile * kTile * C];
-    __shared__ float bufB[(kTile / 2) * (kTile / 2) * C];
-    const int tx = blockIdx.x, ty = blockIdx.y, tid = threadIdx.x;
-    for (int i = tid; i < kTile * kTile * C; i += 256) {
-        const int row = i / (kTile * C), within = i - row * (kTile * C);
-        bufA[i] = __ldg(tex + ((int64_t)(ty * kTile + row) * W + (int64_t)tx * kTile) * C + within);
+__device__ __forceinline__ void load_row4(const float* __restrict__ p, float* row) {  // 4 texels x C channels
+    const float4* q = reinterpret_cast<const float4*>(p);
+#pragma unroll
+    for (int k = 0; k < C; ++k) {
+        const float4 v = q[k];
+        row[4 * k + 0] = v.x; row[4 * k + 1] = v.y; row[4 * k + 2] = v.z; row[4 * k + 3] = v.w;
     }
-    __syncthreads();
-    float* src = bufA;
-    float* dst = bufB;
-    int side = kTile;
-    for (int l = 1; l <= nl; ++l) {
-        const int half = side >> 1;
-        const int wl = W >> l;
-        float* out = mips + mip_offset(H, W, C, l);
-        for (int i = tid; i < half * half * C; i += 256) {
-            const int c = i % C, x = (i / C) % half, y = i / (C * half);
-            const float v = box4(src[((2 * y) * side + 2 * x) * C + c], src[((2 * y) * side + 2 * x + 1) * C + c],
-                                 src[((2 * y + 1) * side + 2 * x) * C + c], src[((2 * y + 1) * side + 2 * x + 1) * C + c]);
-            dst[i] = v;
-            out[((int64_t)(ty * half + y) * wl + (tx * half + x)) * C + c] = v;
+}
+template <int C>
+__device__ __forceinline__ void store_row4(float* __restrict__ p, const float* row) {
+    float4* q = reinterpret_cast<float4*>(p);
+#pragma unroll
+    for (int k = 0; k < C; ++k) q[k] = make_float4(row[4 * k + 0], row[4 * k + 1], row[4 * k + 2], row[4 * k + 3]);
+}
+
+template <int C>
+__global__ void __launch_bounds__(64) k_mip_build_tile(const float* __restrict__ tex, int H, int W, int nl,
+                                                       float* __restrict__ mips) {
+    __shared__ float s4[4][C];  // the tile's four level-4 values
+    const int tx = blockIdx.x, ty = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tx4 = lane & 7, ty4 = (lane >> 3) + 4 * warp;
+    float t0[4][4 * C];
+#pragma unroll
+    for (int y = 0; y < 4; ++y)
+        load_row4<C>(tex + ((int64_t)(ty * kTile + 4 * ty4 + y) * W + (tx * kTile + 4 * tx4)) * C, t0[y]);
+    float t1[2][2][C], t2[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+                t1[j][i][c] = box4(t0[2 * j][(2 * i) * C + c], t0[2 * j][(2 * i + 1) * C + c], t0[2 * j + 1][(2 * i) * C + c],
+                                   t0[2 * j + 1][(2 * i + 1) * C + c]);
+        t2[c] = box4(t1[0][0][c], t1[0][1][c], t1[1][0][c], t1[1][1][c]);
+    }
+    if (nl >= 1) {
+        float* out = mips + mip_offset(H, W, C, 1);
+        const int w1 = W >> 1;
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int c = 0; c < C; ++c)
+                    out[((int64_t)(ty * 16 + 2 * ty4 + j) * w1 + (tx * 16 + 2 * tx4 + i)) * C + c] = t1[j][i][c];
+    }
+    if (nl >= 2) {
+        float* out = mips + mip_offset(H, W, C, 2);
+#pragma unroll
+        for (int c = 0; c < C; ++c) out[((int64_t)(ty * 8 + ty4) * (W >> 2) + (tx * 8 + tx4)) * C + c] = t2[c];
+    }
+    if (nl < 3) return;  // uniform over the CTA
+    float t3[C], t4[C];
+    {
+        const int b3 = lane & ~9;  // the 2x2 thread group's first lane
+        float* out = mips + mip_offset(H, W, C, 3);
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            t3[c] = box4(__shfl_sync(0xFFFFFFFFu, t2[c], b3), __shfl_sync(0xFFFFFFFFu, t2[c], b3 + 1),
+                         __shfl_sync(0xFFFFFFFFu, t2[c], b3 + 8), __shfl_sync(0xFFFFFFFFu, t2[c], b3 + 9));
+            if (lane == b3) out[((int64_t)(ty * 4 + (ty4 >> 1)) * (W >> 3) + (tx * 4 + (tx4 >> 1))) * C + c] = t3[c];
         }
-        __syncthreads();
-        float* t = src;
-        src = dst;
-        dst = t;
-        side = half;
+    }
+    if (nl < 4) return;
+    {
+        const int b4 = lane & 4;  // the 4x4 thread group's first lane (this warp holds two such groups side by side)
+        float* out = mips + mip_offset(H, W, C, 4);
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            t4[c] = box4(__shfl_sync(0xFFFFFFFFu, t3[c], b4), __shfl_sync(0xFFFFFFFFu, t3[c], b4 + 2),
+                         __shfl_sync(0xFFFFFFFFu, t3[c], b4 + 16), __shfl_sync(0xFFFFFFFFu, t3[c], b4 + 18));
+            if (lane == b4) {
+                out[((int64_t)(ty * 2 + warp) * (W >> 4) + (tx * 2 + (tx4 >> 2))) * C + c] = t4[c];
+                s4[2 * warp + (tx4 >> 2)][c] = t4[c];
+            }
+        }
+    }
+    if (nl < 5) return;
+    __syncthreads();
+    if (threadIdx.x < C) {
+        const int c = threadIdx.x;
+        mips[mip_offset(H, W, C, 5) + ((int64_t)ty * (W >> 5) + tx) * C + c] = box4(s4[0][c], s4[1][c], s4[2][c], s4[3][c]);
     }
 }
 
-// levels first..L, each from the level below it, by ONE CTA (plain loads: the source was written by this kernel)
+// levels first..L, each from the level below it, by ONE CTA.  Level `first` is read from global memory; every later
+// level from the copy of its source that the CTA keeps in shared memory (two buffers, ping-pong), so the chain of
+// levels costs one global round trip instead of one per level.  smem_floats = elements of level `first`.
 __global__ void __launch_bounds__(1024) k_mip_build_tail(float* __restrict__ mips, const float* __restrict__ tex, int H,
-                                                         int W, int C, int first, int L) {
+                                                         int W, int C, int first, int L, int smem_floats) {
+    extern __shared__ float sm[];
+    float* buf[2] = {sm, sm + smem_floats};
     for (int l = first; l <= L; ++l) {
-        const float* src = l > 1 ? mips + mip_offset(H, W, C, l - 1) : tex;
+        const float* src = l == first ? (l > 1 ? mips + mip_offset(H, W, C, l - 1) : tex) : buf[(l - first + 1) & 1];
+        float* keep = buf[(l - first) & 1];
         float* dst = mips + mip_offset(H, W, C, l);
         const int Hs = mip_dim(H, l - 1), Ws = mip_dim(W, l - 1), Hd = mip_dim(H, l), Wd = mip_dim(W, l);
         const int sx = Ws > 1 ? 2 : 1, sy = Hs > 1 ? 2 : 1;
@@ -82,77 +146,77 @@ __global__ void __launch_bounds__(1024) k_mip_build_tail(float* __restrict__ mip
             float acc = 0.f;
             for (int dy = 0; dy < sy; ++dy)
                 for (int dx = 0; dx < sx; ++dx) acc += src[((int64_t)(y * sy + dy) * Ws + (x * sx + dx)) * C + c];
-            dst[i] = acc * (1.0f / (float)(sx * sy));
+            const float v = acc * (1.0f / (float)(sx * sy));
+            dst[i] = v;
+            keep[i] = v;
         }
-        __threadfence_block();
         __syncthreads();
     }
 }
 
 // The fold as a gather.  The level-by-level fold computes, coarsest level first,  g_{l-1}[i] += g_l[parent(i)] * w_l ;
 // for one level-0 texel that is the chain  t_L = g_L,  t_{l-1} = g_{l-1} + t_l * w_l,  result t_0 -- evaluated here
-// per texel in that very order (bit-identical), the chain above level 5 once per 32x32 tile.
+// per texel in that very order (bit-identical), in ONE streaming pass: a thread owns four consecutive texels of a row
+// (128-bit loads and stores), their two level-1 parents and the single chain above; the coarse values are shared
+// between neighbouring threads through L1 / L2.  Level l of a [H,W] texture has the texel (y >> min(l, log2 H),
+// x >> min(l, log2 W)) above (y, x), and folding into level l weighs by 1 / ((l < log2 W ? 2 : 1) (l < log2 H ? 2 : 1)).
+struct FoldLevels {
+    int L, ly, lx;        // levels above 0; floor(log2 H), floor(log2 W)
+    int64_t off[24];      // element offset of level l >= 1 in the packed pyramid
+    int w[24];            // width of level l
+};
+
 template <int C>
-__global__ void __launch_bounds__(256) k_mip_fold_tile(float* __restrict__ g_tex, float* __restrict__ g_mips, int H, int W,
-                                                       int L, float* __restrict__ out, int clear) {
-    __shared__ float top[C];
-    __shared__ float bufA[kTile * kTile / 4 * C];
-    __shared__ float bufB[kTile * kTile / 16 * C];
-    const int tx = blockIdx.x, ty = blockIdx.y, tid = threadIdx.x;
-    const int nl = L < kTileLevels ? L : kTileLevels;  // levels handled inside the tile
-    if (tid < C) {
-        float t = 0.f;
-        if (L > kTileLevels) {
-            // ancestors of this tile's level-5 texel (ty, tx), walking up with the build's halving rule
-            int ys[32], xs[32];
-            ys[kTileLevels] = ty;
-            xs[kTileLevels] = tx;
-            for (int l = kTileLevels + 1; l <= L; ++l) {
-                ys[l] = mip_dim(H, l - 1) > 1 ? ys[l - 1] >> 1 : ys[l - 1];
-                xs[l] = mip_dim(W, l - 1) > 1 ? xs[l - 1] >> 1 : xs[l - 1];
-            }
-            t = g_mips[mip_offset(H, W, C, L) + ((int64_t)ys[L] * mip_dim(W, L) + xs[L]) * C + tid];
-            for (int l = L - 1; l >= kTileLevels; --l) {
-                const int sx = mip_dim(W, l) > 1 ? 2 : 1, sy = mip_dim(H, l) > 1 ? 2 : 1;
-                t = g_mips[mip_offset(H, W, C, l) + ((int64_t)ys[l] * mip_dim(W, l) + xs[l]) * C + tid] +
-                    t * (1.0f / (float)(sx * sy));
-            }
-        } else if (L == kTileLevels) {
-            t = g_mips[mip_offset(H, W, C, L) + ((int64_t)ty * mip_dim(W, L) + tx) * C + tid];
+__global__ void __launch_bounds__(256) k_mip_fold_gather(float* __restrict__ g_tex, const float* __restrict__ g_mips,
+                                                         FoldLevels lv, int H, int W, float* __restrict__ out, int clear) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int wq = W >> 2;
+    if (idx >= (int64_t)H * wq) return;
+    const int y = (int)(idx / wq), x = (int)(idx - (int64_t)y * wq) << 2;
+    float t2[C];  // the chain down to level 2 (one texel covers this thread's four)
+    const int L = lv.L;
+#pragma unroll
+    for (int c = 0; c < C; ++c) t2[c] = 0.f;
+    if (L >= 2) {
+        {
+            const int sy = L < lv.ly ? L : lv.ly, sx = L < lv.lx ? L : lv.lx;
+            const float* p = g_mips + lv.off[L] + ((int64_t)(y >> sy) * lv.w[L] + (x >> sx)) * C;
+#pragma unroll
+            for (int c = 0; c < C; ++c) t2[c] = p[c];
         }
-        top[tid] = t;
-        if (clear && L >= kTileLevels) g_mips[mip_offset(H, W, C, kTileLevels) + ((int64_t)ty * mip_dim(W, kTileLevels) + tx) * C + tid] = 0.f;
+        for (int l = L - 1; l >= 2; --l) {
+            const int sy = l < lv.ly ? l : lv.ly, sx = l < lv.lx ? l : lv.lx;
+            const float wgt = 1.0f / (float)((l < lv.lx ? 2 : 1) * (l < lv.ly ? 2 : 1));
+            const float* p = g_mips + lv.off[l] + ((int64_t)(y >> sy) * lv.w[l] + (x >> sx)) * C;
+#pragma unroll
+            for (int c = 0; c < C; ++c) t2[c] = p[c] + t2[c] * wgt;
+        }
     }
-    __syncthreads();
-    // levels nl-1 .. 1 of the tile in shared memory, then level 0 straight to `out`
-    const float* coarse = top;  // side 1 when nl == 5; for nl < 5 there is nothing above the tile's level nl
-    int cside = 1;
-    for (int l = nl - 1; l >= 0; --l) {
-        const int side = kTile >> l;
-        const int wl = mip_dim(W, l);
-        float* g = l ? g_mips + mip_offset(H, W, C, l) : g_tex;
-        float* dst = l ? ((l & 1) ? bufA : bufB) : nullptr;  // level 1 (16x16) and 3 in bufA, 2 and 4 in bufB
-        for (int i = tid; i < side * side * C; i += 256) {
-            const int c = i % C, x = (i / C) % side, y = i / (C * side);
-            const int64_t gi = ((int64_t)(ty * side + y) * wl + (tx * side + x)) * C + c;
-            float v = g[gi];
-            if (l < L) {
-                const float up = (l + 1 == nl && nl < kTileLevels)
-                                     ? g_mips[mip_offset(H, W, C, nl) + ((int64_t)(ty * (side >> 1) + (y >> 1)) * mip_dim(W, nl) + (tx * (side >> 1) + (x >> 1))) * C + c]
-                                     : coarse[((y >> 1) * cside + (x >> 1)) * C + c];
-                v = v + up * 0.25f;
-            }
-            if (l) {
-                dst[i] = v;
-                if (clear) g[gi] = 0.f;
-            } else {
-                out[gi] = v;
-                if (clear && out != g_tex) g[gi] = 0.f;
-            }
-        }
-        __syncthreads();
-        coarse = dst;
-        cside = side;
+    // level 1: two texels above the four (W is a multiple of 4, so level 1 is at least 2 wide and halves in x)
+    float t1[2][C];
+    if (L >= 1) {
+        const int y1 = lv.ly >= 1 ? y >> 1 : y;
+        const float w1 = 1.0f / (float)(2 * (1 < lv.ly ? 2 : 1));  // folding level 2 into level 1
+        const float* p = g_mips + lv.off[1] + ((int64_t)y1 * lv.w[1] + (x >> 1)) * C;
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int c = 0; c < C; ++c) t1[i][c] = L == 1 ? p[i * C + c] : p[i * C + c] + t2[c] * w1;
+    }
+    const float w0 = 1.0f / (float)(2 * (0 < lv.ly ? 2 : 1));  // folding level 1 into level 0
+    const int64_t off = ((int64_t)y * W + x) * C;
+    float row[4 * C];
+    load_row4<C>(g_tex + off, row);
+    if (L >= 1) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int c = 0; c < C; ++c) row[k * C + c] = row[k * C + c] + t1[k >> 1][c] * w0;
+    }
+    store_row4<C>(out + off, row);
+    if (clear && out != g_tex) {
+        const float zero[4 * C] = {};
+        store_row4<C>(g_tex + off, zero);
     }
 }
 
@@ -233,12 +297,17 @@ int texir_texture_mip_build_fast(const float* tex, int H, int W, int C, int leve
     const int nl = levels < kTileLevels ? levels : kTileLevels;
     dim3 grid((unsigned)(W / kTile), (unsigned)(H / kTile));
     if (C == 1)
-        k_mip_build_tile<1><<<grid, 256, 0, st>>>(tex, H, W, nl, mips);
+        k_mip_build_tile<1><<<grid, 64, 0, st>>>(tex, H, W, nl, mips);
     else
-        k_mip_build_tile<3><<<grid, 256, 0, st>>>(tex, H, W, nl, mips);
+        k_mip_build_tile<3><<<grid, 64, 0, st>>>(tex, H, W, nl, mips);
     if (int rc = finish_launch("k_mip_build_tile")) return rc;
     if (levels > kTileLevels) {
-        k_mip_build_tail<<<1, 1024, 0, st>>>(mips, tex, H, W, C, kTileLevels + 1, levels);
+        const int first = kTileLevels + 1;
+        const int n_first = mip_dim(H, first) * mip_dim(W, first) * C;   // <= 16 K floats at 4096^2
+        const size_t smem = 2 * (size_t)n_first * sizeof(float);
+        if (smem > 96 * 1024) return texir_texture_mip_build(tex, H, W, C, levels, mips, stream);
+        if (smem > 48 * 1024) cudaFuncSetAttribute(k_mip_build_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_mip_build_tail<<<1, 1024, smem, st>>>(mips, tex, H, W, C, first, levels, n_first);
         if (int rc = finish_launch("k_mip_build_tail")) return rc;
     }
     return 0;
@@ -254,7 +323,7 @@ int texir_texture_mip_fold_into(float* g_tex, float* g_mips, int H, int W, int C
     cudaStream_t st = (cudaStream_t)stream;
     const size_t bytes0 = (size_t)H * W * C * sizeof(float);
     const size_t bytes_m = (size_t)mip_offset(H, W, C, levels + 1) * sizeof(float);
-    if (!tileable(H, W) || (C != 1 && C != 3) || levels == 0) {  // level by level, then copy / clear
+    if (W % 4 != 0 || (C != 1 && C != 3) || levels == 0 || levels >= 24) {  // level by level, then copy / clear
         if (int rc = texir_texture_mip_fold(g_tex, g_mips, H, W, C, levels, stream)) return rc;
         if (out != g_tex) {
             if (cudaMemcpyAsync(out, g_tex, bytes0, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
@@ -265,17 +334,23 @@ int texir_texture_mip_fold_into(float* g_tex, float* g_mips, int H, int W, int C
             return fail("texir_texture_mip_fold_into: memset failed", 2);
         return 0;
     }
-    dim3 grid((unsigned)(W / kTile), (unsigned)(H / kTile));
-    if (C == 1)
-        k_mip_fold_tile<1><<<grid, 256, 0, st>>>(g_tex, g_mips, H, W, levels, out, clear);
-    else
-        k_mip_fold_tile<3><<<grid, 256, 0, st>>>(g_tex, g_mips, H, W, levels, out, clear);
-    if (int rc = finish_launch("k_mip_fold_tile")) return rc;
-    if (clear && levels != kTileLevels) {  // a level that several CTAs read is cleared afterwards
-        const size_t off = (size_t)mip_offset(H, W, C, levels > kTileLevels ? kTileLevels + 1 : levels) * sizeof(float);
-        if (cudaMemsetAsync((char*)g_mips + off, 0, bytes_m - off, st) != cudaSuccess)
-            return fail("texir_texture_mip_fold_into: memset failed", 2);
+    FoldLevels lv{};
+    lv.L = levels;
+    for (lv.ly = 0; (H >> (lv.ly + 1)) >= 1; ++lv.ly) {}
+    for (lv.lx = 0; (W >> (lv.lx + 1)) >= 1; ++lv.lx) {}
+    for (int l = 1; l <= levels; ++l) {
+        lv.off[l] = mip_offset(H, W, C, l);
+        lv.w[l] = mip_dim(W, l);
     }
+    const int64_t threads = (int64_t)H * (W / 4);
+    const unsigned grid = (unsigned)((threads + 255) / 256);
+    if (C == 1)
+        k_mip_fold_gather<1><<<grid, 256, 0, st>>>(g_tex, g_mips, lv, H, W, out, clear);
+    else
+        k_mip_fold_gather<3><<<grid, 256, 0, st>>>(g_tex, g_mips, lv, H, W, out, clear);
+    if (int rc = finish_launch("k_mip_fold_gather")) return rc;
+    if (clear && bytes_m && cudaMemsetAsync(g_mips, 0, bytes_m, st) != cudaSuccess)
+        return fail("texir_texture_mip_fold_into: memset failed", 2);
     return 0;
 }
 

@@ -3,6 +3,8 @@
 #pragma once
 #include <stdint.h>
 
+#include <vector>
+
 #include "../../include/texir_b200.h"
 #include "texir_bvh.h"
 
@@ -21,6 +23,8 @@ struct texir_scene {
     void* d_wide = nullptr;          // optional warp-cooperative wide layout (texir_wide.cu)
     int64_t geom_bytes = 0, tex_bytes = 0;
     float lo[3] = {0, 0, 0}, hi[3] = {1, 1, 1};  // scene box
-    // what the host keeps to build the optional layouts lazily (BVH8, float BVH2 nodes)
-    void* host_keep = nullptr;
+    // host copy of the mesh: the 8-wide layout is built from it when texir_scene_set_bvh(scene, 8) first asks for it
+    std::vector<float> h_verts;
+    std::vector<int32_t> h_tris;
+    int builder = 0;  // TEXIR_BUILDER_HOST / TEXIR_BUILDER_DEVICE: who built the tree that is resident
 };

@@ -386,7 +386,7 @@ class MatWorkspace:
         H, W, C = (int(x) for x in tex.shape)
         L = mip_levels(H, W, max_mip_level)
         lib = _lib.load()
-        n = max(int(lib.texir_texture_mip_elems(H, W, C, L)), 1)
+        n = mip_elems(H, W, C, L)
         mips = hit[1] if (hit is not None and hit[1].numel() == n and hit[1].device == tex.device) else \
             torch.empty(n, dtype=torch.float32, device=tex.device)
         t = _f32c(tex)
@@ -401,7 +401,7 @@ class MatWorkspace:
         key = (H, W, C, L, str(dev))
         hit = self._scatter.get(name)
         if hit is None or hit[0] != key or self.dirty:
-            n = max(int(_lib.load().texir_texture_mip_elems(H, W, C, L)), 1)
+            n = mip_elems(H, W, C, L)
             hit = (key, torch.zeros(H, W, C, dtype=torch.float32, device=dev), torch.zeros(n, dtype=torch.float32, device=dev))
             self._scatter[name] = hit
         return hit[1], hit[2]
@@ -452,6 +452,7 @@ class _MatStage(torch.autograd.Function):
         saved = [nrm, albedo, rough_in, pos, camc, irr, shs, uv, da] + ([drgb] if drgb is not None else [])
         ctx.save_for_backward(*saved)
         ctx.mark_non_differentiable(irr)
+        ctx.set_materialize_grads(False)   # an output the loss does not touch arrives as None, not as a tensor of zeros
         return rgb, albedo, rough.unsqueeze(-1), rough_w.unsqueeze(-1), irr
 
     @staticmethod
@@ -701,12 +702,31 @@ class _TextureFetch(torch.autograd.Function):
         return g_tex, None
 
 
+_mip_levels_cache = {}
+
+
 def mip_levels(H: int, W: int, max_mip_level: Optional[int] = None) -> int:
     """mip levels above level 0 that dr.texture builds for a [H,W] texture under a max_mip_level cap"""
-    L = int(_lib.load().texir_texture_mip_levels(int(H), int(W), -1 if max_mip_level is None else int(max_mip_level)))
+    key = (int(H), int(W), max_mip_level)
+    L = _mip_levels_cache.get(key)
+    if L is None:
+        L = int(_lib.load().texir_texture_mip_levels(int(H), int(W), -1 if max_mip_level is None else int(max_mip_level)))
+        _mip_levels_cache[key] = L
     if L < 0:
         raise ValueError("a %dx%d texture has an odd side that would have to be halved; lower max_mip_level" % (H, W))
     return L
+
+
+_mip_elems_cache = {}
+
+
+def mip_elems(H: int, W: int, C: int, L: int) -> int:
+    """floats in the packed pyramid (levels 1..L) of a [H,W,C] texture"""
+    key = (int(H), int(W), int(C), int(L))
+    n = _mip_elems_cache.get(key)
+    if n is None:
+        n = _mip_elems_cache[key] = max(int(_lib.load().texir_texture_mip_elems(*key)), 1)
+    return n
 
 
 def build_mips(tex: torch.Tensor, max_mip_level: Optional[int] = None):

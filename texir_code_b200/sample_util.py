@@ -56,9 +56,35 @@ def generate_fixed_samples(b: int, num_sample_dir: int) -> torch.Tensor:
     return s.cuda().repeat(b, 1, 1).detach()
 
 
+_shift_ring = {}   # (b, device index) -> [next slot, [(pinned buffer, copy-done event) ...]]
+
+
 def draw_shift(b: int, device) -> torch.Tensor:
-    """the reference's ``shift = torch.rand(b, 1, 2).cuda()``: CPU default generator, then moved"""
-    return torch.rand(b, 1, 2).to(device)
+    """the reference's ``shift = torch.rand(b, 1, 2).cuda()`` (utils/sample_util.py:102): the same draw from the CPU
+    default generator, then moved.  The draw lands in a pinned staging buffer and the copy is asynchronous: a pageable
+    ``.cuda()`` would make the host wait for everything queued on the stream first, once per generate_dir call.  Three
+    staging buffers per size rotate; one is reused only after the copy that read it has finished."""
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        return torch.rand(b, 1, 2).to(dev)
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    ring = _shift_ring.get((b, idx))
+    if ring is None:
+        if len(_shift_ring) > 16:
+            _shift_ring.clear()
+        ring = _shift_ring[(b, idx)] = [0, [(torch.empty(b, 1, 2).pin_memory(), None) for _ in range(3)]]
+    slot = ring[0]
+    ring[0] = (slot + 1) % len(ring[1])
+    buf, ev = ring[1][slot]
+    if ev is not None:
+        ev.synchronize()
+    torch.rand(b, 1, 2, out=buf)          # same values as torch.rand(b, 1, 2) for the same generator state
+    with torch.cuda.device(idx):
+        out = buf.to(dev, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(idx))
+    ring[1][slot] = (buf, ev)
+    return out
 
 
 class _GenerateDir(torch.autograd.Function):

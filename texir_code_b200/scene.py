@@ -42,7 +42,7 @@ class Scene:
     """BVH + triangles + per-corner UVs (+ radiance texture) resident on one GPU."""
 
     def __init__(self, vertices, triangles, triangle_uvs=None, device=None, build_threads: int = 0,
-                 bvh: int = _lib.BVH2):
+                 bvh: int = _lib.BVH2, builder: str = "auto"):
         lib = _lib.load()
         if not torch.cuda.is_available():
             raise _lib.TexirError("texir_code_b200.Scene needs a CUDA device (there is no CPU path)")
@@ -61,8 +61,10 @@ class Scene:
             uv_ptr = uv.ctypes.data
         torch.cuda.init()
         h = ctypes.c_void_p()
-        _lib.check(lib.texir_scene_create(v.ctypes.data, v.shape[0], t.ctypes.data, t.shape[0], uv_ptr,
-                                          self.device.index, build_threads, ctypes.byref(h)), "texir_scene_create")
+        # builder: "auto" (the device for >= 4096 triangles), "host" or "device" -- the same tree either way
+        _lib.check(lib.texir_scene_create_ex(v.ctypes.data, v.shape[0], t.ctypes.data, t.shape[0], uv_ptr,
+                                             self.device.index, build_threads, _lib.BUILDERS[builder], ctypes.byref(h)),
+                   "texir_scene_create")
         self._h = h
         self.num_tris = int(t.shape[0])
         self.has_uvs = triangle_uvs is not None
