@@ -544,6 +544,13 @@ def bench_material_stage(scene, sc, dev, args, texture, timer):
                 train_step()
                 ms_c, _ = timer.run(train_step, reps, 3)
                 out[key]["ms_with_cached_gbuffer"] = ms_c / reps
+                # ... and with the Cranley-Patterson shift drawn on the device (opt-in shift_rng='device': not the
+                # reference's CPU stream any more; torch.rand(98304,1,2) on the host is what bounds the step otherwise)
+                mm.shift_rng = "device"
+                train_step()
+                ms_d, _ = timer.run(train_step, reps, 3)
+                out[key]["ms_with_cached_gbuffer_and_device_rng"] = ms_d / reps
+                mm.shift_rng = "reference"
                 mm.cache_gbuffers = False
             del mm
     out["train_step_what"] = ("MaterialModel.forward(mvp, id, cam, stage) + backward: G-buffer of 6x128^2 primary rays (1 launch), "
@@ -623,6 +630,11 @@ def bench_mat_sharded(scene, sc, dev, args, texture, timer, rank, world):
         out["stage2_%dspp" % nspec] = {"ms_per_step": ms / reps, "ray_samples_per_s": 6 * 128 * 128 * nspec / (ms / reps * 1e-3),
                                        "allreduce_bytes": nbytes, "compute_ms_max_rank": float(t[0]), "allreduce_ms_max_rank": float(t[1]),
                                        "timed_steps": reps}
+        mm.shift_rng, mm.cache_gbuffers = "device", True      # opt-ins: shift from the CUDA generator, G-buffer kept per view
+        torch.cuda.manual_seed(1234)
+        step()
+        ms, _ = timer.run(step, reps, 3)
+        out["stage2_%dspp" % nspec]["ms_per_step_device_rng_cached_gbuffer"] = ms / reps
         del mm
     out["what"] = ("MaterialModel(shard=(rank, world)).forward(mvp, id, cam, 2) + backward on this rank's pixels, then ONE "
                    "all-reduce(sum) over the flat buffer that holds both texture gradients (2048^2x3 + 4096^2x1 fp32), "
@@ -632,24 +644,30 @@ def bench_mat_sharded(scene, sc, dev, args, texture, timer, rank, world):
 
 def bench_relight_sharded(scene, sc, dev, args, timer, rank, world):
     """BASELINE configs[4] shape over all ranks: relighting forward (3072 uniform diffuse + 1024 importance specular
-    samples per pixel, models/test_nvdiffrast.py:275-295), pixels split in contiguous 512-aligned slices, one
-    all_gather of the colours inside the timed step"""
+    samples per pixel, models/test_nvdiffrast.py:275-295), pixels dealt out in 128-blocks (block-cyclic: every rank gets
+    the same mix of cube faces), one all_gather of the colours + the permutation back inside the timed step"""
     import torch
+    import torch.distributed as dist
     from texir_code_b200 import ops, parallel
     pos, nrm, rough, albedo, irr, g_rgb = mat_inputs(scene, sc, dev)
     P = pos.shape[0]
-    b, e = parallel.shard_bounds(P, rank, world, 512)
-    t = lambda x: torch.from_numpy(x[b:e]).to(dev)
+    sel = parallel.block_cyclic_index(P, rank, world, 128)
+    order = torch.cat([parallel.block_cyclic_index(P, r, world, 128) for r in range(world)]).to(dev)   # rank-major -> pixel
+    inverse = torch.empty_like(order)
+    inverse[order] = torch.arange(P, device=dev)
+    t = lambda x: torch.from_numpy(x)[sel].to(dev)
     torch.manual_seed(666)
-    sh = torch.rand(P, 1, 2)[b:e].to(dev)
-    sh2 = torch.rand(P, 1, 2)[b:e].to(dev)
+    sh = torch.rand(P, 1, 2)[sel].to(dev)
+    sh2 = torch.rand(P, 1, 2)[sel].to(dev)
     nrm_d, pos_d, a0, r0, cam = t(nrm), t(pos), t(albedo), t(rough), torch.zeros(3, device=dev)
+    full = torch.empty(P, 3, device=dev)
     out = {"pixels": P}
     for tag, nd, ns in (("3072_1024", 3072, 1024), ("1024_256", 1024, 256)):
         def step():
             rgb = ops.shade(scene, nrm_d, a0, r0, pos_d, cam, None, sh, num_spec=ns, shift_diff=sh2, num_diff=nd,
                             mode_diff="uniform", eps=1e-6)
-            return parallel.gather_points(rgb, P, 512)
+            dist.all_gather_into_tensor(full, rgb)
+            return full[inverse]
         ms, _ = timer.run(step, 10, 2)
         out[tag] = {"ms_per_step": ms / 10, "ray_samples_per_s": P * (nd + ns) / (ms / 10 * 1e-3)}
     return out

@@ -183,3 +183,135 @@ def test_bench_reference_arm_prints_one_json_line():
     assert d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["gpu_launches"] == 0 and "workload" in d["config"]
+
+
+# ---------------------------------------------------------------------------------------------------
+# round 2: block-cyclic sharding, the flat gradient buffer, the IrT producer's index arithmetic
+# ---------------------------------------------------------------------------------------------------
+def test_block_cyclic_shares_partition_the_items():
+    from texir_code_b200.parallel import block_cyclic_index, local_pixels
+    for num, world, block in ((1 << 14, 4, 512), (5000, 3, 512), (700, 8, 128), (6, 2, 4)):
+        parts = [block_cyclic_index(num, r, world, block) for r in range(world)]
+        allidx = torch.cat(parts)
+        assert torch.equal(torch.sort(allidx).values, torch.arange(num))           # every item exactly once
+        for r, p in enumerate(parts):
+            assert bool(((p // block) % world == r).all()) and bool((p[1:] > p[:-1]).all())
+        if num % (block * world) == 0:
+            assert len({len(p) for p in parts}) == 1                               # equal shares
+    img = torch.arange(6 * 16 * 16 * 2, dtype=torch.float32).reshape(6, 16, 16, 2)  # 256 pixels per view = 2 blocks of 128
+    a, b = local_pixels(img, 0, 2, 6), local_pixels(img, 1, 2, 6)
+    assert a.shape == (6 * 128, 2) and torch.equal(a[:128], img[0].reshape(-1, 2)[:128]) and torch.equal(b[:128], img[0].reshape(-1, 2)[128:])
+    assert torch.equal(local_pixels(img, 0, 1, 6), img.reshape(-1, 2))
+    with pytest.raises(ValueError):
+        local_pixels(img, 0, 4, 6)                                                 # 256 is not a multiple of 128 * 4
+
+
+def _worker_flat(rank, world, port, q):
+    import torch.distributed as dist
+    from texir_code_b200.parallel import _flat_view_of, allreduce_gradients
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        class TwoGrads(torch.autograd.Function):      # what ops._MatStage.backward does: both gradients are views of ONE buffer
+            @staticmethod
+            def forward(ctx, a, r):
+                return a.sum() + r.sum()
+
+            @staticmethod
+            def backward(ctx, g):
+                flat = torch.full((8 * 8 * 3 + 16 * 16,), float(rank + 1))
+                TwoGrads.flat = flat
+                return flat[:192].view(8, 8, 3), flat[192:].view(16, 16, 1)
+
+        a = torch.nn.Parameter(torch.zeros(8, 8, 3))
+        r = torch.nn.Parameter(torch.zeros(16, 16, 1))
+        TwoGrads.apply(a, r).backward()
+        flat = _flat_view_of([a.grad, r.grad])
+        shares = flat is not None and flat.data_ptr() == TwoGrads.flat.data_ptr() and flat.numel() == 448
+        before = a.grad.data_ptr()
+        nbytes = allreduce_gradients([a, r])
+        ok = bool((a.grad == 3).all() and (r.grad == 3).all()) and nbytes == 448 * 4 and a.grad.data_ptr() == before \
+            and bool((TwoGrads.flat == 3).all())                                   # reduced in place, no copy
+        other = _flat_view_of([a.grad, torch.ones(3)]) is None and _flat_view_of([a.grad]) is not None
+        q.put((rank, bool(shares), ok, other))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_flat_gradient_buffer_is_reduced_in_place_world2_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_flat, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(60)
+    assert res == [(0, True, True, True), (1, True, True, True)]
+
+
+def test_seam_mask_sums_in_the_arrays_own_dtype():
+    """tracer_o3d_irt.py:138,177 adds the three uint16 channels of the index texture in uint16 (numpy): 30000 + 30000 +
+    5536 wraps to 0 and counts as a seam there, so it must here"""
+    from texir_code_b200.models import _seam_mask
+    idx = np.zeros((2, 3, 3), np.uint16)
+    idx[0, 1] = (30000, 30000, 5536)      # wraps to 0
+    idx[1, 2] = (1, 0, 0)
+    idx[1, 0] = (50000, 20000, 3)
+    ref = (idx[:, :, 0] + idx[:, :, 1] + idx[:, :, 2]) == 0
+    assert np.array_equal(_seam_mask(idx, "cpu").numpy(), ref) and ref[0, 1] and not ref[1, 2]
+    assert np.array_equal(_seam_mask(idx.astype(np.int64), "cpu").numpy(), idx.astype(np.int64).sum(-1) == 0)
+
+
+def test_position_normal_texture_lookup_matches_the_reference_numpy():
+    """calcute_position_normal_texture (tracer_o3d_irt.py:115-142): index -> panorama pixel with the reference's
+    arithmetic ((idx / 50000 * size).astype(int), clip), per view, seams zeroed -- restated here in numpy"""
+    rng = np.random.default_rng(2)
+    H = W = 24
+    views = [rng.normal(size=(16, 32, 6)).astype(np.float32) for _ in range(3)]
+    idx = np.zeros((H, W, 3), np.uint16)
+    idx[..., 0] = rng.integers(0, 50001, (H, W))
+    idx[..., 1] = rng.integers(0, 50001, (H, W))
+    idx[..., 2] = rng.integers(0, 3, (H, W))
+    idx[3, 4] = 0
+    idx[10, 0] = (50000, 50000, 2)
+    pos_ref = np.zeros((H, W, 3), np.float32)
+    nrm_ref = np.zeros((H, W, 3), np.float32)
+    for v in np.unique(idx[:, :, 2]):
+        rows, cols = np.where(idx[:, :, 2] == v)
+        hdr = views[v]
+        h, w, _ = hdr.shape
+        c = np.clip((idx[rows, cols, 1] / 50000 * w).astype(int), 0, w - 1)
+        r = np.clip((idx[rows, cols, 0] / 50000 * h).astype(int), 0, h - 1)
+        pos_ref[rows, cols] = hdr[r, c, 0:3]
+        nrm_ref[rows, cols] = hdr[r, c, 3:6]
+    seam = (idx[:, :, 0] + idx[:, :, 1] + idx[:, :, 2]) == 0
+    pos_ref[seam] = 0
+    nrm_ref[seam] = 0
+
+    from texir_code_b200 import models
+
+    class Stub(models.TracerO3d):          # the lookup needs no scene: give it a CPU "device"
+        def __init__(self):
+            torch.nn.Module.__init__(self)
+            self.scene = type("S", (), {"device": torch.device("cpu")})()
+            self.position_texture = self.normal_texture = self.index_texture = None
+
+    t = Stub()
+    pos, nrm = t.calcute_position_normal_texture([torch.from_numpy(v) for v in views], idx)
+    assert np.array_equal(pos.numpy(), pos_ref) and np.array_equal(nrm.numpy(), nrm_ref)
+    assert t.position_texture is pos and t.index_texture is idx
+    with pytest.raises(ValueError):
+        Stub().forward()                                                          # nothing to trace yet
+
+
+def test_draw_shift_is_the_reference_stream_on_any_path():
+    from texir_code_b200.sample_util import draw_shift
+    torch.manual_seed(11)
+    a = torch.rand(7, 1, 2)
+    b = torch.rand(5, 1, 2)
+    torch.manual_seed(11)
+    assert torch.equal(draw_shift(7, "cpu"), a) and torch.equal(draw_shift(5, "cpu"), b)
