@@ -89,6 +89,16 @@ TEXIR_API int texir_scene_set_bvh(texir_scene* scene, int bvh_kind);
 TEXIR_API int texir_scene_set_texture(texir_scene* scene, const float* tex, int H, int W, int layout,
                                       int src_on_device, void* stream);
 
+/* The same texture kept as the 4-byte Radiance RGBE texels of its .hdr file (the reference's texture always comes from
+ * hdr_texture.hdr, mat_nvdiffrast.py:89): rgbe [H,W,4] bytes in file order (R, G, B mantissas, shared exponent; what
+ * texir_hdr_read_host returns), flip_rows != 0 = cv2.flip(texture, 0) (:90), exposure = train.hdr_exposure (an integer:
+ * a power-of-two factor folds into the exponent).  The kernels decode mantissa * 2^(E - 136 + exposure) per tap, which
+ * is EXACTLY the float32 value of the cv2.imread + multiply path -- results are bit-identical to
+ * texir_scene_set_texture of the decoded texture, with a quarter of the texture bytes in HBM / L2.  The texture set
+ * last (this call or texir_scene_set_texture) is the active one. */
+TEXIR_API int texir_scene_set_texture_rgbe(texir_scene* scene, const uint8_t* rgbe, int H, int W, int flip_rows,
+                                           int exposure, int src_on_device, void* stream);
+
 /* ---- cast_rays: replaces RaycastingScene.cast_rays (mat_nvdiffrast.py:294-295).
  * rays [R,6] = (origin, direction).  Outputs: t_hit [R] (inf on miss, units of |d|),
  * prim_id [R] u32 (0xFFFFFFFF on miss), prim_uv [R,2] (0 on miss), prim_normal [R,3] (unit

@@ -47,6 +47,7 @@ SIGNATURES = {
     "texir_scene_get_info": (c_int, [_P, POINTER(SceneInfo)]),
     "texir_scene_set_bvh": (c_int, [_P, c_int]),
     "texir_scene_set_texture": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P]),
+    "texir_scene_set_texture_rgbe": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     "texir_cast_rays": (c_int, [_P, _P, c_int64, _P, _P, _P, _P, _P]),
     "texir_cast_rays_stats": (c_int, [_P, _P, c_int64, _P, _P, _P, _P, _P]),
     "texir_generate_dir": (c_int, [_P, _P, _P, c_int64, c_int, c_int, _P, _P]),

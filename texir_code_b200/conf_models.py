@@ -249,6 +249,14 @@ def _radiance_texture(path_mesh: str, exposure: float, device) -> torch.Tensor:
     return (t.permute(2, 0, 1).unsqueeze(0).float() * (2 ** exposure)).contiguous()
 
 
+def _packed_texture(path_mesh: str, exposure: float, float_texture: torch.Tensor):
+    """the same texture as the file's own 4-byte RGBE texels for Scene.set_texture_rgbe (exact for an integer exposure)"""
+    if int(exposure) != exposure:
+        return None
+    from .postprocess import imread_hdr_rgbe
+    return (imread_hdr_rgbe(path_mesh.replace("out1.obj", "hdr_texture.hdr")), int(exposure), float_texture)
+
+
 class MaterialModel(models.MaterialModel):
     """models.mat_nvdiffrast.MaterialModel with the reference's constructor (mat_nvdiffrast.py:36-101)."""
 
@@ -268,6 +276,8 @@ class MaterialModel(models.MaterialModel):
                          device=dev, materials_a_res=2048, materials_r_res=4096, cube_res=int(pano_res[1] / 4), irrt=irrt,
                          max_mip_level=_mip_level(8192), hdr_exposure=conf.get_float("train.hdr_exposure"),
                          vertex_normals=mesh["vertex_normals"], flip_tex_coords=True, **kw)
+        if gt_irf:  # the kernels read the .hdr's own RGBE texels (bit-identical radiance, a quarter of the bytes)
+            self.texture_rgbe = _packed_texture(path, conf.get_float("train.hdr_exposure"), self.texture)
         self.conf, self.ids, self.extrinsics, self.optim_cam = conf, ids, extrinsics, optim_cam
         self.path_traced_mesh, self.pano_res, self.gt_irrt = path, pano_res, gt_irrt
         self.resolution = conf.get_list("train.env_res", default=[8, 16])
@@ -288,6 +298,7 @@ class TracerO3d(models.TracerO3d):
         super().__init__(mesh["vertices"], mesh["triangles"], mesh["triangle_uvs"], texture,
                          sample_l=conf.get_list("train.sample_light", default=[64, 64]),
                          sample_type=conf.get_list("models.render.sample_type", default=["uniform", "importance"]), device=dev)
+        self.texture_rgbe = _packed_texture(path, conf.get_float("train.hdr_exposure"), self.texture)
         self.conf, self.ids, self.extrinsics, self.optim_cam = conf, ids, extrinsics, optim_cam
         self.path_traced_mesh = path
         self.cube_res = 256

@@ -44,6 +44,7 @@ struct DeviceBVH {
     void* d_tris2 = nullptr;         // float4 [3 * nt]
     void* d_slot_of_prim = nullptr;  // uint32 [nt]
     int64_t num_nodes = 0;
+    int top_nodes = 0;               // nodes [0, top_nodes) are the top levels, breadth first (the rest depth first)
     int depth = 0;
     double sah = 0.0, seconds = 0.0;
     float qmin[3], qstep[3];

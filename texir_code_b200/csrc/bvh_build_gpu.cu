@@ -457,7 +457,25 @@ __global__ void k_init_root(Ctx c, int64_t nt) {
     }
 }
 
-// depth-first numbering: inner-node counts of the subtrees (deepest level first), then the numbers (root first)
+// Numbering of the inner nodes: the top kTopDepth levels breadth first (a contiguous prefix of the node arrays that a
+// CTA can stage in shared memory with one bulk copy), every subtree below them depth first.  One thread walks the
+// (at most 2^kTopDepth) top nodes; the subtrees follow from their inner-node counts (deepest level first), top down.
+constexpr int kTopDepth = 10;
+__global__ void k_number_top(DNode* nodes, const int* __restrict__ level_begin, int levels, int* __restrict__ top_count) {
+    int next = 0;
+    const int dmax = levels < kTopDepth ? levels : kTopDepth;
+    for (int d = 0; d < dmax; ++d)
+        for (int i = level_begin[d]; i < level_begin[d + 1]; ++i)
+            if (nodes[i].left >= 0) nodes[i].index = next++;
+    *top_count = next;
+    if (dmax < levels)
+        for (int i = level_begin[dmax]; i < level_begin[dmax + 1]; ++i)
+            if (nodes[i].left >= 0) {
+                nodes[i].index = next;
+                next += nodes[i].inner;
+            }
+}
+
 __global__ void __launch_bounds__(256) k_count_inner(DNode* nodes, int begin, int end) {
     const int i = begin + blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= end) return;
@@ -678,7 +696,16 @@ bool build_bvh_device(const float* verts_host, int64_t nv, const int32_t* tris_h
         const int b = level_begin[d], e = level_begin[d + 1];
         if (e > b) k_count_inner<<<(unsigned)((e - b + 255) / 256), 256, 0, st>>>(d_nodes, b, e);
     }
-    for (int d = 0; d < levels; ++d) {
+    int* d_levels;
+    if (!S.alloc(&d_levels, level_begin.size())) {
+        cudaGetLastError();
+        err = "device BVH build: out of device memory";
+        return false;
+    }
+    GB_CUDA(cudaMemcpyAsync(d_levels, level_begin.data(), level_begin.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    int* d_top_count = d_small + 7;
+    k_number_top<<<1, 1, 0, st>>>(d_nodes, d_levels, levels, d_top_count);
+    for (int d = std::min(levels, kTopDepth); d < levels; ++d) {
         const int b = level_begin[d], e = level_begin[d + 1];
         if (e > b) k_number_inner<<<(unsigned)((e - b + 255) / 256), 256, 0, st>>>(d_nodes, b, e);
     }
@@ -731,6 +758,7 @@ bool build_bvh_device(const float* verts_host, int64_t nv, const int32_t* tris_h
     GB_CUDA(cudaStreamSynchronize(st));
     GB_CUDA(cudaGetLastError());
     out.depth = host_small[6];
+    out.top_nodes = host_small[7];
     if (out.depth > kStackSize - 2) {
         err = "build_bvh: BVH2 deeper than the traversal stack";
         return false;

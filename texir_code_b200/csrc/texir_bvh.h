@@ -85,6 +85,9 @@ struct SceneView {
     const float4* __restrict__ tex;        // radiance texture, RGBA float4 [H][W]
     int tex_w, tex_h;
     uint32_t num_tris;
+    int top_nodes;                         // qnodes2[0 .. top_nodes) are the top levels of the tree, breadth first
+    const uint32_t* __restrict__ tex_rgbe; // the same texture as 4-byte Radiance RGBE texels (R | G<<8 | B<<16 | E<<24), or null
+    int tex_rgbe_bias;                     // hdr_exposure folded into the shared exponent: value = mantissa * 2^(E - 136 + bias)
 };
 
 TX_HD float int_as_float_(int i) {
@@ -332,6 +335,29 @@ TX_HD Hit trace_bvh8(const SceneView& s, V3 o, V3 d, uint32_t* nodes_visited = n
 struct double2_ {
     double x, y;
 };
+// One RGBE texel -> the float32 values cv2.imread + `* 2**hdr_exposure` give for it (models/mat_nvdiffrast.py:89-93):
+// OpenCV's rgbe2float is mantissa * 2^(E - 136) (black when E == 0), the exposure another power of two, so the product
+// is exact in float32 -- the packed texture reproduces the fp32 one bit for bit at a quarter of the bytes.
+TX_HD void rgbe_texel(uint32_t w, int bias, float* r, float* g, float* b) {
+    const uint32_t e = w >> 24;
+    if (e == 0u) {
+        *r = *g = *b = 0.f;
+        return;
+    }
+    const int k = (int)e - 136 + bias;
+    const float fr = (float)(w & 0xFFu), fg = (float)((w >> 8) & 0xFFu), fb = (float)((w >> 16) & 0xFFu);
+    if (k >= -126 && k <= 127) {
+        const float scale = int_as_float_((k + 127) << 23);
+        *r = fr * scale;
+        *g = fg * scale;
+        *b = fb * scale;
+    } else {  // denormal or overflowing scale: exact scaling by the library
+        *r = ldexpf(fr, k);
+        *g = ldexpf(fg, k);
+        *b = ldexpf(fb, k);
+    }
+}
+
 TX_HD V3 fetch_radiance(const SceneView& s, const Hit& h) {
     if (!(h.t > kHitEps && h.t < INFINITY)) return v3(0.f, 0.f, 0.f);
     double tuv[6];
@@ -345,6 +371,16 @@ TX_HD V3 fetch_radiance(const SceneView& s, const Hit& h) {
     float gu, gv;
     interp_uv(tuv, h.u, h.v, &gu, &gv);
     Bilerp b4 = bilerp_setup(gu, gv, s.tex_w, s.tex_h);
+    if (s.tex_rgbe) {
+        const uint32_t* q0 = s.tex_rgbe + (size_t)b4.y0 * (size_t)s.tex_w;
+        const uint32_t* q1 = s.tex_rgbe + (size_t)b4.y1 * (size_t)s.tex_w;
+        float nwr, nwg, nwb, ner, neg, neb, swr, swg, swb, ser, seg, seb;
+        rgbe_texel(TX_LDG(q0 + b4.x0), s.tex_rgbe_bias, &nwr, &nwg, &nwb);
+        rgbe_texel(TX_LDG(q0 + b4.x1), s.tex_rgbe_bias, &ner, &neg, &neb);
+        rgbe_texel(TX_LDG(q1 + b4.x0), s.tex_rgbe_bias, &swr, &swg, &swb);
+        rgbe_texel(TX_LDG(q1 + b4.x1), s.tex_rgbe_bias, &ser, &seg, &seb);
+        return v3(bilerp_apply(b4, nwr, ner, swr, ser), bilerp_apply(b4, nwg, neg, swg, seg), bilerp_apply(b4, nwb, neb, swb, seb));
+    }
     const float4* r0 = s.tex + (size_t)b4.y0 * (size_t)s.tex_w;
     const float4* r1 = s.tex + (size_t)b4.y1 * (size_t)s.tex_w;
     float4 nw = TX_LD_LEAF(r0 + b4.x0), ne = TX_LD_LEAF(r0 + b4.x1), sw = TX_LD_LEAF(r1 + b4.x0), se = TX_LD_LEAF(r1 + b4.x1);

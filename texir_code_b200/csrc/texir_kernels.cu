@@ -85,6 +85,14 @@ static bool use_front() {  // TEXIR_FRONT=0: every ray walks from the root (no s
     static const bool on = env_int("TEXIR_FRONT", 1) != 0;
     return on;
 }
+static int top_smem_nodes() {  // TEXIR_TOP_SMEM=<nodes>: the north-star variant (top of the tree staged by TMA); 0 = off
+    static const int n = env_int("TEXIR_TOP_SMEM", 0);
+    return n;
+}
+static bool coop8() {  // TEXIR_COOP8=1: the warp-cooperative 8-wide walk (needs the 8-wide layout: built eagerly then)
+    static const bool on = env_int("TEXIR_COOP8", 0) != 0;
+    return on;
+}
 static int patch_bits(int N) {  // TEXIR_COHERENT_BITS=a overrides coherent_bits(N): shape of a warp's sample patch
     static const int forced = env_int("TEXIR_COHERENT_BITS", -1);
     if (forced < 0) return coherent_bits(N);
@@ -583,6 +591,215 @@ __global__ void __launch_bounds__(128, TX_LEAN_MINB) k_irradiance_lean(SceneView
     }
     float ax = group_sum(sm_acc[0][threadIdx.x], 32), ay = group_sum(sm_acc[1][threadIdx.x], 32),
           az = group_sum(sm_acc[2][threadIdx.x], 32);
+    if (live && lane == 0) store3_peers(E, p, irradiance_finish(ax, N), irradiance_finish(ay, N), irradiance_finish(az, N));
+}
+
+// North-star variant of the IrT kernel (BASELINE.json north_star; selected with TEXIR_TOP_SMEM=<nodes>, default off):
+// k_irradiance_lean<4, FRONT> whose CTA first stages the top `top_count` nodes of the QBVH2 into shared memory with one
+// TMA bulk copy (cp.async.bulk + mbarrier, texir_walk.h) and whose node step reads staged nodes with LDS.  Same sample
+// order, same visiting order, same sums: bit-identical results.  Dynamic shared memory: top_count * 32 bytes.
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) k_irradiance_top(SceneView s, const float* __restrict__ pos,
+                                                              const float* __restrict__ nrm, const float* __restrict__ shift,
+                                                              const int32_t* __restrict__ order, int64_t P, int N, int mode,
+                                                              int abits, int top_count, PeerOut E) {
+    extern __shared__ __align__(16) uint4 sm_top[];
+    __shared__ __align__(8) uint64_t sm_bar;
+    __shared__ IrtPointSmem sm_pt[4];
+    __shared__ float sm_acc[3][128];
+    __shared__ uint4 sm_front[4][kMaxFront];
+    __shared__ int sm_front_n[4], sm_front_start[4];
+    tma_stage_1d(sm_top, s.qnodes2, (uint32_t)top_count * 32u, &sm_bar, threadIdx.x == 0);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int64_t p = (int64_t)blockIdx.x * 4 + wid;
+    const bool live = p < P;
+    if (!live) p = P - 1;
+    if (order) p = __ldg(order + p);
+    if (lane == 0) {
+        V3 n = load3(nrm, p);
+        Frame f = make_frame(n);
+        IrtPointSmem& q = sm_pt[wid];
+        q.nx = n.x; q.ny = n.y; q.nz = n.z;
+        q.fn[0] = f.n.x; q.fn[1] = f.n.y; q.fn[2] = f.n.z;
+        q.fu[0] = f.u.x; q.fu[1] = f.u.y; q.fu[2] = f.u.z;
+        q.fv[0] = f.v.x; q.fv[1] = f.v.y; q.fv[2] = f.v.z;
+        q.sh0 = __ldg(shift + 2 * p + 0);
+        q.sh1 = __ldg(shift + 2 * p + 1);
+    }
+    sm_acc[0][threadIdx.x] = 0.f;
+    sm_acc[1][threadIdx.x] = 0.f;
+    sm_acc[2][threadIdx.x] = 0.f;
+    const V3 o = load3(pos, p);
+    if (lane == 0) qbvh2_point_front(s, o, sm_front[wid], &sm_front_n[wid], &sm_front_start[wid]);
+    __syncwarp();
+    const volatile IrtPointSmem* q = &sm_pt[wid];
+    const int M = (N + (1 << abits) - 1) >> abits;
+    for (int c = 0; c < (1 << abits); ++c) {
+        for (int j = lane; j < M; j += 32) {
+            const uint32_t i = ((uint32_t)j << abits) + (uint32_t)c;
+            if (i >= (uint32_t)N) continue;
+            V3 d;
+            {
+                Frame f;
+                f.n = v3(q->fn[0], q->fn[1], q->fn[2]);
+                f.u = v3(q->fu[0], q->fu[1], q->fu[2]);
+                f.v = v3(q->fv[0], q->fv[1], q->fv[2]);
+                float s0 = shift_wrap_clamp(hammersley0(i, (uint32_t)N), q->sh0);
+                float s1 = shift_wrap_clamp(radical_inverse(i), q->sh1);
+                d = sample_dir<false>(f, mode, s0, s1, 0.f).d;
+            }
+            Hit h = trace_qbvh2_front_top(s, o, d, sm_front[wid], ((volatile int*)sm_front_n)[wid],
+                                          ((volatile int*)sm_front_start)[wid], sm_top, top_count);
+            V3 L = fetch_radiance(s, h);
+            float ndl = clamp01(rn_dot(v3(q->nx, q->ny, q->nz), d));
+            sm_acc[0][threadIdx.x] += L.x * ndl;
+            sm_acc[1][threadIdx.x] += L.y * ndl;
+            sm_acc[2][threadIdx.x] += L.z * ndl;
+        }
+    }
+    float ax = group_sum(sm_acc[0][threadIdx.x], 32), ay = group_sum(sm_acc[1][threadIdx.x], 32),
+          az = group_sum(sm_acc[2][threadIdx.x], 32);
+    if (live && lane == 0) store3_peers(E, p, irradiance_finish(ax, N), irradiance_finish(ay, N), irradiance_finish(az, N));
+}
+
+// Second half of the north-star structure (BASELINE.json: "warp-per-ray ... with coalesced node loads"), as the widest
+// cooperative form this tree supports: the compressed 8-wide nodes (texir_bvh.h, BVH8), EIGHT LANES PER RAY -- lane k
+// of a group decodes and tests child k of the current node (the node's 80 bytes are read by the whole group in
+// coalesced broadcast loads), the group's hit bits come from one ballot, the ordered (octant-priority) traversal state
+// is kept redundantly by the eight lanes, and a leaf's triangles are tested one per lane with a shuffle arg-min.  Four
+// rays per warp.  Selected with TEXIR_COOP8=1 (measured against the default thread-per-ray walk).
+// Sample j of a point adds into accumulator slot j & 31 (shared memory), and the 32 slots are reduced like the lanes
+// of k_irradiance_lean: bit-identical results.
+__device__ __forceinline__ uint32_t group_or(uint32_t v, uint32_t gmask) { return __reduce_or_sync(gmask, v); }
+
+__device__ __forceinline__ Hit trace_bvh8_coop(const SceneView& s, V3 o, V3 d, int k /*lane in group*/, uint32_t gmask,
+                                               int gshift /*bit of the group's lane 0 in a ballot*/) {
+    Hit hit;
+    hit_reset(hit);
+    const V3 id = safe_rcp_dir(d);
+    const uint32_t oct_inv = (d.x < 0.f ? 0u : 1u) | (d.y < 0.f ? 0u : 2u) | (d.z < 0.f ? 0u : 4u);
+    Group8 stack[kStack8];
+    int sp = 0;
+    Group8 ng, tg;
+    ng.base = 0;
+    ng.mask = 0x80000000u;
+    tg.base = 0;
+    tg.mask = 0;
+    for (;;) {
+        if (ng.mask > 0x00FFFFFFu) {
+            const int bit = 31 - __clz(ng.mask);
+            ng.mask &= ~(1u << bit);
+            const uint32_t slot = (uint32_t)(bit - 24) ^ oct_inv;
+            const uint32_t node_idx = ng.base + __popc((ng.mask & 0xFFu) & ((1u << slot) - 1u));
+            if (ng.mask > 0x00FFFFFFu) stack[sp++] = ng;
+            const uint4* np = s.nodes8 + 5 * (size_t)node_idx;
+            const uint4 q0 = __ldg(np + 0), q1 = __ldg(np + 1);
+            // lane k's child: one byte of each of the six plane arrays (q2..q4 hold 8 bytes per array)
+            const unsigned char* qb = reinterpret_cast<const unsigned char*>(np + 2);
+            const float lx = (float)__ldg(qb + k), ly = (float)__ldg(qb + 8 + k), lz = (float)__ldg(qb + 16 + k);
+            const float hx = (float)__ldg(qb + 24 + k), hy = (float)__ldg(qb + 32 + k), hz = (float)__ldg(qb + 40 + k);
+            const uint32_t m = ((k < 4 ? q1.z : q1.w) >> (8 * (k & 3))) & 0xFFu;
+            const float px = __uint_as_float(q0.x), py = __uint_as_float(q0.y), pz = __uint_as_float(q0.z);
+            const float sx = __uint_as_float((q0.w & 0xFFu) << 23) * id.x, sy = __uint_as_float(((q0.w >> 8) & 0xFFu) << 23) * id.y,
+                        sz = __uint_as_float(((q0.w >> 16) & 0xFFu) << 23) * id.z;
+            const float ox = (px - o.x) * id.x, oy = (py - o.y) * id.y, oz = (pz - o.z) * id.z;
+            const float ax = lx * sx + ox, bx = hx * sx + ox, ay = ly * sy + oy, by = hy * sy + oy, az = lz * sz + oz, bz = hz * sz + oz;
+            const float tmin = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f));
+            const float tmax = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), hit.t));
+            const bool h = m != 0 && tmin * 0.9999996f <= tmax * 1.0000004f;
+            uint32_t mine_inner = 0, mine_tris = 0;
+            if (h) {
+                if ((m >> 5) == 1u && (m & 31u) >= 24u)
+                    mine_inner = 1u << (24 + ((uint32_t)k ^ oct_inv));
+                else
+                    mine_tris = (m >> 5) << (m & 31u);
+            }
+            ng.base = q1.x;
+            ng.mask = group_or(mine_inner, gmask) | (q0.w >> 24);
+            tg.base = q1.y;
+            tg.mask = group_or(mine_tris, gmask);
+        } else {
+            tg = ng;
+            ng.base = 0;
+            ng.mask = 0;
+        }
+        while (tg.mask != 0) {  // up to eight triangles at a time, one per lane, highest bit first like trace_bvh8
+            uint32_t rest = tg.mask;
+            int mybit = -1;
+            for (int i = 0; i <= k && rest; ++i) {
+                mybit = 31 - __clz(rest);
+                rest &= ~(1u << mybit);
+                if (i < k) mybit = -1;
+            }
+            // bits taken by this round: the (up to) eight highest
+            uint32_t taken = 0, r2 = tg.mask;
+            for (int i = 0; i < 8 && r2; ++i) {
+                const int b = 31 - __clz(r2);
+                r2 &= ~(1u << b);
+                taken |= 1u << b;
+            }
+            tg.mask &= ~taken;
+            Hit cand;
+            hit_reset(cand);
+            if (mybit >= 0) test_slot(s.tris8, (int)(tg.base + (uint32_t)mybit), o, d, cand);
+            // closest over the group (ties -> lowest primitive id), then against the ray's best so far
+            for (int off = 4; off > 0; off >>= 1) {
+                const float ot = __shfl_xor_sync(gmask, cand.t, off);
+                const float ou = __shfl_xor_sync(gmask, cand.u, off), ov = __shfl_xor_sync(gmask, cand.v, off);
+                const uint32_t op = __shfl_xor_sync(gmask, cand.prim, off);
+                if (ot < cand.t || (ot == cand.t && op < cand.prim)) {
+                    cand.t = ot; cand.u = ou; cand.v = ov; cand.prim = op;
+                }
+            }
+            if (cand.t < hit.t || (cand.t == hit.t && cand.prim < hit.prim)) hit = cand;
+        }
+        if (ng.mask <= 0x00FFFFFFu) {
+            if (sp == 0) break;
+            ng = stack[--sp];
+        }
+    }
+    (void)gshift;
+    return hit;
+}
+
+__global__ void __launch_bounds__(128, 6) k_irradiance_coop8(SceneView s, const float* __restrict__ pos,
+                                                             const float* __restrict__ nrm, const float* __restrict__ shift,
+                                                             const int32_t* __restrict__ order, int64_t P, int N, int mode,
+                                                             int abits, PeerOut E) {
+    __shared__ float sm_acc[4][3][32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, k = lane & 7, grp = lane >> 3;
+    const uint32_t gmask = 0xFFu << (8 * grp);
+    int64_t p = (int64_t)blockIdx.x * 4 + wid;
+    const bool live = p < P;
+    if (!live) p = P - 1;
+    if (order) p = __ldg(order + p);
+    const V3 n = load3(nrm, p), o = load3(pos, p);
+    const Frame f = make_frame(n);
+    const float sh0 = __ldg(shift + 2 * p + 0), sh1 = __ldg(shift + 2 * p + 1);
+    for (int c = 0; c < 3; ++c) sm_acc[wid][c][lane] = 0.f;
+    __syncwarp();
+    const int M = (N + (1 << abits) - 1) >> abits;
+    for (int c = 0; c < (1 << abits); ++c) {
+        for (int j0 = 0; j0 < M; j0 += 4) {  // the warp's four groups take four consecutive j
+            const int j = j0 + grp;
+            const uint32_t i = ((uint32_t)j << abits) + (uint32_t)c;
+            const bool active = j < M && i < (uint32_t)N;  // uniform over the group
+            if (!active) continue;
+            const float s0 = shift_wrap_clamp(hammersley0(i, (uint32_t)N), sh0);
+            const float s1 = shift_wrap_clamp(radical_inverse(i), sh1);
+            const V3 d = sample_dir<false>(f, mode, s0, s1, 0.f).d;
+            const Hit h = trace_bvh8_coop(s, o, d, k, gmask, 8 * grp);
+            if (k == 0) {
+                const V3 L = fetch_radiance(s, h);
+                const float ndl = clamp01(rn_dot(n, d));
+                sm_acc[wid][0][j & 31] += L.x * ndl;   // slot j & 31 = the lane that owns sample j in k_irradiance_lean
+                sm_acc[wid][1][j & 31] += L.y * ndl;
+                sm_acc[wid][2][j & 31] += L.z * ndl;
+            }
+        }
+    }
+    __syncwarp();
+    float ax = group_sum(sm_acc[wid][0][lane], 32), ay = group_sum(sm_acc[wid][1][lane], 32), az = group_sum(sm_acc[wid][2][lane], 32);
     if (live && lane == 0) store3_peers(E, p, irradiance_finish(ax, N), irradiance_finish(ay, N), irradiance_finish(az, N));
 }
 
@@ -1183,7 +1400,7 @@ int texir_scene_destroy(texir_scene* sc) {
     if (!sc) return 0;
     DeviceGuard guard(sc->info.device);
     void* ptrs[] = {sc->d_nodes2, sc->d_tris2, sc->d_qnodes2, sc->d_nodes8, sc->d_tris8,
-                    sc->d_uvs,    sc->d_slot_of_prim, sc->d_tex};
+                    sc->d_uvs,    sc->d_slot_of_prim, sc->d_tex, sc->d_tex_rgbe};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     delete sc;
@@ -1212,6 +1429,7 @@ static int upload_host_bvh(texir_scene* sc, const HostBVH& bvh, int64_t nt, bool
         sc->info.num_nodes2 = (int64_t)bvh.nodes2.size() / 4;
         sc->info.depth2 = bvh.depth2;
         sc->info.sah2 = bvh.sah2;
+        sc->view.top_nodes = bvh.top_nodes2;
     }
     if (!bvh.nodes8.empty()) {
         if ((rc = upload(bvh.nodes8, &sc->d_nodes8, &bytes)) || (rc = upload(bvh.tris8, &sc->d_tris8, &bytes))) return rc;
@@ -1276,6 +1494,7 @@ int texir_scene_create_ex(const float* verts_host, int64_t nv, const int32_t* tr
                 sc->hi[a] = d.scene_hi[a];
             }
             sc->info.num_nodes2 = d.num_nodes;
+            sc->view.top_nodes = d.top_nodes;
             sc->info.depth2 = d.depth;
             sc->info.sah2 = d.sah;
             sc->geom_bytes += d.num_nodes * 96 + nt * 52;
@@ -1299,6 +1518,15 @@ int texir_scene_create_ex(const float* verts_host, int64_t nv, const int32_t* tr
     if (builder == TEXIR_BUILDER_HOST)
         if (int rc = upload_host_bvh(sc, bvh, nt, false)) return bail(rc);
     sc->builder = builder;
+    if (coop8()) {  // the cooperative variant walks the 8-wide layout: build it now
+        HostBVH b8;
+        std::string e8;
+        if (!build_bvh(verts_host, nv, tris_host, nt, build_threads, b8, e8, true)) {
+            g_err = e8;
+            return bail(1);
+        }
+        if (int rc = upload_host_bvh(sc, b8, nt, /*only8=*/true)) return bail(rc);
+    }
     if (tri_uvs_host) {
         const size_t bytes = 6 * (size_t)nt * sizeof(double);
         if (cudaMalloc(&sc->d_uvs, bytes) != cudaSuccess || cudaMemcpy(sc->d_uvs, tri_uvs_host, bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
@@ -1380,7 +1608,12 @@ int texir_scene_set_texture(texir_scene* sc, const float* tex, int H, int W, int
     float* staging = nullptr;
     if (!src_on_device) {
         TX_CUDA(cudaMalloc((void**)&staging, (size_t)n * 3 * sizeof(float)));
-        TX_CUDA(cudaMemcpyAsync(staging, tex, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+        cudaError_t e = cudaMemcpyAsync(staging, tex, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) {
+            cudaFree(staging);
+            g_err = std::string("texir_scene_set_texture: upload: ") + cudaGetErrorString(e);
+            return 2;
+        }
         src = staging;
     }
     k_pack_texture<<<grid_for(n, 256), 256, 0, st>>>(src, H, W, layout, (float4*)sc->d_tex);
@@ -1391,8 +1624,59 @@ int texir_scene_set_texture(texir_scene* sc, const float* tex, int H, int W, int
     }
     if (rc) return rc;
     sc->view.tex = (const float4*)sc->d_tex;
+    sc->view.tex_rgbe = nullptr;  // the float texture is the active one from here on
     sc->view.tex_h = H;
     sc->view.tex_w = W;
+    return 0;
+}
+
+// file rows -> texture rows (optionally flipped: cv2.flip(texture, 0), mat_nvdiffrast.py:90), 4 bytes per texel kept
+__global__ void __launch_bounds__(256) k_pack_rgbe(const uint32_t* __restrict__ src, int H, int W, int flip,
+                                                   uint32_t* __restrict__ dst) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)H * W) return;
+    const int y = (int)(i / W), x = (int)(i - (int64_t)y * W);
+    dst[i] = src[(int64_t)(flip ? H - 1 - y : y) * W + x];
+}
+
+int texir_scene_set_texture_rgbe(texir_scene* sc, const uint8_t* rgbe, int H, int W, int flip_rows, int exposure,
+                                 int src_on_device, void* stream) {
+    if (!sc || !rgbe) TX_FAIL("texir_scene_set_texture_rgbe: NULL argument");
+    if (H <= 0 || W <= 0) TX_FAIL("texir_scene_set_texture_rgbe: empty texture");
+    if (exposure < -64 || exposure > 64) TX_FAIL("texir_scene_set_texture_rgbe: exposure out of range");
+    DeviceGuard guard(sc->info.device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n = (int64_t)H * W;
+    if (sc->d_tex_rgbe && (sc->view.tex_h != H || sc->view.tex_w != W)) {
+        TX_CUDA(cudaStreamSynchronize(st));
+        TX_CUDA(cudaFree(sc->d_tex_rgbe));
+        sc->d_tex_rgbe = nullptr;
+    }
+    if (!sc->d_tex_rgbe) TX_CUDA(cudaMalloc(&sc->d_tex_rgbe, (size_t)n * 4));
+    const uint32_t* src = (const uint32_t*)rgbe;
+    uint32_t* staging = nullptr;
+    if (!src_on_device) {
+        TX_CUDA(cudaMalloc((void**)&staging, (size_t)n * 4));
+        cudaError_t e = cudaMemcpyAsync(staging, rgbe, (size_t)n * 4, cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) {
+            cudaFree(staging);
+            g_err = std::string("texir_scene_set_texture_rgbe: upload: ") + cudaGetErrorString(e);
+            return 2;
+        }
+        src = staging;
+    }
+    k_pack_rgbe<<<grid_for(n, 256), 256, 0, st>>>(src, H, W, flip_rows, (uint32_t*)sc->d_tex_rgbe);
+    int rc = finish_launch("k_pack_rgbe");
+    if (staging) {
+        cudaStreamSynchronize(st);
+        cudaFree(staging);
+    }
+    if (rc) return rc;
+    sc->view.tex_rgbe = (const uint32_t*)sc->d_tex_rgbe;
+    sc->view.tex_rgbe_bias = exposure;
+    sc->view.tex_h = H;
+    sc->view.tex_w = W;
+    sc->tex_bytes = n * 4 + (sc->d_tex ? n * 16 : 0);
     return 0;
 }
 
@@ -1502,7 +1786,7 @@ static int check_scene_tex(const char* fn, const texir_scene* sc) {
         g_err = std::string(fn) + ": NULL scene";
         return 1;
     }
-    if (!sc->view.tex || !sc->view.tri_uvs) {
+    if ((!sc->view.tex && !sc->view.tex_rgbe) || !sc->view.tri_uvs) {
         g_err = std::string(fn) + ": scene has no radiance texture / triangle uvs";
         return 1;
     }
@@ -1676,7 +1960,22 @@ static int irradiance_launch(const char* fn, const texir_scene* sc, const float*
     cudaStream_t st = (cudaStream_t)stream;
     if (sc->info.bvh_kind == TEXIR_BVH8)
         k_irradiance<8><<<g, 128, 0, st>>>(sc->view, pos, nrm, shift, order, P, N, mode, G, ab, E);
-    else if (stream_mode() == 3 && G == 32 && use_qnodes())
+    else if (G == 32 && coop8() && sc->d_nodes8)
+        // north-star variant: warp-cooperative walk over 8-wide nodes, eight lanes per ray (TEXIR_COOP8=1); measured, not default
+        k_irradiance_coop8<<<g, 128, 0, st>>>(sc->view, pos, nrm, shift, order, P, N, mode, ab, E);
+    else if (stream_mode() == 3 && G == 32 && use_qnodes() && top_smem_nodes() > 0 && sc->view.top_nodes > 0) {
+        // north-star variant: top levels staged in shared memory by TMA (TEXIR_TOP_SMEM=<nodes>); measured, not default
+        int top = top_smem_nodes() < sc->view.top_nodes ? top_smem_nodes() : sc->view.top_nodes;
+        const size_t smem = (size_t)top * 32;
+        if (smem > 40 * 1024) {
+            static bool once = (cudaFuncSetAttribute(k_irradiance_top<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024), true);
+            (void)once;
+            if (top > 3072) top = 3072;
+            k_irradiance_top<4><<<g, 128, (size_t)top * 32, st>>>(sc->view, pos, nrm, shift, order, P, N, mode, ab, top, E);
+        } else {
+            k_irradiance_top<TX_LEAN_MINB><<<g, 128, smem, st>>>(sc->view, pos, nrm, shift, order, P, N, mode, ab, top, E);
+        }
+    } else if (stream_mode() == 3 && G == 32 && use_qnodes())
         if (use_front())
             k_irradiance_lean<4, true><<<g, 128, 0, st>>>(sc->view, pos, nrm, shift, order, P, N, mode, ab, E);
         else

@@ -216,6 +216,69 @@ TX_HD int qbvh2_step(const SceneView& s, const RayQ& r, float tbest, int node, i
 #endif
 }
 
+// ---------------------------------------------------------------------------------------------------
+// North-star variant (BASELINE.json: "flattened BVH staged into shared memory via TMA"): the first `top_count` nodes
+// of the array -- the top levels of the tree, breadth first -- are copied into the CTA's shared memory with ONE bulk
+// asynchronous copy (cp.async.bulk, the 1-D TMA path) that completes on an mbarrier; a node step then reads a staged
+// node with two LDS.128 instead of two global loads.  Measured against the default walk in profiles/ (DESIGN.md 3).
+// ---------------------------------------------------------------------------------------------------
+#ifdef __CUDA_ARCH__
+TX_D uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+TX_D void tma_stage_1d(void* dst_smem, const void* src_global, uint32_t bytes, uint64_t* mbar, bool issuer) {
+    // bytes: a multiple of 16; dst / src 16-byte aligned.  Call from every thread of the CTA.
+    if (issuer) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (issuer) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar)), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         smem_u32(dst_smem)),
+                     "l"(src_global), "r"(bytes), "r"(smem_u32(mbar))
+                     : "memory");
+    }
+    uint32_t done = 0;
+    while (!done)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done)
+                     : "r"(smem_u32(mbar))
+                     : "memory");
+}
+#endif
+
+// node step that reads staged nodes from shared memory (`top` = staged copy of qnodes2[0 .. top_count))
+TX_HD int qbvh2_step_top(const SceneView& s, const RayQ& r, float tbest, int node, int*& sp, const uint4* top, int top_count) {
+    uint4 q0, q1;
+    if (node < top_count) {
+        q0 = top[2 * node];
+        q1 = top[2 * node + 1];
+    } else {
+        const uint4* np = s.qnodes2 + 2 * (size_t)node;
+        q0 = ld_nc_u4(np + 0);
+        q1 = ld_nc_u4(np + 1);
+    }
+    const uint32_t fx = r.selx ^ 0x0022u, fy = r.sely ^ 0x0022u, fz = r.selz ^ 0x0022u;
+    const float t0n = fmaxf(fmaxf(qplane_(q0.x, r.selx, r.S.x, r.O.x), qplane_(q0.y, r.sely, r.S.y, r.O.y)),
+                            fmaxf(qplane_(q0.z, r.selz, r.S.z, r.O.z), 0.0f));
+    const float t0f = fminf(fminf(qplane_(q0.x, fx, r.S.x, r.O.x), qplane_(q0.y, fy, r.S.y, r.O.y)),
+                            fminf(qplane_(q0.z, fz, r.S.z, r.O.z), tbest));
+    const float t1n = fmaxf(fmaxf(qplane_(q0.w, r.selx, r.S.x, r.O.x), qplane_(q1.x, r.sely, r.S.y, r.O.y)),
+                            fmaxf(qplane_(q1.y, r.selz, r.S.z, r.O.z), 0.0f));
+    const float t1f = fminf(fminf(qplane_(q0.w, fx, r.S.x, r.O.x), qplane_(q1.x, fy, r.S.y, r.O.y)),
+                            fminf(qplane_(q1.y, fz, r.S.z, r.O.z), tbest));
+    const int c0 = (int)q1.z, c1 = (int)q1.w;
+    const bool h0 = t0n <= t0f, h1 = t1n <= t1f;
+    if (h0 && h1) {
+        const bool swap = t1n < t0n;
+        *sp++ = swap ? c0 : c1;
+        return swap ? c1 : c0;
+    }
+    if (h0) return c0;
+    if (h1) return c1;
+    return *--sp;
+}
+
 #ifndef TX_SPECULATIVE
 #define TX_SPECULATIVE 0
 #endif
@@ -374,6 +437,38 @@ TX_HD Hit trace_qbvh2_front(const SceneView& s, V3 o, V3 d, const uint4* entries
         if (node < 0 && node != kQSentinel) {
             qbvh2_leaf(s, r, node, hit);
             node = qstack_pop(sp, top);
+        }
+    }
+    return hit;
+}
+
+// trace_qbvh2_front with the staged top levels (same visiting order, same hits)
+TX_HD Hit trace_qbvh2_front_top(const SceneView& s, V3 o, V3 d, const uint4* entries, int count, int start, const uint4* top,
+                                int top_count) {
+    RayQ r;
+    rayq_setup(s, r, o, d);
+    Hit hit;
+    hit_reset(hit);
+    int stack[kStackSize];
+    int* sp = stack;
+    *sp++ = kQSentinel;
+    {
+        const uint32_t fx = r.selx ^ 0x0022u, fy = r.sely ^ 0x0022u, fz = r.selz ^ 0x0022u;
+        for (int k = 0; k < count; ++k) {
+            const uint4 e = entries[k];
+            const float tn = fmaxf(fmaxf(qplane_(e.x, r.selx, r.S.x, r.O.x), qplane_(e.y, r.sely, r.S.y, r.O.y)),
+                                   fmaxf(qplane_(e.z, r.selz, r.S.z, r.O.z), 0.0f));
+            const float tf = fminf(fminf(qplane_(e.x, fx, r.S.x, r.O.x), qplane_(e.y, fy, r.S.y, r.O.y)),
+                                   qplane_(e.z, fz, r.S.z, r.O.z));
+            if (tn <= tf) *sp++ = (int)e.w;
+        }
+    }
+    int node = start;
+    while (node != kQSentinel) {
+        while (node >= 0) node = qbvh2_step_top(s, r, hit.t, node, sp, top, top_count);
+        if (node < 0 && node != kQSentinel) {
+            qbvh2_leaf(s, r, node, hit);
+            node = *--sp;
         }
     }
     return hit;

@@ -25,6 +25,18 @@ from .sample_util import draw_shift, generate_dir
 from .scene import Scene
 
 
+def _upload_texture(model, sc: Scene) -> None:
+    """makes ``model.texture`` the scene's resident radiance texture.  ``model.texture_rgbe = (rgbe uint8 [H,W,4],
+    exposure, float_texture)`` (opt-in) keeps it as the 4-byte RGBE texels of the .hdr file it came from -- used as long
+    as model.texture still IS that float texture (stage -1 swaps in a thresholded copy, mat_nvdiffrast.py:143-150, which
+    goes up as floats)."""
+    packed = getattr(model, "texture_rgbe", None)
+    if packed is not None and model.texture is packed[2]:
+        sc.set_texture_rgbe(packed[0], packed[1], flip=True)
+    else:
+        sc.set_texture(model.texture)
+
+
 class HotPathMixin:
     """Expects on ``self``: scene (texir_code_b200.Scene built WITH triangle_uvs), texture (the reference's
     [1,3,H,W] tensor; re-uploaded when it is swapped or modified in place), sample_l, sample_type, and
@@ -36,7 +48,7 @@ class HotPathMixin:
         sc = self.scene
         if not isinstance(sc, Scene):
             raise TypeError("HotPathMixin needs self.scene to be a texir_code_b200.Scene built with triangle_uvs")
-        sc.set_texture(self.texture)
+        _upload_texture(self, sc)
         return sc
 
     def _draw_shift(self, b: int, device) -> torch.Tensor:
@@ -387,12 +399,12 @@ class TracerO3d(nn.Module):
 
     def query_irf(self, points, directions, num_sample):
         """tracer_o3d_irt.py:240"""
-        self.scene.set_texture(self.texture)
+        _upload_texture(self, self.scene)
         return ops.query_irf(self.scene, points, directions, num_sample)
 
     def irradiance(self, position: torch.Tensor, normal: torch.Tensor, shift: Optional[torch.Tensor] = None):
         """position, normal [P,3] -> E [P,3]; one fused launch"""
-        self.scene.set_texture(self.texture)
+        _upload_texture(self, self.scene)
         P = position.shape[0]
         if shift is None:
             shift = draw_shift(P, position.device)

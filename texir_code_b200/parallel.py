@@ -270,8 +270,9 @@ class ShardedIrradiance:
 
     def __call__(self, position: torch.Tensor, normal: torch.Tensor, shift: torch.Tensor) -> torch.Tensor:
         from . import ops
+        from .models import _upload_texture
         scene = self.tracer.scene
-        scene.set_texture(self.tracer.texture)
+        _upload_texture(self.tracer, scene)
         N, mode = int(self.tracer.sample_l[0]), self.tracer.sample_type[0]
         # Morton order of ALL texels (the same on every rank); a rank takes every world-th block of it
         order = ops.point_order(scene, position) if (self.world > 1 or self.P > 4096) else None

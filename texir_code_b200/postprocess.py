@@ -93,6 +93,18 @@ def imread_hdr(path: str, device="cuda") -> torch.Tensor:
     return rgbe_decode(host.to(device, non_blocking=True), bgr=True)
 
 
+def imread_hdr_rgbe(path: str) -> torch.Tensor:
+    """the raw RGBE texels of a .hdr file: uint8 [H,W,4] in file order (R, G, B mantissas, shared exponent), pinned host
+    memory -- what Scene.set_texture_rgbe takes (no float decode at all)"""
+    lib = _lib.load()
+    h, w = ctypes.c_int(), ctypes.c_int()
+    _lib.check(lib.texir_hdr_read_info(os.fsencode(path), ctypes.byref(h), ctypes.byref(w)), "texir_hdr_read_info")
+    pin = torch.cuda.is_available()
+    host = torch.empty((h.value, w.value, 4), dtype=torch.uint8, pin_memory=pin)
+    _lib.check(lib.texir_hdr_read_host(os.fsencode(path), host.data_ptr(), h.value, w.value), "texir_hdr_read_host")
+    return host
+
+
 def save_irr_texture(irr_texture: torch.Tensor, path: str) -> None:
     """trainer/generate_ir_texture.py:80-82: the model's RGB [H,W,3] texture is written channel-reversed (BGR)"""
     imwrite_hdr(path, irr_texture.flip(-1))

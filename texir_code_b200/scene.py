@@ -136,6 +136,35 @@ class Scene:
         self._tex_ref = texture  # keeps data_ptr from being recycled by another tensor
         self.tex_hw = (H, W)
 
+    def set_texture_rgbe(self, rgbe, exposure: int = 0, flip: bool = True) -> None:
+        """The radiance texture as the RGBE texels of its .hdr file: rgbe uint8 [H,W,4] in file order (R, G, B, E --
+        ``postprocess.imread_hdr_rgbe(path)``), CPU or CUDA; ``flip`` = the reference's cv2.flip(texture, 0) and
+        ``exposure`` its integer train.hdr_exposure (mat_nvdiffrast.py:89-93).  Bit-identical results to set_texture of
+        the decoded float texture, 4 bytes per texel resident instead of 16."""
+        if int(exposure) != exposure:
+            raise ValueError("the RGBE form needs an integer hdr_exposure (a power-of-two factor folds into the exponent); "
+                             "use set_texture for %r" % (exposure,))
+        t = rgbe if isinstance(rgbe, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(np.asarray(rgbe), dtype=np.uint8))
+        if t.dtype != torch.uint8 or t.dim() != 3 or t.shape[2] != 4:
+            raise ValueError("rgbe must be uint8 [H,W,4]")
+        t = t.contiguous()
+        H, W = int(t.shape[0]), int(t.shape[1])
+        key = ("rgbe", t.data_ptr(), t._version, (H, W), int(exposure), bool(flip))
+        if key == self._tex_key:
+            return
+        on_dev = t.is_cuda
+        if on_dev and t.device != self.device:
+            t = t.to(self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().texir_scene_set_texture_rgbe(self.handle, _ptr(t), H, W, int(bool(flip)), int(exposure),
+                                                                int(on_dev), _stream_ptr(self.device)),
+                       "texir_scene_set_texture_rgbe")
+            if on_dev:
+                torch.cuda.current_stream(self.device).synchronize()
+        self._tex_key = key
+        self._tex_ref = (rgbe, t)
+        self.tex_hw = (H, W)
+
     def texture_key(self):
         """identity of the radiance texture that is resident now (what a ray-recomputing backward must find again)"""
         return self._tex_key
