@@ -287,13 +287,13 @@ def run_ours(args):
     if world > 1:
         collective = args.collective
         try:
-            job = parallel.ShardedIrradiance(tracer, P, collective=collective)
+            job = parallel.ShardedIrradiance(tracer, P, collective=collective, block=args.block)
         except Exception as exc:  # no peer mapping between these GPUs: the library collective does the same step
             if collective != "peer":
                 raise
             sys.stderr.write("peer memory unavailable (%s); using the NCCL formulation\n" % exc)
             collective = "nccl"
-            job = parallel.ShardedIrradiance(tracer, P, collective="nccl")
+            job = parallel.ShardedIrradiance(tracer, P, collective="nccl", block=args.block)
     else:
         job = parallel.ShardedIrradiance(tracer, P)
 
@@ -338,7 +338,7 @@ def run_ours(args):
     # ---- the library formulation of the same collective, for comparison (N > 1, peer path only) -----
     nccl_cmp = None
     if world > 1 and collective == "peer":
-        job2 = parallel.ShardedIrradiance(tracer, P, collective="nccl")
+        job2 = parallel.ShardedIrradiance(tracer, P, collective="nccl", block=args.block)
         ms2, _ = timer.run(lambda: job2(d_pos, d_nrm, d_shift), args.steps, 1)
         same = bool(torch.equal(job2.result, job.result))
         nccl_cmp = {"ms_per_step": ms2 / args.steps, "value": P * SPP * args.steps / (ms2 * 1e-3), "bit_identical_to_peer": same,
@@ -411,7 +411,7 @@ def run_ours(args):
                 "l2": "no flush: BVH + triangles + UVs + texture = %.0f MB resident, larger than the 126 MB L2"
                       % (info["device_bytes"] / 1e6),
                 "scene_create_s": round(t_build, 3), "bvh_builder": {1: "host", 2: "device"}.get(info.get("builder"), "?"),
-                "sharding": "none" if world == 1 else "texels dealt out in 512-blocks along a Morton curve, block-cyclic over %d ranks" % world,
+                "sharding": "none" if world == 1 else "texels dealt out in %d-blocks along a Morton curve, block-cyclic over %d ranks" % (args.block, world),
                 "collective": {"none": "none (one GPU)", "peer": "all-gather fused into the kernel epilogue (NVLink peer stores) + flag barrier, inside the timed step",
                                "nccl": "one NCCL all-reduce(sum) of [P,3] per step, inside the timed step"}[collective],
             },
@@ -583,12 +583,11 @@ def bench_material_stage(scene, sc, dev, args, texture, timer):
 
 
 def train_step_breakdown(mm, mvp, cam, g_img, dev):
-    """CUDA-event split of one stage-2 step: G-buffer / pyramids+fetch+render (forward) / backward kernel + folds"""
+    """CUDA-event split of one stage-2 step (median of 15): G-buffer / pyramids+fetch+render (forward) / backward kernel + folds"""
     import torch
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-    acc = [0.0, 0.0, 0.0]
-    reps = 10
-    for _ in range(reps):
+    parts = [[], [], []]
+    for _ in range(15):
         mm.zero_grad(set_to_none=True)
         torch.cuda.synchronize(dev)
         ev[0].record()
@@ -602,8 +601,10 @@ def train_step_breakdown(mm, mvp, cam, g_img, dev):
         ev[3].record()
         torch.cuda.synchronize(dev)
         for k in range(3):
-            acc[k] += ev[k].elapsed_time(ev[k + 1])
-    return {"gbuffer": acc[0] / reps, "pyramids_fetch_render": acc[1] / reps, "backward_and_folds": acc[2] / reps}
+            parts[k].append(ev[k].elapsed_time(ev[k + 1]))
+    med = [statistics.median(p) for p in parts]
+    return {"gbuffer": med[0], "pyramids_fetch_render": med[1], "backward_and_folds": med[2],
+            "note": "each part is timed after a device synchronise, so it includes the host time to launch it"}
 
 
 def bench_mat_sharded(scene, sc, dev, args, texture, timer, rank, world):
@@ -652,8 +653,25 @@ def bench_mat_sharded(scene, sc, dev, args, texture, timer, rank, world):
         out["stage2_%dspp" % nspec] = {"ms_per_step": ms / reps, "ray_samples_per_s": 6 * 128 * 128 * nspec / (ms / reps * 1e-3),
                                        "allreduce_bytes": nbytes, "compute_ms_max_rank": float(t[0]), "allreduce_ms_max_rank": float(t[1]),
                                        "timed_steps": reps}
+        # the other synchronisation: all-gather of the per-pixel gradient rows (11 floats per pixel) inside the backward,
+        # every rank scatters all rows -- no all-reduce of the 112 MiB textures
+        mm.grad_sync = "gather"
+
+        def step_gather():
+            mm.zero_grad(set_to_none=True)
+            res = mm(mvp, 0, cam, 2)
+            res["rgb"].backward(g_loc)
+
+        step_gather()
+        ms, _ = timer.run(step_gather, reps, 3)
+        out["stage2_%dspp" % nspec]["ms_per_step_gather_sync"] = ms / reps
+        out["stage2_%dspp" % nspec]["gather_bytes"] = 6 * 128 * 128 * 11 * 4
         mm.shift_rng, mm.cache_gbuffers = "device", True      # opt-ins: shift from the CUDA generator, G-buffer kept per view
         torch.cuda.manual_seed(1234)
+        step_gather()
+        ms, _ = timer.run(step_gather, reps, 3)
+        out["stage2_%dspp" % nspec]["ms_per_step_gather_sync_device_rng_cached_gbuffer"] = ms / reps
+        mm.grad_sync = "allreduce"
         step()
         ms, _ = timer.run(step, reps, 3)
         out["stage2_%dspp" % nspec]["ms_per_step_device_rng_cached_gbuffer"] = ms / reps
@@ -705,6 +723,7 @@ def main():
     ap.add_argument("--bvh", type=int, default=2, choices=[2, 8], help="BVH layout the kernels traverse")
     ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
                     help="multi-GPU IrT: results stored to every rank by the kernel (peer) or one NCCL all-reduce")
+    ap.add_argument("--block", type=int, default=512, help="multi-GPU IrT: texels per dealt-out block of the Morton order")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-mat", action="store_true", help="skip the material-stage legs")
     ap.add_argument("--no-cold", action="store_true", help="skip the cold-start (scene creation included) leg")

@@ -302,6 +302,14 @@ TEXIR_API int texir_mat_fetch(const float* tex_a, const float* mips_a, int Ha, i
                               int Wi, int Li, const float* uv, const float* uv_da, int64_t P, float* albedo, float* rough,
                               float* rough_womip, float* irr, void* stream);
 
+/* The texture-space half of the Mat-stage backward on its own: P rows of 11 floats = (u, v, du/dX, du/dY, dv/dX, dv/dY,
+ * g_albedo[3], g_roughness taken through the mip-mapped fetch, g_roughness taken through the bilinear fetch) scattered
+ * with atomics into the gradient pyramids (zero-initialised by the caller; fold afterwards).  Used when the per-pixel
+ * gradients of all ranks were all-gathered (4.3 MB at the reference's 98 304 pixels) instead of all-reducing the
+ * 112 MiB texture gradients: every rank then scatters the same rows. */
+TEXIR_API int texir_mat_scatter_rows(const float* rows, int64_t P, float* g_tex_a, float* g_mips_a, int Ha, int Wa, int La,
+                                     float* g_tex_r, float* g_mips_r, int Hr, int Wr, int Lr, void* stream);
+
 /* ---- peer memory of the multi-GPU path: one process per GPU; a rank exports a device buffer as a 64-byte
  *      handle (CUDA IPC), the other ranks map it over NVLink / NVSwitch and kernels store into it directly.
  * texir_peer_alloc: zeroed buffer on `device` + its handle (handle_out: TEXIR_PEER_HANDLE_BYTES, HOST memory);

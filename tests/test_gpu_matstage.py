@@ -316,3 +316,74 @@ def test_two_ranks_sharded_irt_with_peer_stores(tx, cuda_device, tmp_path):
         assert p.returncode == 0, o[-3000:]
         line = [l for l in o.splitlines() if l.startswith("RESULT")][-1].split()
         assert line[1:] == [str(r), "True", "True", "False"], o[-3000:]
+
+
+_MAT_WORKER = r"""
+import os, sys
+sys.path.insert(0, sys.argv[1])
+import numpy as np, torch, torch.distributed as dist
+rank, world, port = int(sys.argv[2]), int(sys.argv[3]), sys.argv[4]
+os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=port)
+dist.init_process_group("gloo", rank=rank, world_size=world)
+sys.path.insert(0, os.path.join(sys.argv[1], "tests"))
+from test_host_logic import _reference_cube_mvps
+from texir_code_b200 import models, parallel, synth, Scene
+dev = torch.device("cuda", 0)
+torch.cuda.set_device(dev)
+sc = synth.make_room_scene(4000, seed=666, clutter=6, tex_res=128, uv_kind="planar")
+tex = torch.from_numpy(synth.make_radiance_texture(128, kind="smooth"))
+scene = Scene(sc.vertices, sc.triangles, sc.triangle_uvs, device=dev)
+c2w = np.eye(4, dtype=np.float32); c2w[:3, 3] = [0.2, -0.1, 0.3]
+mvp, cam = _reference_cube_mvps(c2w)
+res = 32
+rng = np.random.default_rng(3)
+irrt = rng.uniform(0.5, 3.0, (32, 32, 3)).astype(np.float32)
+a0 = torch.from_numpy(rng.uniform(0.1, 0.9, (64, 64, 3)).astype(np.float32)).to(dev)
+r0 = torch.from_numpy(rng.uniform(0.05, 0.7, (64, 64, 1)).astype(np.float32)).to(dev)
+g_full = torch.from_numpy(rng.normal(size=(6, res, res, 3)).astype(np.float32)).to(dev)
+w_r = torch.from_numpy(rng.normal(size=(6, res, res, 1)).astype(np.float32)).to(dev)
+def run(shard, sync):
+    mm = models.MaterialModel(None, None, sc.triangle_uvs, tex, sample_l=[16, 16], scene=scene, materials_a_res=64,
+                              materials_r_res=64, cube_res=res, irrt=irrt, max_mip_level=13, shard=shard, grad_sync=sync)
+    mm._warned_normals = True
+    with torch.no_grad():
+        mm.materials_a.copy_(a0); mm.materials_r.copy_(r0)
+    torch.manual_seed(666)
+    out = mm(mvp.to(dev), 0, cam, 2)
+    loc = (lambda t: t) if shard is None else (lambda t: parallel.local_pixels(t, shard[0], shard[1], 6))
+    loss = (out["rgb"] * loc(g_full).reshape(out["rgb"].shape)).sum() + (out["roughness"] * loc(w_r).reshape(out["roughness"].shape)).sum()
+    loss.backward()
+    if shard is not None and sync == "allreduce":
+        parallel.allreduce_gradients([mm.materials_a, mm.materials_r])
+    return mm.materials_a.grad.clone(), mm.materials_r.grad.clone()
+full = run(None, "allreduce")
+ar = run((rank, world), "allreduce")
+ga = run((rank, world), "gather")
+rel = lambda x, y: float(torch.linalg.norm(x - y) / torch.linalg.norm(y))
+print("RESULT", rank, rel(ar[0], full[0]) < 1e-5, rel(ar[1], full[1]) < 1e-5, rel(ga[0], full[0]) < 1e-5, rel(ga[1], full[1]) < 1e-5, flush=True)
+dist.barrier()
+dist.destroy_process_group()
+"""
+
+
+def test_two_ranks_sharded_mat_step_allreduce_and_gather(tx, cuda_device, tmp_path):
+    """the sharded Mat-stage step on two processes (both on cuda:0, gloo): with either synchronisation -- ONE all-reduce of
+    the flat texture-gradient buffer, or one all-gather of the per-pixel gradient rows followed by the same scatter on every
+    rank -- every rank ends up with the one-GPU texture gradients (render terms and the loss's direct roughness term)"""
+    script = tmp_path / "mat_worker.py"
+    script.write_text(_MAT_WORKER)
+    port = str(31500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, str(r), "2", port], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = []
+    for p in procs:
+        try:
+            o, _ = p.communicate(timeout=300)
+        except subprocess.TimeoutExpired:
+            p.kill()
+            o, _ = p.communicate()
+        outs.append(o)
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, o[-3000:]
+        line = [l for l in o.splitlines() if l.startswith("RESULT")][-1].split()
+        assert line[1:] == [str(r), "True", "True", "True", "True"], o[-3000:]

@@ -273,6 +273,31 @@ __global__ void __launch_bounds__(256) k_mat_fetch(FetchTex ta, FetchTex tr, Fet
     }
 }
 
+// per-pixel gradient rows scattered into the two textures' gradient pyramids: the texture-space half of the Mat-stage
+// backward on its own, for rows that were gathered from all ranks (parallel: "gather" gradient synchronisation).
+// row = (u, v, du/dX, du/dY, dv/dX, dv/dY, g_albedo[3], g_rough through the mip-mapped fetch, g_rough through the bilinear one)
+__global__ void __launch_bounds__(256) k_mat_scatter_rows(const float* __restrict__ rows, int64_t P, TexGrad ga, TexGrad gr) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    const float* r = rows + 11 * p;
+    const float u = __ldg(r + 0), v = __ldg(r + 1);
+    const float dudx = __ldg(r + 2), dudy = __ldg(r + 3), dvdx = __ldg(r + 4), dvdy = __ldg(r + 5);
+    if (ga.tex) {
+        const float t[3] = {__ldg(r + 6), __ldg(r + 7), __ldg(r + 8)};
+        if (t[0] != 0.f || t[1] != 0.f || t[2] != 0.f) tex_scatter_point(ga, u, v, mip_lod(dudx, dudy, dvdx, dvdy, ga.H, ga.W, ga.L), t);
+    }
+    if (gr.tex) {
+        const float r_mip = __ldg(r + 9), r_bil = __ldg(r + 10);
+        if (r_mip != 0.f) tex_scatter_point(gr, u, v, mip_lod(dudx, dudy, dvdx, dvdy, gr.H, gr.W, gr.L), &r_mip);
+        if (r_bil != 0.f) {
+            MipLod m0;
+            m0.level0 = m0.level1 = 0;
+            m0.frac = 0.f;
+            tex_scatter_point(gr, u, v, m0, &r_bil);
+        }
+    }
+}
+
 bool tileable(int H, int W) { return H >= kTile && W >= kTile && H % kTile == 0 && W % kTile == 0; }
 
 int check_tex(const char* fn, int H, int W, int C, int L) {
@@ -352,6 +377,26 @@ int texir_texture_mip_fold_into(float* g_tex, float* g_mips, int H, int W, int C
     if (clear && bytes_m && cudaMemsetAsync(g_mips, 0, bytes_m, st) != cudaSuccess)
         return fail("texir_texture_mip_fold_into: memset failed", 2);
     return 0;
+}
+
+int texir_mat_scatter_rows(const float* rows, int64_t P, float* g_tex_a, float* g_mips_a, int Ha, int Wa, int La, float* g_tex_r,
+                           float* g_mips_r, int Hr, int Wr, int Lr, void* stream) {
+    const char* fn = "texir_mat_scatter_rows";
+    if (P < 0) return fail(std::string(fn) + ": bad size");
+    if (P == 0) return 0;
+    if (!rows || (!g_tex_a && !g_tex_r)) return fail(std::string(fn) + ": NULL argument");
+    if (g_tex_a) {
+        if (int rc = check_tex(fn, Ha, Wa, 3, La)) return rc;
+        if (La > 0 && !g_mips_a) return fail(std::string(fn) + ": NULL pyramid");
+    }
+    if (g_tex_r) {
+        if (int rc = check_tex(fn, Hr, Wr, 1, Lr)) return rc;
+        if (Lr > 0 && !g_mips_r) return fail(std::string(fn) + ": NULL pyramid");
+    }
+    texir_host::ScopedDevice guard(texir_host::device_of(rows));
+    const TexGrad ga{g_tex_a, g_mips_a, Ha, Wa, 3, La}, gr{g_tex_r, g_mips_r, Hr, Wr, 1, Lr};
+    k_mat_scatter_rows<<<(unsigned)((P + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rows, P, ga, gr);
+    return finish_launch("k_mat_scatter_rows");
 }
 
 int texir_mat_fetch(const float* tex_a, const float* mips_a, int Ha, int Wa, int La, const float* tex_r,

@@ -165,8 +165,15 @@ class MaterialModel(HotPathMixin, nn.Module):
                  fused: bool = True, backward_mode: str = "stash", cube_res: int = 128, irrt=None,
                  max_mip_level: Optional[int] = 13, hdr_exposure: float = 5.0, vertex_normals=None,
                  scene: Optional[Scene] = None, flip_tex_coords: bool = True, shard=None, cache_gbuffers: bool = False,
-                 shift_rng: str = "reference"):
+                 shift_rng: str = "reference", grad_sync: str = "allreduce"):
         super().__init__()
+        if grad_sync not in ("allreduce", "gather"):
+            raise ValueError("grad_sync must be 'allreduce' or 'gather'")
+        # sharded model only.  'allreduce': the backward leaves this rank's partial texture gradients and the caller runs
+        # parallel.allreduce_gradients (ONE all-reduce of 112 MiB; replicas stay bit-identical).  'gather': the backward
+        # all-gathers the per-pixel gradients (4.3 MB) and every rank scatters all of them -- the full gradients without an
+        # all-reduce of the textures (float atomics arrive in a different order on each rank: equal up to rounding).
+        self.grad_sync = grad_sync
         if shift_rng not in ("reference", "device"):
             raise ValueError("shift_rng must be 'reference' (CPU generator, the reference's stream) or 'device'")
         self.shift_rng = shift_rng
@@ -255,7 +262,8 @@ class MaterialModel(HotPathMixin, nn.Module):
             self._scene(), self.mat_ws, self.materials_a, self.materials_r, self.irrt, n, p, cam_position, texc, texd,
             shift_spec, stage=stage, num_spec=int(self.sample_l[1]), max_mip_level=self.max_mip_level,
             mode_spec=self.sample_type[1], eps=getattr(self, "brdf_eps", 1e-14),
-            backward=getattr(self, "backward_mode", "stash"))
+            backward=getattr(self, "backward_mode", "stash"),
+            gather_group=(True, None) if (self.shard is not None and self.shard[1] > 1 and self.grad_sync == "gather") else None)
         alb = alb.reshape(*lead, 3)
         res = {"rgb": rgb.reshape(*lead, 3), "albedo": alb.detach() if stage == 1 else alb, "normal": normal.detach(),
                "position": (points + 2e-2 * normal).detach()}

@@ -415,7 +415,7 @@ class _MatStage(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, materials_a, materials_r, ws, scene, irrt, normal, points, cam, texc, texd, shift_spec, stage,
-                N_spec, mode_spec, eps, backward_mode, max_mip_level):
+                N_spec, mode_spec, eps, backward_mode, max_mip_level, gather_group):
         dev = normal.device
         P = int(normal.shape[0])
         lib = _lib.load()
@@ -446,6 +446,7 @@ class _MatStage(torch.autograd.Function):
                                            _ptr(irr), _ptr(shs), None, P, N_spec, 0, mode_spec, _lib.MODE_UNIFORM, eps,
                                            _ptr(rgb), _ptr(drgb), None, st), "texir_shade_fwd")
         ctx.ws, ctx.scene = ws, scene
+        ctx.gather_group = gather_group
         ctx.tex_key = scene.texture_key()
         ctx.cfg = (P, N_spec, mode_spec, eps, stage, La, Lr, (int(Ha), int(Wa)), (int(Hr), int(Wr)), need_a)
         ctx.have_drgb = drgb is not None
@@ -463,9 +464,10 @@ class _MatStage(torch.autograd.Function):
         P, N_spec, mode_spec, eps, stage, La, Lr, (Ha, Wa), (Hr, Wr), render_a = ctx.cfg
         dev = nrm.device
         need_a, need_r = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        need_a = need_a and (render_a or g_albedo is not None)   # stage 1: the render saw albedo.detach()
+        gather = ctx.gather_group is not None
+        need_a = need_a and (render_a or g_albedo is not None or gather)   # stage 1: the render saw albedo.detach()
         if not need_a and not need_r:
-            return (None,) * 17
+            return (None,) * 18
         _check_recompute_texture(ctx, need_r and drgb is None)
         lib, ws = _lib.load(), ctx.ws
         g = _f32c(g_rgb).reshape(P, 3) if g_rgb is not None else torch.zeros(P, 3, dtype=torch.float32, device=dev)
@@ -479,6 +481,38 @@ class _MatStage(torch.autograd.Function):
         out_a = flat[:n_a].view(Ha, Wa, 3) if need_a else None
         out_r = flat[n_a:].view(Hr, Wr, 1) if need_r else None
         ws.dirty = True
+        if gather:
+            # "gather" synchronisation: per-pixel gradients of THIS rank's pixels, then one all-gather of 11 floats per
+            # pixel over all ranks and the same scatter on every rank -- instead of an all-reduce of the textures
+            import torch.distributed as dist
+            g_alb_px = torch.zeros(P, 3, dtype=torch.float32, device=dev)
+            g_rough_px = torch.zeros(P, dtype=torch.float32, device=dev)
+            with torch.cuda.device(dev):
+                _lib.check(lib.texir_shade_bwd(ctx.scene.handle, _ptr(nrm), _ptr(albedo), _ptr(rough_in), _ptr(pos), _ptr(camc),
+                                               _ptr(irr), _ptr(shs), None, P, N_spec, 0, mode_spec, _lib.MODE_UNIFORM, eps, _ptr(g),
+                                               _ptr(drgb), None, _ptr(g_alb_px) if (render_a and need_a) else None,
+                                               _ptr(g_rough_px) if need_r else None, None, _stream_ptr(dev)), "texir_shade_bwd")
+            if add_a is not None:
+                g_alb_px = g_alb_px + add_a
+            zero = torch.zeros(P, dtype=torch.float32, device=dev)
+            r_mip = (g_rough_px if stage == 2 else zero) + (add_r if add_r is not None else 0)
+            r_bil = (g_rough_px if stage == 1 else zero) + (add_rw if add_rw is not None else 0)
+            rows = torch.cat([uv, da, g_alb_px, r_mip.unsqueeze(1), r_bil.unsqueeze(1)], 1).contiguous()
+            from .parallel import all_gather_rows
+            world = dist.get_world_size(ctx.gather_group[1])
+            allrows = all_gather_rows(rows, ctx.gather_group[1])
+            with torch.cuda.device(dev):
+                st = _stream_ptr(dev)
+                _lib.check(lib.texir_mat_scatter_rows(_ptr(allrows), world * P, _ptr(sa), _ptr(sma), Ha, Wa, La if need_a else 0,
+                                                      _ptr(sr), _ptr(smr), Hr, Wr, Lr if need_r else 0, st), "texir_mat_scatter_rows")
+                if need_a:
+                    _lib.check(lib.texir_texture_mip_fold_into(_ptr(sa), _ptr(sma), Ha, Wa, 3, La, _ptr(out_a), 1, st),
+                               "texir_texture_mip_fold_into")
+                if need_r:
+                    _lib.check(lib.texir_texture_mip_fold_into(_ptr(sr), _ptr(smr), Hr, Wr, 1, Lr, _ptr(out_r), 1, st),
+                               "texir_texture_mip_fold_into")
+            ws.dirty = False
+            return (out_a, out_r) + (None,) * 16
         with torch.cuda.device(dev):
             st = _stream_ptr(dev)
             _lib.check(lib.texir_shade_bwd_mat(
@@ -494,24 +528,27 @@ class _MatStage(torch.autograd.Function):
                 _lib.check(lib.texir_texture_mip_fold_into(_ptr(sr), _ptr(smr), Hr, Wr, 1, Lr, _ptr(out_r), 1, st),
                            "texir_texture_mip_fold_into")
         ws.dirty = False
-        return (out_a, out_r) + (None,) * 15
+        return (out_a, out_r) + (None,) * 16
 
 
 def mat_stage(scene: Scene, ws: MatWorkspace, materials_a, materials_r, irrt, normal, points, cam_position, texc, texd,
               shift_spec, *, stage: int, num_spec: int, max_mip_level: Optional[int] = None,
-              mode_spec: str = "importance", eps: float = TINY_TINY_NUMBER, backward: str = "stash"):
+              mode_spec: str = "importance", eps: float = TINY_TINY_NUMBER, backward: str = "stash", gather_group=None):
     """One Mat-stage step on flat per-pixel G-buffer tensors (normal, points [P,3]; texc [P,2]; texd [P,4]):
     -> (rgb [P,3], albedo [P,3], roughness [P,1], roughness_womipmap [P,1], irr [P,3]) exactly as
     MaterialModel.forward computes them for stage 1 (render(albedo.detach(), roughness_womipmap)) or stage 2
     (render(albedo, roughness)), models/mat_nvdiffrast.py:131-139,179-182.  Gradients of every output reach
-    materials_a / materials_r through ONE backward kernel + one fold per texture."""
+    materials_a / materials_r through ONE backward kernel + one fold per texture.
+    gather_group = (True, process group or None): multi-GPU "gather" synchronisation -- the pixels are this rank's share,
+    the backward all-gathers the per-pixel gradients of all ranks (11 floats per pixel) and scatters all of them, so every
+    rank ends up with the FULL texture gradients and no all-reduce of the textures is needed."""
     _need_cuda("mat_stage", normal)
     if stage not in (1, 2):
         raise ValueError("mat_stage covers the ray-traced stages 1 and 2")
     if backward not in ("stash", "recompute"):
         raise ValueError("backward must be 'stash' or 'recompute'")
     return _MatStage.apply(materials_a, materials_r, ws, scene, irrt, normal, points, cam_position, texc, texd, shift_spec,
-                           int(stage), int(num_spec), _lib.MODES[mode_spec], float(eps), backward, max_mip_level)
+                           int(stage), int(num_spec), _lib.MODES[mode_spec], float(eps), backward, max_mip_level, gather_group)
 
 
 # --------------------------------------------------------------------------------------------------

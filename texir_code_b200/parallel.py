@@ -103,6 +103,17 @@ def gather_points(local: torch.Tensor, num_points: int, align: int = 1, group=No
     return torch.cat([b[:n] for b, n in zip(bufs, sizes)], dim=0)
 
 
+def all_gather_rows(rows: torch.Tensor, group=None) -> torch.Tensor:
+    """[n, C] on every rank (same n) -> [world * n, C], rank-major; one collective"""
+    world = dist.get_world_size(group)
+    out = torch.empty((world * rows.shape[0],) + tuple(rows.shape[1:]), dtype=rows.dtype, device=rows.device)
+    if dist.get_backend(group) == "nccl":
+        dist.all_gather_into_tensor(out, rows.contiguous(), group=group)
+    else:  # gloo (the CPU-side tests): list form
+        dist.all_gather(list(out.chunk(world, 0)), rows.contiguous(), group=group)
+    return out
+
+
 def _flat_view_of(grads: List[torch.Tensor]) -> Optional[torch.Tensor]:
     """the ONE contiguous buffer the gradients tile, if they do (ops._MatStage returns both texture gradients as
     views of one allocation and autograd hands those views out as .grad unchanged); None otherwise"""
