@@ -310,6 +310,13 @@ TEXIR_API int texir_mat_fetch(const float* tex_a, const float* mips_a, int Ha, i
 TEXIR_API int texir_mat_scatter_rows(const float* rows, int64_t P, float* g_tex_a, float* g_mips_a, int Ha, int Wa, int La,
                                      float* g_tex_r, float* g_mips_r, int Hr, int Wr, int Lr, void* stream);
 
+/* ---- the reference's shift stream on the device: n values of torch.rand (float32, CPU default generator:
+ * at::mt19937 + uniform_real_distribution<float>, utils/sample_util.py:102) from the generator state
+ * (state_in: the 624 state words; left / next: the engine's counters, all from torch.get_rng_state()), bit for bit, and
+ * the advanced state (state_out: 624 words, then left, next) for torch.set_rng_state.  One CTA; device pointers. */
+TEXIR_API int texir_mt19937_uniform(const uint32_t* state_in, int left, int next, int64_t n, float* out,
+                                    uint32_t* state_out, void* stream);
+
 /* ---- peer memory of the multi-GPU path: one process per GPU; a rank exports a device buffer as a 64-byte
  *      handle (CUDA IPC), the other ranks map it over NVLink / NVSwitch and kernels store into it directly.
  * texir_peer_alloc: zeroed buffer on `device` + its handle (handle_out: TEXIR_PEER_HANDLE_BYTES, HOST memory);

@@ -160,3 +160,34 @@ def test_conf_driven_tracer_runs_from_textures(tx, cuda_device, tmp_path):
     torch.manual_seed(5)
     want = ref.forward(t.position_texture, t.normal_texture, t.index_texture)
     assert torch.equal(out, want) and t.scene.texture_key()[0] == "rgbe"
+
+
+def test_device_shift_stream_is_torch_rand(tx, cuda_device):
+    """draw_shift for a cube map's 98 304 pixels runs the CPU generator's mt19937 stream on the device
+    (texir_mt19937_uniform): the values AND the state the host generator is left in must be those of
+    torch.rand(b, 1, 2) -- from a fresh seed, from mid-block, and across consecutive draws of different sizes"""
+    from texir_code_b200 import sample_util
+    assert sample_util.MT_MIN_DRAWS <= 2 * 98304
+    for seed in (666, 12345):
+        torch.manual_seed(seed)
+        torch.rand(333)                                              # not on a block boundary
+        st = torch.get_rng_state()
+        want = [torch.rand(98304, 1, 2), torch.rand(7, 1, 2), torch.rand(98304, 1, 2), torch.rand(49152, 1, 2)]
+        end = torch.get_rng_state()
+        torch.set_rng_state(st)
+        n0 = tx.launch_count()
+        got = [sample_util.draw_shift(98304, cuda_device), sample_util.draw_shift(7, cuda_device),
+               sample_util.draw_shift(98304, cuda_device), sample_util.draw_shift(49152, cuda_device)]
+        assert tx.launch_count() - n0 == 3 and sample_util._mt_ok is True   # three device draws, the 7-pixel one on the host
+        for g, w in zip(got, want):
+            assert g.shape == w.shape and torch.equal(g.cpu(), w)
+        assert torch.equal(torch.get_rng_state(), end)
+    # the model's step draws through it: same colours as with the host draw
+    os.environ["TEXIR_SHIFT_DEVICE"] = "0"
+    try:
+        torch.manual_seed(5)
+        a = sample_util.draw_shift(98304, cuda_device)
+    finally:
+        del os.environ["TEXIR_SHIFT_DEVICE"]
+    torch.manual_seed(5)
+    assert torch.equal(sample_util.draw_shift(98304, cuda_device), a)

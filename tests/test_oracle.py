@@ -224,3 +224,28 @@ def test_closest_hit_oracle_vs_float64_geometry(oracle):
     miss = ids == 0xFFFFFFFF
     assert np.array_equal(miss[~near_edge], ~hit64[~near_edge])
     assert np.all(np.isinf(t[miss])) and np.all(bary[miss] == 0)
+
+
+def test_mt19937_restatement_is_torch_rand():
+    """oracle/mt19937_oracle.py (the checker of the device-side shift generator) against torch itself: values of
+    torch.rand and the generator state it ends in, from block boundaries and from mid-block, chained"""
+    import torch
+    import mt19937_oracle as mt
+    for seed in (666, 1, 2 ** 40 + 7):
+        torch.manual_seed(seed)
+        st = torch.get_rng_state()
+        words, left, nxt = mt.parse_state(st.numpy())
+        assert words.shape == (624,) and left == 1 and nxt == 0
+        for n in (1, 623, 624, 625, 5000, 196608):
+            torch.set_rng_state(st)
+            ref = torch.rand(n).numpy()
+            got, w2, l2, n2 = mt.rand_float32(words, left, nxt, n)
+            assert np.array_equal(ref, got)
+            assert np.array_equal(mt.store_state(st.numpy(), w2, l2, n2), torch.get_rng_state().numpy())
+        torch.set_rng_state(st)
+        torch.rand(777)
+        mid = torch.get_rng_state()
+        ref = torch.rand(98304, 1, 2).numpy().reshape(-1)
+        w, l, x = mt.parse_state(mid.numpy())
+        got, w2, l2, n2 = mt.rand_float32(w, l, x, 2 * 98304)
+        assert np.array_equal(ref, got) and np.array_equal(mt.store_state(mid.numpy(), w2, l2, n2), torch.get_rng_state().numpy())

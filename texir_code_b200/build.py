@@ -21,7 +21,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 SO = os.path.join(HERE, "libtexir_b200.so")
 SOURCES = [os.path.join(CSRC, f) for f in (
-    "texir_kernels.cu", "texir_post.cu", "texir_texture.cu", "texir_matstage.cu", "texir_peer.cu", "texir_wide.cu",
+    "texir_kernels.cu", "texir_post.cu", "texir_texture.cu", "texir_matstage.cu", "texir_peer.cu", "texir_rng.cu",
     "bvh_build_gpu.cu", "bvh_build.cpp")]
 HEADERS = [os.path.join(CSRC, h) for h in (
     "texir_math.h", "texir_bvh.h", "texir_walk.h", "texir_point.h", "texir_post.h", "texir_tex.h", "texir_host.h",

@@ -12,6 +12,7 @@ generator reproduces the reference's sample set.
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import numpy as np
@@ -57,17 +58,14 @@ def generate_fixed_samples(b: int, num_sample_dir: int) -> torch.Tensor:
 
 
 _shift_ring = {}   # (b, device index) -> [next slot, [(pinned buffer, copy-done event) ...]]
+_MT_N, _OFF_LEFT, _OFF_NEXT, _OFF_STATE = 624, 8, 16, 24   # layout of torch.get_rng_state() (CPUGeneratorImplStateLegacy)
+_mt_dev = {}       # device index -> dict(stream, pinned in/out, device in/out) of the device-side generator path
+_mt_ok = None      # None: not checked yet; True / False: the device stream reproduced torch.rand in this process
+MT_MIN_DRAWS = 1 << 15   # below this many numbers the host draws them faster than a kernel round trip
 
 
-def draw_shift(b: int, device) -> torch.Tensor:
-    """the reference's ``shift = torch.rand(b, 1, 2).cuda()`` (utils/sample_util.py:102): the same draw from the CPU
-    default generator, then moved.  The draw lands in a pinned staging buffer and the copy is asynchronous: a pageable
-    ``.cuda()`` would make the host wait for everything queued on the stream first, once per generate_dir call.  Three
-    staging buffers per size rotate; one is reused only after the copy that read it has finished."""
-    dev = torch.device(device)
-    if dev.type != "cuda":
-        return torch.rand(b, 1, 2).to(dev)
-    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+def _draw_cpu(b: int, dev: torch.device, idx: int) -> torch.Tensor:
+    """torch.rand(b, 1, 2) into a pinned staging buffer, asynchronous copy (three buffers per size rotate)"""
     ring = _shift_ring.get((b, idx))
     if ring is None:
         if len(_shift_ring) > 16:
@@ -85,6 +83,79 @@ def draw_shift(b: int, device) -> torch.Tensor:
         ev.record(torch.cuda.current_stream(idx))
     ring[1][slot] = (buf, ev)
     return out
+
+
+def _draw_mt_device(n: int, dev: torch.device, idx: int, state: Optional[torch.Tensor] = None, commit: bool = True):
+    """n values of torch.rand (CPU default generator, or the generator state `state`) produced ON THE DEVICE by
+    texir_mt19937_uniform from the generator's own mt19937 state, and the host generator advanced to where torch.rand
+    would have left it (commit).  -> (float32 [n] on dev, new state tensor)"""
+    st = torch.get_rng_state() if state is None else state.clone()
+    a = st.numpy()
+    left = int(a[_OFF_LEFT:_OFF_LEFT + 4].view(np.int32)[0])
+    nxt = int(a[_OFF_NEXT:_OFF_NEXT + 8].view(np.uint64)[0])
+    ctx = _mt_dev.get(idx)
+    if ctx is None:
+        with torch.cuda.device(idx):
+            ctx = _mt_dev[idx] = {
+                "stream": torch.cuda.Stream(device=idx, priority=-1),   # not behind the work queued on the caller's stream
+                "h_in": torch.empty(_MT_N, dtype=torch.int32).pin_memory(), "h_out": torch.empty(_MT_N + 2, dtype=torch.int32).pin_memory(),
+                "d_in": torch.empty(_MT_N, dtype=torch.int32, device=dev), "d_out": torch.empty(_MT_N + 2, dtype=torch.int32, device=dev)}
+    ctx["h_in"].numpy().view(np.uint32)[:] = a[_OFF_STATE:_OFF_STATE + 8 * _MT_N].view(np.uint64).astype(np.uint32)
+    main = torch.cuda.current_stream(idx)
+    with torch.cuda.device(idx), torch.cuda.stream(ctx["stream"]):
+        out = torch.empty(n, dtype=torch.float32, device=dev)
+        ctx["d_in"].copy_(ctx["h_in"], non_blocking=True)
+        _lib.check(_lib.load().texir_mt19937_uniform(_ptr(ctx["d_in"]), left, nxt, n, _ptr(out), _ptr(ctx["d_out"]),
+                                                     _stream_ptr(dev)), "texir_mt19937_uniform")
+        ctx["h_out"].copy_(ctx["d_out"], non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(ctx["stream"])
+    done.synchronize()                     # about one kernel (0.1 ms): the generator state comes back to the host
+    w = ctx["h_out"].numpy().view(np.uint32)
+    a[_OFF_STATE:_OFF_STATE + 8 * _MT_N] = w[:_MT_N].astype(np.uint64).view(np.uint8)
+    a[_OFF_LEFT:_OFF_LEFT + 4] = np.array([int(w[_MT_N])], np.int32).view(np.uint8)
+    a[_OFF_NEXT:_OFF_NEXT + 8] = np.array([int(w[_MT_N + 1])], np.uint64).view(np.uint8)
+    if commit:
+        torch.set_rng_state(st)
+    main.wait_event(done)
+    out.record_stream(main)
+    return out, st
+
+
+def _mt_device_selfcheck(dev: torch.device, idx: int) -> bool:
+    """once per process: the device stream against torch.rand itself, on a copy of the current generator state (values and
+    the state torch ends in), from mid-block; a torch build that lays its generator out differently simply keeps the host draw"""
+    try:
+        st = torch.get_rng_state()
+        g = torch.Generator()
+        g.set_state(st)
+        torch.rand(1000, generator=g)                      # move off the block boundary
+        mid = g.get_state()
+        ref = torch.rand(5000, generator=g)
+        got, st2 = _draw_mt_device(5000, dev, idx, state=mid, commit=False)
+        return bool(torch.equal(got.cpu(), ref)) and bool(torch.equal(st2, g.get_state()))
+    except Exception:
+        return False
+
+
+def draw_shift(b: int, device) -> torch.Tensor:
+    """the reference's ``shift = torch.rand(b, 1, 2).cuda()`` (utils/sample_util.py:102): the same numbers from the same
+    CPU default generator, which ends in the same state.  Small draws run torch.rand on the host into a pinned staging
+    buffer with an asynchronous copy (a pageable ``.cuda()`` makes the host wait for everything queued on the stream);
+    large ones (the 98 304-pixel cube map of a Mat-stage step: 0.3 ... 0.7 ms of serial mt19937 on the host) regenerate
+    the generator's stream on the device (texir_mt19937_uniform) and hand the advanced state back to torch.
+    TEXIR_SHIFT_DEVICE=0 keeps everything on the host."""
+    global _mt_ok
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        return torch.rand(b, 1, 2).to(dev)
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    if 2 * b >= MT_MIN_DRAWS and _mt_ok is not False and os.environ.get("TEXIR_SHIFT_DEVICE", "1") != "0":
+        if _mt_ok is None:
+            _mt_ok = _mt_device_selfcheck(dev, idx)
+        if _mt_ok:
+            return _draw_mt_device(2 * b, dev, idx)[0].view(b, 1, 2)
+    return _draw_cpu(b, dev, idx)
 
 
 class _GenerateDir(torch.autograd.Function):
