@@ -68,6 +68,16 @@ def ncu_traffic(key: str):
         return None
 
 
+def issue_frac(rate: float, key: str, clocks) -> dict:
+    """instruction-issue yardstick next to the HBM one: warp instructions per ray-sample from the
+    committed ncu capture x measured rate, against 148 SMs x 4 schedulers x the SM clock sampled during the run"""
+    inst = ncu_traffic(key)
+    mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    slots = 148 * 4 * mhz * 1e6
+    return {"issue_frac": None if inst is None else rate * inst / slots, "warp_inst_per_ray_sample": inst,
+            "issue_slots_per_s": slots}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)"""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -419,6 +429,7 @@ def run_ours(args):
                          "traffic": None if tr is None else tr * rays_per_launch, "peak_source": peak_src,
                          "kernel": "k_irradiance_lean<4,FRONT> (QBVH2, shared first descent)" if info["bvh_kind"] == 2 else "k_irradiance<8>",
                          "kernel_ms": k_ms, "alg_bytes_per_ray_sample": balg, "ray_samples_per_launch": rays_per_launch,
+                         **issue_frac(rays_per_launch / (k_ms * 1e-3), "warp_inst_per_ray_sample", clocks),
                          "issue_frac_note": "see DESIGN.md section 3: the kernel is bound by instruction issue, not by HBM"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / args.steps, "checksum": checksum},
@@ -511,7 +522,8 @@ def bench_material_stage(scene, sc, dev, args, texture, timer):
         leg = {"ms": ms, "ray_samples_per_s": rate, "spp": N,
                "roofline": {"bound": "hbm", "achieved": rate * casts * balg / 1e9, "peak": peak, "unit": "GB/s",
                             "frac": rate * casts * balg / 1e9 / peak, "alg_bytes_per_ray_sample": casts * balg,
-                            "traffic": ncu_traffic("shade_%s_dram_bytes_per_ray_sample" % mode)},
+                            "traffic": ncu_traffic("shade_%s_dram_bytes_per_ray_sample" % mode),
+                            **issue_frac(rate, "shade_%s_warp_inst_per_ray_sample" % mode, clocks)},
                "clocks": clocks}
         out["fwd_bwd_%s_%dspp" % (mode, N)] = leg
 

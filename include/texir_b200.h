@@ -350,6 +350,10 @@ TEXIR_API int texir_rgbe_decode(const uint8_t* rgbe, int64_t n, int bgr, float* 
 TEXIR_API int texir_hdr_write_host(const char* path, const uint8_t* rgbe_host /*[H,W,4]*/, int H, int W);
 TEXIR_API int texir_hdr_read_info(const char* path, int* H, int* W);
 TEXIR_API int texir_hdr_read_host(const char* path, uint8_t* rgbe_host /*[H,W,4]*/, int H, int W);
+/* the 16-bit PNG index texture (tools/padding_texture.py:8-43 reads and writes it through cv2): undo the PNG scanline
+ * filters of an inflated, non-interlaced IDAT stream.  filtered = H rows of 1 + row_bytes bytes, out = H rows of
+ * row_bytes, bpp = bytes per pixel.  HOST memory only; chunk parsing and zlib stay with the caller. */
+TEXIR_API int texir_png_unfilter_host(const uint8_t* filtered, int H, int row_bytes, int bpp, uint8_t* out);
 
 #ifdef __cplusplus
 }

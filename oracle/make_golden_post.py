@@ -10,6 +10,11 @@ scipy, numpy and torch, all present in the build container) and cv2's own .hdr c
         hdr_out    bytes of the file the reference's padding_texture() wrote ('t.hdr')
         img_out    cv2.imread(hdr_out, -1)
 
+    tests/golden/post_index.npz     the 16-bit PNG index texture through the tool's padding_index_texture (:8-43)
+        png_in     bytes of cv2.imwrite('idx.png', uint16 [H,W,3])
+        img_in     cv2.imread(png_in, -1)
+        img_out    cv2.imread of the 'idx_padding.png' the reference's tool wrote
+
 The external `oidnDenoise` command the tool shells out to afterwards does not exist here; os.system just reports
 that and the padded file is already on disk.
 
@@ -68,6 +73,22 @@ def main():
                             indices=indices.astype(np.int32), hdr_out=hdr_out, img_out=img_out)
         print("wrote post_%s.npz: %dx%d, %d empty texels, hdr %d -> %d bytes" % (tag, H, W, int(mask.sum()), len(hdr_in),
                                                                                len(hdr_out)))
+    # the index texture (view id, pixel column, pixel row of the panorama a texel was seen in), 16-bit PNG
+    rng = np.random.default_rng(7)
+    H, W = 72, 56
+    valid = island_texture(H, W, 4)[:, :, 0] > 0
+    idx = np.stack([rng.integers(1, 40, (H, W)), rng.integers(0, 65536, (H, W)), rng.integers(0, 65536, (H, W))], -1).astype(np.uint16)
+    idx[~valid] = 0
+    with tempfile.TemporaryDirectory() as tmp:
+        src = os.path.join(tmp, "idx.png")
+        cv2.imwrite(src, idx)
+        png_in = np.frombuffer(open(src, "rb").read(), np.uint8)
+        img_in = cv2.imread(src, -1)
+        ref_tool.padding_index_texture(src)
+        img_out = cv2.imread(os.path.join(tmp, "idx_padding.png"), -1)
+    assert img_in.dtype == np.uint16 and img_out.dtype == np.uint16 and np.array_equal(img_in, idx)
+    np.savez_compressed(os.path.join(OUT, "post_index.npz"), png_in=png_in, img_in=img_in, img_out=img_out)
+    print("wrote post_index.npz: %dx%d, %d empty texels, png %d bytes" % (H, W, int((~valid).sum()), len(png_in)))
 
 
 if __name__ == "__main__":

@@ -127,3 +127,28 @@ def test_pad_texture_rejects_cpu_tensors(pp):
     import texir_code_b200 as tx
     with pytest.raises(tx.TexirError):
         pp.pad_texture(torch.zeros(4, 4, 3))
+
+
+def test_padding_index_texture_tool(pp, cuda_device, tmp_path):
+    """tools/padding_texture.py:8-43: 16-bit PNG in -> pad -> '<name>_padding.png', the pixels the reference's tool wrote;
+    a fourth channel stays out of the mask and is sampled like the others"""
+    g = load_golden("post_index")
+    src = tmp_path / "idx.png"
+    src.write_bytes(g["png_in"].tobytes())
+    dst = pp.padding_index_texture(str(src), device=cuda_device)
+    assert dst == str(tmp_path / "idx_padding.png")
+    out = pp.imread_png(dst)
+    assert out.dtype == np.uint16 and np.array_equal(out, g["img_out"])
+    rng = np.random.default_rng(2)
+    alpha = rng.integers(0, 65536, g["img_in"].shape[:2]).astype(np.uint16)
+    four = np.concatenate([g["img_in"], alpha[:, :, None]], -1)
+    src4 = tmp_path / "four.png"
+    pp.imwrite_png(str(src4), four)
+    out4 = pp.imread_png(pp.padding_index_texture(str(src4), device=cuda_device))
+    assert np.array_equal(out4[:, :, :3], g["img_out"])
+    empty = g["img_in"].astype(np.int64).sum(-1) == 0
+    assert np.array_equal(out4[~empty, 3], alpha[~empty])
+    # the fourth channel of a padded texel comes from the texel its colour came from (colours here are unique enough)
+    key = {tuple(c): a for c, a in zip(g["img_in"][~empty].tolist(), alpha[~empty].tolist())}
+    picked = out4[empty]
+    assert all(key[tuple(p[:3])] == p[3] for p in picked.tolist() if tuple(p[:3]) != (0, 0, 0))

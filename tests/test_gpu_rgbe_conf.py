@@ -168,6 +168,9 @@ def test_device_shift_stream_is_torch_rand(tx, cuda_device):
     torch.rand(b, 1, 2) -- from a fresh seed, from mid-block, and across consecutive draws of different sizes"""
     from texir_code_b200 import sample_util
     assert sample_util.MT_MIN_DRAWS <= 2 * 98304
+    keep = torch.get_rng_state()
+    sample_util.draw_shift(98304, cuda_device)                       # first use runs the one-time self-check (one extra launch)
+    torch.set_rng_state(keep)
     for seed in (666, 12345):
         torch.manual_seed(seed)
         torch.rand(333)                                              # not on a block boundary

@@ -159,3 +159,50 @@ def test_hdr_container_rejects_bad_files(lib, tmp_path):
     assert lib.texir_hdr_read_host(os.fsencode(str(trunc)), buf.ctypes.data, 4, 8) != 0  # size mismatch
     assert lib.texir_pad_texture(None, 4, 4, 3, None, None, None, None) != 0              # validation, no GPU touched
     assert lib.texir_pad_texture(None, 4, 4, 5, None, None, None, None) != 0
+
+
+def test_index_texture_padding_vs_reference_tool(emul, oracle):
+    """tools/padding_texture.py:8-43 (16-bit PNG index texture): oracle and device header against what the tool wrote"""
+    g = load_golden("post_index")
+    img = g["img_in"].astype(np.float32)
+    res, _ = oracle.padding_texture_array(img)
+    assert np.array_equal(res.astype(np.uint16), g["img_out"])
+    out, _ = _emul_pad(emul, img)
+    assert np.array_equal(out.astype(np.uint16), g["img_out"])
+
+
+def test_png_codec_reads_cv2_files_and_cv2_reads_ours(lib, tmp_path):
+    """imread_png / imwrite_png (chunks + zlib in Python, scanline filters in the library) against cv2's PNG codec:
+    the committed 16-bit file of the golden, then every supported layout, smooth images (cv2 picks Sub / Up / Average /
+    Paeth filters on them) and noise"""
+    from texir_code_b200 import postprocess as pp
+    g = load_golden("post_index")
+    src = tmp_path / "idx.png"
+    src.write_bytes(g["png_in"].tobytes())
+    got = pp.imread_png(str(src))
+    assert got.dtype == np.uint16 and np.array_equal(got, g["img_in"])
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(11)
+    yy, xx = np.mgrid[0:37, 0:53]
+    for dtype, top in ((np.uint8, 255), (np.uint16, 65535)):
+        for C in (1, 3, 4):
+            smooth = ((yy * 3 + xx * 5)[:, :, None] * (np.arange(C) + 1) * (top // 600 + 1) % (top + 1)).astype(dtype)
+            noise = rng.integers(0, top + 1, (37, 53, C)).astype(dtype)
+            for img in (smooth, noise):
+                img = img[:, :, 0] if C == 1 else img
+                a, b = str(tmp_path / "a.png"), str(tmp_path / "b.png")
+                cv2.imwrite(a, img)
+                assert np.array_equal(pp.imread_png(a), cv2.imread(a, -1))
+                pp.imwrite_png(b, img)
+                back = cv2.imread(b, -1)
+                assert back.dtype == img.dtype and np.array_equal(back, img)
+                assert np.array_equal(pp.imread_png(b), img)
+    bad = tmp_path / "bad.png"
+    bad.write_bytes(b"not a png at all")
+    from texir_code_b200._lib import TexirError
+    with pytest.raises(TexirError):
+        pp.imread_png(str(bad))
+    raw = np.zeros((2, 1 + 6), np.uint8)
+    raw[1, 0] = 9                                                     # no such filter type
+    out = np.zeros((2, 6), np.uint8)
+    assert lib.texir_png_unfilter_host(raw.ctypes.data, 2, 6, 6, out.ctypes.data) != 0

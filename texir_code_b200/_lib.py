@@ -97,6 +97,7 @@ SIGNATURES = {
     "texir_hdr_write_host": (c_int, [c_char_p, _P, c_int, c_int]),
     "texir_hdr_read_info": (c_int, [c_char_p, POINTER(c_int), POINTER(c_int)]),
     "texir_hdr_read_host": (c_int, [c_char_p, _P, c_int, c_int]),
+    "texir_png_unfilter_host": (c_int, [_P, c_int, c_int, c_int, _P]),
 }
 
 _lib = None

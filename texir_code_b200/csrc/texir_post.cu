@@ -12,6 +12,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <thread>
@@ -375,6 +376,42 @@ int texir_hdr_read_host(const char* path, uint8_t* rgbe_host, int H, int W) {
         }
         for (int x = 0; x < W; ++x)
             for (int c = 0; c < 4; ++c) row[4 * x + c] = plane[(size_t)c * W + x];
+    }
+    return 0;
+}
+
+// PNG scanline filters (PNG 1.2 section 6: None / Sub / Up / Average / Paeth), undone in place row by row.
+// `filtered` holds H rows of 1 + row_bytes bytes (the inflated IDAT stream of a non-interlaced image), `out` H rows of
+// row_bytes; bpp = bytes per complete pixel (6 for the 16-bit RGB index texture).  Host memory only.
+int texir_png_unfilter_host(const uint8_t* filtered, int H, int row_bytes, int bpp, uint8_t* out) {
+    if (!filtered || !out || H <= 0 || row_bytes <= 0 || bpp <= 0 || bpp > 8) return fail("texir_png_unfilter_host: bad argument");
+    std::vector<uint8_t> zero((size_t)row_bytes, 0);
+    for (int y = 0; y < H; ++y) {
+        const uint8_t* src = filtered + (size_t)y * (row_bytes + 1);
+        const int type = src[0];
+        ++src;
+        uint8_t* cur = out + (size_t)y * row_bytes;
+        const uint8_t* up = y ? cur - row_bytes : zero.data();
+        switch (type) {
+        case 0: memcpy(cur, src, (size_t)row_bytes); break;
+        case 1:
+            for (int i = 0; i < row_bytes; ++i) cur[i] = (uint8_t)(src[i] + (i >= bpp ? cur[i - bpp] : 0));
+            break;
+        case 2:
+            for (int i = 0; i < row_bytes; ++i) cur[i] = (uint8_t)(src[i] + up[i]);
+            break;
+        case 3:
+            for (int i = 0; i < row_bytes; ++i) cur[i] = (uint8_t)(src[i] + (((i >= bpp ? cur[i - bpp] : 0) + up[i]) >> 1));
+            break;
+        case 4:
+            for (int i = 0; i < row_bytes; ++i) {
+                const int a = i >= bpp ? cur[i - bpp] : 0, b = up[i], c = i >= bpp ? up[i - bpp] : 0;
+                const int pa = abs(b - c), pb = abs(a - c), pc = abs(a + b - 2 * c);
+                cur[i] = (uint8_t)(src[i] + (pa <= pb && pa <= pc ? a : pb <= pc ? b : c));
+            }
+            break;
+        default: return fail("texir_png_unfilter_host: unknown filter type in scanline");
+        }
     }
     return 0;
 }

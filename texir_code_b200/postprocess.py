@@ -7,6 +7,9 @@
                          models/mat_nvdiffrast.py:73,89): RGBE pixel codec on the device, run-length container in
                          host C++ (libtexir_b200.so), byte-identical to OpenCV's files
     save_irr_texture     trainer/generate_ir_texture.py:80-82
+    padding_index_texture    tools/padding_texture.py:8-43: the same padding for the 16-bit PNG index texture
+    imread_png / imwrite_png  cv2.imread(path, -1) / cv2.imwrite for 8/16-bit PNG (chunks + zlib here, scanline filters
+                         in libtexir_b200.so); channel order as cv2 returns it (BGR / BGRA)
 
 No cv2 / scipy is imported here and nothing falls back to them.
 """
@@ -14,7 +17,11 @@ from __future__ import annotations
 
 import ctypes
 import os
+import struct
+import zlib
 from typing import Callable, Optional
+
+import numpy as np
 
 import torch
 
@@ -121,4 +128,97 @@ def padding_texture(path: str, denoise: Optional[Callable[[str, str], None]] = N
     imwrite_hdr(dst, padded)
     if denoise is not None:
         denoise(dst, path.replace("0_irr_texture", "0_irr_texture_denoised_padding"))
+    return dst
+
+
+_PNG_SIG = b"\x89PNG\r\n\x1a\n"
+_PNG_CHANNELS = {0: 1, 2: 3, 4: 2, 6: 4}     # colour type -> samples per pixel (palette images are not index textures)
+
+
+def imread_png(path: str) -> np.ndarray:
+    """cv2.imread(path, -1) for a non-interlaced 8- or 16-bit grey / RGB / RGBA PNG: uint8 / uint16 [H,W] or [H,W,C]
+    with cv2's channel order (BGR, BGRA)."""
+    data = open(path, "rb").read()
+    if data[:8] != _PNG_SIG:
+        raise _lib.TexirError("imread_png: %s is not a PNG file" % path)
+    pos, idat, head = 8, [], None
+    while pos + 8 <= len(data):
+        n, kind = struct.unpack(">I4s", data[pos:pos + 8])
+        body = data[pos + 8:pos + 8 + n]
+        if len(body) != n:
+            raise _lib.TexirError("imread_png: truncated chunk in %s" % path)
+        if kind == b"IHDR":
+            head = struct.unpack(">IIBBBBB", body)
+        elif kind == b"IDAT":
+            idat.append(body)
+        elif kind == b"IEND":
+            break
+        pos += 12 + n
+    if head is None or not idat:
+        raise _lib.TexirError("imread_png: %s has no IHDR / IDAT" % path)
+    W, H, depth, ctype, _, _, interlace = head
+    if depth not in (8, 16) or ctype not in _PNG_CHANNELS or interlace != 0:
+        raise _lib.TexirError("imread_png: unsupported PNG (bit depth %d, colour type %d, interlace %d)" % (depth, ctype, interlace))
+    C = _PNG_CHANNELS[ctype]
+    bpp = C * depth // 8
+    raw = np.frombuffer(zlib.decompress(b"".join(idat)), np.uint8)
+    if raw.size != H * (1 + W * bpp):
+        raise _lib.TexirError("imread_png: %s: IDAT holds %d bytes, expected %d" % (path, raw.size, H * (1 + W * bpp)))
+    out = np.empty((H, W * bpp), np.uint8)
+    _lib.check(_lib.load().texir_png_unfilter_host(raw.ctypes.data, H, W * bpp, bpp, out.ctypes.data), "texir_png_unfilter_host")
+    img = out.view(">u2").astype(np.uint16) if depth == 16 else out
+    img = img.reshape(H, W, C)
+    if C >= 3:
+        img = img[:, :, [2, 1, 0] + ([3] if C == 4 else [])]
+    return np.ascontiguousarray(img[:, :, 0] if C == 1 else img)
+
+
+def imwrite_png(path: str, img: np.ndarray) -> None:
+    """cv2.imwrite(path, img) for uint8 / uint16 [H,W], [H,W,3] (BGR) or [H,W,4] (BGRA): the same pixels in the file
+    (the compressed bytes differ from OpenCV's: filter type 0 on every scanline)"""
+    a = np.asarray(img)
+    if a.dtype not in (np.uint8, np.uint16) or a.ndim not in (2, 3) or (a.ndim == 3 and a.shape[2] not in (1, 3, 4)):
+        raise ValueError("imwrite_png expects uint8 / uint16 [H,W], [H,W,3] or [H,W,4]")
+    if a.ndim == 2:
+        a = a[:, :, None]
+    H, W, C = a.shape
+    if C >= 3:
+        a = a[:, :, [2, 1, 0] + ([3] if C == 4 else [])]
+    depth = 16 if a.dtype == np.uint16 else 8
+    rows = np.ascontiguousarray(a.astype(">u2") if depth == 16 else a).view(np.uint8).reshape(H, -1)
+    body = np.concatenate([np.zeros((H, 1), np.uint8), rows], axis=1).tobytes()
+
+    def chunk(kind, payload):
+        return struct.pack(">I", len(payload)) + kind + payload + struct.pack(">I", zlib.crc32(kind + payload) & 0xFFFFFFFF)
+
+    ctype = {1: 0, 3: 2, 4: 6}[C]
+    with open(path, "wb") as f:
+        f.write(_PNG_SIG + chunk(b"IHDR", struct.pack(">IIBBBBB", W, H, depth, ctype, 0, 0, 0))
+                + chunk(b"IDAT", zlib.compress(body, 1)) + chunk(b"IEND", b""))
+
+
+def padding_index_texture(path: str, device="cuda") -> str:
+    """tools/padding_texture.py:8-43 with the same file naming: reads the 16-bit index texture `path` (….png), gives every
+    empty texel (channel sum 0) the index of its nearest non-empty texel, writes path.replace('.png', '_padding.png')
+    and returns that path.  The indices go through float32 exactly as in the reference (they are < 2^16)."""
+    img = imread_png(path)
+    if img.ndim != 3:
+        raise ValueError("padding_index_texture expects a colour PNG (the reference unpacks h, w, c)")
+    out_dtype = np.uint16                                             # the tool always casts to uint16 (:39)
+    src = torch.from_numpy(img.astype(np.float32)).to(device)
+    if src.shape[2] > 3:
+        # channels beyond the first three do not enter the mask (:12) but are sampled like the others (:36-37): pad an
+        # image of (row + 1, col + 1) with the same mask -- it comes back holding the texel grid_sample picked -- and gather
+        H, W = int(src.shape[0]), int(src.shape[1])
+        full = (src[:, :, 0] + src[:, :, 1] + src[:, :, 2] != 0.0).to(torch.float32)
+        rows = torch.arange(1, H + 1, device=src.device, dtype=torch.float32).view(H, 1).expand(H, W)
+        cols = torch.arange(1, W + 1, device=src.device, dtype=torch.float32).view(1, W).expand(H, W)
+        where = pad_texture(torch.stack([rows * full, cols * full, torch.zeros_like(full)], -1))
+        picked = (where[..., 0] > 0).unsqueeze(-1)                    # grid_sample's zero padding: nothing picked
+        got = src[(where[..., 0].long() - 1).clamp_(min=0), (where[..., 1].long() - 1).clamp_(min=0)] * picked
+        padded = torch.where(full.bool().unsqueeze(-1), src, got)
+    else:
+        padded = pad_texture(src)
+    dst = path.replace(".png", "_padding.png")
+    imwrite_png(dst, padded.cpu().numpy().astype(out_dtype))
     return dst
