@@ -462,13 +462,18 @@ def bench_cold(sc, tex, dev, h_pos, h_nrm, h_shift, h_out, P):
     tr.scene.set_texture(tr.texture)
     torch.cuda.synchronize(dev)
     t1 = time.perf_counter()
-    e = tr.irradiance(h_pos.to(dev, non_blocking=True), h_nrm.to(dev, non_blocking=True), h_shift.to(dev, non_blocking=True))
+    d_in = [h.to(dev, non_blocking=True) for h in (h_pos, h_nrm, h_shift)]
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    ev[0].record()
+    e = tr.irradiance(*d_in)
+    ev[1].record()
     h_out.copy_(e, non_blocking=True)
     torch.cuda.synchronize(dev)
     t2 = time.perf_counter()
     inf = tr.scene.info()
     tr.scene.close()
     return {"total_s": t2 - t0, "scene_create_and_texture_s": t1 - t0, "irt_s": t2 - t1, "scene_create_s": inf["build_seconds"],
+            "irradiance_device_s": ev[0].elapsed_time(ev[1]) * 1e-3,
             "bvh_builder": {1: "host", 2: "device"}.get(inf.get("builder"), "?"),
             "ray_samples_per_s": P * SPP / (t2 - t0), "what": "scene_create + set_texture + H2D + irradiance + D2H, wall clock"}
 

@@ -505,4 +505,16 @@ void emul_cast_rays_front(EmulScene* s, const float* org, const float* dirs, int
     }
 }
 
+// closest hits of R rays through the free-running walk (texir_walk.h, trace_qbvh2_free): the G-buffer kernel's loop
+void emul_cast_rays_free(EmulScene* s, const float* rays, int64_t R, float* t, uint32_t* id, float* uv) {
+    for (int64_t q = 0; q < R; ++q) {
+        const float* r = rays + 6 * q;
+        Hit h = trace_qbvh2_free(s->view, v3(r[0], r[1], r[2]), v3(r[3], r[4], r[5]));
+        t[q] = h.t;
+        id[q] = h.prim;
+        uv[2 * q] = h.u;
+        uv[2 * q + 1] = h.v;
+    }
+}
+
 }  // extern "C"

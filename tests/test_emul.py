@@ -218,3 +218,32 @@ def test_shared_first_descent_bit_exact_vs_plain_walk(emul):
     t1, i1, u1 = np.empty(3, np.float32), np.empty(3, np.uint32), np.empty((3, 2), np.float32)
     emul.emul_cast_rays_front(one.h, p.ctypes.data, d.ctypes.data, 3, t1.ctypes.data, i1.ctypes.data, u1.ctypes.data, None)
     assert i1.tolist() == [0, 0xFFFFFFFF, 0] and t1[0] == 1.0 and np.isinf(t1[1])
+
+
+def test_free_running_walk_bit_exact_vs_plain_walk(emul):
+    """texir_walk.h trace_qbvh2_free (the G-buffer kernel's loop: node step or leaf test per iteration, whichever the ray
+    stands at): same visiting order per ray, so hits must be bit-identical to the while-while walk -- primary rays from
+    inside the room, rays from outside, degenerate directions, and the single-triangle scene"""
+    from texir_code_b200 import synth
+    rng = np.random.default_rng(5)
+    for num_tris, clutter in ((4000, 6), (60000, 16)):
+        sc = synth.make_room_scene(num_tris, seed=666, clutter=clutter)
+        es = EmulScene(emul, sc.vertices, sc.triangles)
+        rays = np.ascontiguousarray(synth.cube_map_rays(24), np.float32)
+        o = rng.uniform(-6, 6, (2000, 3)).astype(np.float32)
+        d = rng.normal(size=(2000, 3)).astype(np.float32)
+        d[:4] = [[0, 0, 0], [1, 0, 0], [0, np.inf, 0], [np.nan, 0, 1]]
+        rays = np.ascontiguousarray(np.concatenate([rays, np.concatenate([o, d], 1)]), np.float32)
+        R = len(rays)
+        t0, i0, u0 = np.empty(R, np.float32), np.empty(R, np.uint32), np.empty((R, 2), np.float32)
+        emul.emul_cast_rays_fast(es.h, 1, rays.ctypes.data, R, t0.ctypes.data, i0.ctypes.data, u0.ctypes.data)
+        t1, i1, u1 = np.empty(R, np.float32), np.empty(R, np.uint32), np.empty((R, 2), np.float32)
+        emul.emul_cast_rays_free(es.h, rays.ctypes.data, R, t1.ctypes.data, i1.ctypes.data, u1.ctypes.data)
+        assert np.array_equal(t0.view(np.uint32), t1.view(np.uint32))
+        assert np.array_equal(i0, i1) and np.array_equal(u0.view(np.uint32), u1.view(np.uint32))
+        assert (i0 != 0xFFFFFFFF).mean() > 0.5
+    one = EmulScene(emul, np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32), np.array([[0, 1, 2]], np.int32))
+    rays = np.ascontiguousarray(np.array([[0.2, 0.2, 1.0, 0, 0, -1], [0.2, 0.2, 1.0, 0, 0, 1]], np.float32))
+    t1, i1, u1 = np.empty(2, np.float32), np.empty(2, np.uint32), np.empty((2, 2), np.float32)
+    emul.emul_cast_rays_free(one.h, rays.ctypes.data, 2, t1.ctypes.data, i1.ctypes.data, u1.ctypes.data)
+    assert i1.tolist() == [0, 0xFFFFFFFF] and t1[0] == 1.0 and np.isinf(t1[1])

@@ -223,6 +223,35 @@ def test_forward_addresses_the_material_textures_like_the_reference(tx, cuda_dev
     assert float((irr[..., 1][hit] - v)[inside].abs().max()) > 0.1
 
 
+def test_model_step_leaves_the_cpu_generator_where_the_reference_does(tx, cuda_device):
+    """cube_res 128 -> the 98 304-pixel shift comes from the device-side mt19937 with a deferred hand-back of the state:
+    after forward() torch's CPU generator must stand where torch.rand(98304, 1, 2) leaves it (utils/sample_util.py:102),
+    and the step must have drawn exactly those numbers (same colours as a step fed by the host draw)"""
+    import os
+    from texir_code_b200 import models, sample_util, synth
+    from test_host_logic import _reference_cube_mvps
+    sc = synth.make_room_scene(4000, seed=3, tex_res=256, clutter=6)
+    mvp, cam = _reference_cube_mvps(np.eye(4, dtype=np.float32))
+    mvp, cam = mvp.to(cuda_device), cam.to(cuda_device)
+    mm = models.MaterialModel(sc.vertices, sc.triangles, sc.triangle_uvs, torch.from_numpy(synth.make_radiance_texture(256)), sample_l=[32, 16],
+                              materials_a_res=128, materials_r_res=256, cube_res=128, irrt=torch.rand(64, 64, 3), device=cuda_device)
+    mm._warned_normals = True
+    torch.manual_seed(41)
+    torch.rand(98304, 1, 2)
+    want_state = torch.get_rng_state()
+    torch.manual_seed(41)
+    a = mm(mvp, 0, cam, 2)["rgb"]
+    assert sample_util._mt_pending is None and sample_util._mt_ok is True
+    assert torch.equal(torch.get_rng_state(), want_state)
+    os.environ["TEXIR_SHIFT_DEVICE"] = "0"
+    try:
+        torch.manual_seed(41)
+        b = mm(mvp, 0, cam, 2)["rgb"]
+    finally:
+        del os.environ["TEXIR_SHIFT_DEVICE"]
+    assert torch.equal(torch.get_rng_state(), want_state) and torch.equal(a, b)
+
+
 def test_sharded_mat_step_sums_to_the_one_gpu_step(tx, cuda_device, scene_golden):
     """two shards run one after the other on one GPU: their colours are the one-GPU colours of their pixels and their
     texture gradients add up to the one-GPU gradient (what the single all-reduce computes)"""

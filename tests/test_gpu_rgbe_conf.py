@@ -185,6 +185,18 @@ def test_device_shift_stream_is_torch_rand(tx, cuda_device):
         for g, w in zip(got, want):
             assert g.shape == w.shape and torch.equal(g.cpu(), w)
         assert torch.equal(torch.get_rng_state(), end)
+    # deferred hand-back (what MaterialModel.forward wraps itself in): same values, the state arrives when the block ends,
+    # and a second draw inside the block starts from the first one's state
+    torch.manual_seed(99)
+    want = [torch.rand(98304, 1, 2), torch.rand(49152, 1, 2)]
+    end = torch.get_rng_state()
+    torch.manual_seed(99)
+    with sample_util.deferred_rng_commit():
+        a = sample_util.draw_shift(98304, cuda_device)
+        assert sample_util._mt_pending is not None
+        b = sample_util.draw_shift(49152, cuda_device)
+    assert sample_util._mt_pending is None and torch.equal(torch.get_rng_state(), end)
+    assert torch.equal(a.cpu(), want[0]) and torch.equal(b.cpu(), want[1])
     # the model's step draws through it: same colours as with the host draw
     os.environ["TEXIR_SHIFT_DEVICE"] = "0"
     try:

@@ -321,10 +321,8 @@ struct GBufferOut {
 };
 
 // one G-buffer pixel from its primary ray: hit point, geometric normal turned against the ray, interpolated UVs
-template <int KIND>
-__device__ __forceinline__ Hit gbuffer_pixel(const SceneView& s, const uint32_t* __restrict__ slot_of_prim, V3 o, V3 d,
-                                             int64_t r, const GBufferOut& g) {
-    Hit h = trace<KIND>(s, o, d);
+__device__ __forceinline__ Hit gbuffer_store(const SceneView& s, const uint32_t* __restrict__ slot_of_prim, V3 o, V3 d,
+                                             int64_t r, const GBufferOut& g, Hit h) {
     const bool hit = h.prim != kInvalidId;
     V3 x = v3(1.f, 0.f, 0.f), n = v3(1.f, 0.f, 0.f);
     float tu = 0.f, tv = 0.f;
@@ -354,6 +352,12 @@ __device__ __forceinline__ Hit gbuffer_pixel(const SceneView& s, const uint32_t*
     if (g.bary) { g.bary[2 * r + 0] = h.u; g.bary[2 * r + 1] = h.v; }
     if (g.mask) g.mask[r] = hit ? 1.0f : 0.0f;
     return h;
+}
+
+template <int KIND>
+__device__ __forceinline__ Hit gbuffer_pixel(const SceneView& s, const uint32_t* __restrict__ slot_of_prim, V3 o, V3 d,
+                                             int64_t r, const GBufferOut& g) {
+    return gbuffer_store(s, slot_of_prim, o, d, r, g, trace<KIND>(s, o, d));
 }
 
 // screen-space UV derivatives of a G-buffer pixel (dr.interpolate(..., rast_db, diff_attrs='all') -> texd,
@@ -415,15 +419,26 @@ __global__ void __launch_bounds__(128) k_gbuffer_uv_da(SceneView s, const float*
 // the view; the CTA inverts that view's 4x4 mvp once (float64 cofactors, shared memory), every thread un-projects its
 // pixel centre to a unit ray direction and its two screen-space differentials, walks the BVH and writes position,
 // normal, texc, texd and mask.  clip = [v,1] @ mvp (row vectors), pixel row 0 at ndc y = -1 (nvdiffrast's layout).
-template <int KIND>
+//
+// FRONT: every primary ray of a view leaves the camera position, so the first descent of the walk (texir_walk.h,
+// "shared first descent") is the same for the whole view: thread 0 of the CTA walks it once while the others invert the
+// mvp, and every pixel starts from the siblings along it.  tile != 0 (unsharded launch, res a multiple of 8): a warp
+// takes an 8 x 4 pixel tile instead of 32 pixels of one row -- neighbouring rays in both directions walk the same nodes.
+// WALK: 0 = the lock-step walk of trace<KIND>, 1 = FRONT, 2 = free-running walk (texir_walk.h, trace_qbvh2_free).
+template <int KIND, int WALK>
 __global__ void __launch_bounds__(128) k_gbuffer_mvp(SceneView s, const float* __restrict__ mvp,
                                                      const float* __restrict__ cam, int res,
                                                      const uint32_t* __restrict__ slot_of_prim, GBufferOut g,
                                                      float* __restrict__ rays_out, int shard_rank, int shard_world,
-                                                     int flip_v) {
+                                                     int flip_v, int tile) {
     __shared__ double inv[16];
     __shared__ int ok;
+    constexpr bool FRONT = WALK == 1;
+    __shared__ uint4 sm_front[FRONT ? kMaxFront : 1];
+    __shared__ int sm_front_n, sm_front_start;
     const int view = blockIdx.y;
+    if (FRONT && threadIdx.x == 32)
+        qbvh2_point_front(s, v3(__ldg(cam + 0), __ldg(cam + 1), __ldg(cam + 2)), sm_front, &sm_front_n, &sm_front_start);
     if (threadIdx.x < 16) {  // cofactor (i, j) -> inverse entry (j, i)
         const float* m = mvp + 16 * view;
         const int i = threadIdx.x >> 2, j = threadIdx.x & 3;
@@ -447,7 +462,11 @@ __global__ void __launch_bounds__(128) k_gbuffer_mvp(SceneView s, const float* _
     __syncthreads();
     // block-cyclic pixel sharding (multi-GPU Mat stage): this rank takes the 128-pixel blocks b = rank (mod world) of
     // every view and stores them compactly, view after view
-    const int pix = (blockIdx.x * shard_world + shard_rank) * blockDim.x + threadIdx.x;
+    int pix = (blockIdx.x * shard_world + shard_rank) * blockDim.x + threadIdx.x;
+    if (tile) {
+        const int w = pix >> 5, lane = pix & 31, tiles_x = res >> 3;
+        pix = ((w / tiles_x) * 4 + (lane >> 3)) * res + (w % tiles_x) * 8 + (lane & 7);
+    }
     if (pix >= res * res) return;
     const int64_t r = shard_world > 1 ? ((int64_t)view * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x
                                       : (int64_t)view * res * res + pix;
@@ -477,7 +496,11 @@ __global__ void __launch_bounds__(128) k_gbuffer_mvp(SceneView s, const float* _
         rays_out[6 * r + 0] = o.x; rays_out[6 * r + 1] = o.y; rays_out[6 * r + 2] = o.z;
         rays_out[6 * r + 3] = d.x; rays_out[6 * r + 4] = d.y; rays_out[6 * r + 5] = d.z;
     }
-    const Hit h = gbuffer_pixel<KIND>(s, slot_of_prim, o, d, r, g);
+    const Hit h = FRONT ? gbuffer_store(s, slot_of_prim, o, d, r, g,
+                                        trace_qbvh2_front(s, o, d, sm_front, ((volatile int*)&sm_front_n)[0],
+                                                          ((volatile int*)&sm_front_start)[0]))
+                  : WALK == 2 ? gbuffer_store(s, slot_of_prim, o, d, r, g, trace_qbvh2_free(s, o, d))
+                              : gbuffer_pixel<KIND>(s, slot_of_prim, o, d, r, g);
     float4 da = make_float4(0.f, 0.f, 0.f, 0.f);
     if (g.uv_da && s.tri_uvs) da = gbuffer_uv_da(s, slot_of_prim, o, d, dd[0], dd[1], h.prim);
     if (flip_v) {
@@ -1914,8 +1937,21 @@ static int gbuffer_mvp_impl(const char* fn, const texir_scene* sc, const float* 
     DeviceGuard guard(sc->info.device);
     GBufferOut g{pos, nrm, uv, prim, bary, mask, uv_da};
     dim3 grid((unsigned)(blocks / shard_world), (unsigned)V);
-    k_gbuffer_mvp<4><<<grid, 128, 0, (cudaStream_t)stream>>>(sc->view, mvp, cam, res, (const uint32_t*)sc->d_slot_of_prim, g,
-                                                             rays_out, shard_rank, shard_world, flip_v);
+    // TEXIR_GB_WALK = 0 lock step / 1 shared first descent from the camera / 2 free-running (default);  TEXIR_GB_TILE=0:
+    // 32 pixels of a row per warp instead of an 8 x 4 tile.  Measured on B200, 6 x 128^2 rays at T = 2^20
+    // (profiles/r02_gbuffer_ab.txt): 154 us lock step (with or without the shared descent or tiles), 137 us free-running,
+    // 132 us free-running on tiles.
+    static const int walk = env_int("TEXIR_GB_WALK", 2);
+    static const bool tile_on = env_int("TEXIR_GB_TILE", 1) != 0;
+    const int tile = tile_on && shard_world == 1 && res % 8 == 0 && ((int64_t)res * res) % 128 == 0;
+    const uint32_t* slots = (const uint32_t*)sc->d_slot_of_prim;
+    const cudaStream_t st = (cudaStream_t)stream;
+    if (walk == 1 && use_front())
+        k_gbuffer_mvp<4, 1><<<grid, 128, 0, st>>>(sc->view, mvp, cam, res, slots, g, rays_out, shard_rank, shard_world, flip_v, tile);
+    else if (walk == 2)
+        k_gbuffer_mvp<4, 2><<<grid, 128, 0, st>>>(sc->view, mvp, cam, res, slots, g, rays_out, shard_rank, shard_world, flip_v, tile);
+    else
+        k_gbuffer_mvp<4, 0><<<grid, 128, 0, st>>>(sc->view, mvp, cam, res, slots, g, rays_out, shard_rank, shard_world, flip_v, tile);
     return finish_launch("k_gbuffer_mvp");
 }
 

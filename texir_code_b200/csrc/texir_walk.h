@@ -359,6 +359,33 @@ TX_HD Hit trace_qbvh2(const SceneView& s, V3 o, V3 d) {
     return hit;
 }
 
+// Free-running walk: every lane takes a node step or a leaf test per iteration, whichever its ray stands at, and no
+// lane waits for the others to reach a leaf.  A round costs both bodies whenever the warp holds both kinds of lanes, so
+// on a kernel that is bound by instruction issue (the IrT, the render) the lock-step while-while loop above is faster;
+// on one that is bound by the LATENCY of its slowest warp (the G-buffer: 0.65 waves, every warp resident from the start)
+// the number of rounds is what counts -- max over the lanes of their own steps, instead of the sum over rounds of the
+// slowest lane (profiles/simulate_gbuffer_warps.py).  Same visiting order per ray, same hits.
+TX_HD Hit trace_qbvh2_free(const SceneView& s, V3 o, V3 d) {
+    RayQ r;
+    rayq_setup(s, r, o, d);
+    Hit hit;
+    hit_reset(hit);
+    int stack[kStackSize];
+    int* sp = stack;
+    *sp++ = kQSentinel;
+    int top = kQSentinel;
+    int node = 0;
+    while (node != kQSentinel) {
+        if (node >= 0) {
+            node = qbvh2_step(s, r, hit.t, node, sp, top);
+        } else {
+            qbvh2_leaf(s, r, node, hit);
+            node = qstack_pop(sp, top);
+        }
+    }
+    return hit;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Shared first descent.  All rays of a surface point start at the same origin, and a near-first walk always
 // descends first into the child whose box CONTAINS the origin (its entry distance is 0): the chain of nodes from the

@@ -20,7 +20,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from . import ops
+from . import ops, sample_util
 from .sample_util import draw_shift, generate_dir
 from .scene import Scene
 
@@ -309,16 +309,25 @@ class MaterialModel(HotPathMixin, nn.Module):
     def forward(self, mvp, id, cam_position, stage=1):
         """mat_nvdiffrast.py:105-191, same arguments and result keys (rgb, albedo, normal, position, empty_mask,
         roughness_womipmap, roughness); stage -1 / 0 / 1 / 2 as in the reference."""
+        # a device-side shift draw hands torch's CPU generator its advanced state when this call returns, not in the
+        # middle of the launches (nothing in here reads that generator in between)
+        with sample_util.deferred_rng_commit():
+            return self._forward(mvp, id, cam_position, stage)
+
+    def _forward(self, mvp, id, cam_position, stage):
         for name in ("materials_a", "materials_r", "irrt"):
             if not hasattr(self, name):
                 raise ValueError("MaterialModel.forward needs %s (constructor: materials_a_res / materials_r_res / irrt)" % name)
         dev = self.scene.device
+        fused = getattr(self, "fused", True) and not getattr(self, "relighting", False)
+        if stage in (1, 2) and fused:
+            # the pyramids of the textures do not depend on the view: build them beside the G-buffer walk (side stream)
+            self.mat_ws.prefetch({"a": self.materials_a, "r": self.materials_r, "i": self.irrt}, self.max_mip_level)
         gb = self.gbuffers(mvp, cam_position, id)       # (keyed on the caller's own tensors when cache_gbuffers is on)
         cam_position = cam_position.to(dev)
         normal, pos, mask = gb["normal"].detach(), gb["position"].detach(), gb["mask"]
         shp = normal.shape[:-1]
         texc, texd = gb["texc"].reshape(-1, 2), gb["texd"].reshape(-1, 4)
-        fused = getattr(self, "fused", True) and not getattr(self, "relighting", False)
         if stage in (1, 2) and fused:
             # fetches, render and the texture-space backward are ONE autograd node (ops.mat_stage)
             albedo = roughness = roughness_womipmap = irr = None

@@ -11,6 +11,7 @@ Each one is a thin torch.autograd.Function over one entry point of libtexir_b200
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -361,6 +362,12 @@ def shade_textured(scene: Scene, materials_a: Optional[torch.Tensor], materials_
 # --------------------------------------------------------------------------------------------------
 # the whole Mat-stage step as ONE autograd node (fetch -> render -> texture-space backward)
 # --------------------------------------------------------------------------------------------------
+# measured on B200 (profiles/r02_gbuffer_ab.txt): 0.859 -> 0.802 ms per 16-spp step once the host no longer waits for
+# the shift kernel (sample_util.deferred_rng_commit); while it did, the extra stream / event calls cost more than the
+# overlap gave back.  TEXIR_MAT_PREFETCH=0 builds the pyramids on the caller's stream.
+_PREFETCH = os.environ.get("TEXIR_MAT_PREFETCH", "1") != "0"
+
+
 class MatWorkspace:
     """Buffers a Mat-stage step re-uses from one optimiser step to the next (one per model and device):
 
@@ -375,10 +382,17 @@ class MatWorkspace:
         self._pyr = {}       # name -> (key, mips, L)
         self._scatter = {}   # name -> (shape key, level-0 buffer, pyramid buffer)
         self.dirty = False   # a backward died between the scatter and the fold: re-zero before the next use
+        self._ahead = {}     # name -> (key, event): pyramids built ahead of the step on the side stream (prefetch)
+        self._side = {}      # device -> side stream
 
     def pyramid(self, name: str, tex: torch.Tensor, max_mip_level: Optional[int]):
         key = (tex.data_ptr(), tex._version, tuple(tex.shape), max_mip_level)
         hit = self._pyr.get(name)
+        ahead = self._ahead.pop(name, None)
+        if ahead is not None:
+            torch.cuda.current_stream(tex.device).wait_event(ahead[1])   # built ahead on the side stream (prefetch)
+            if hit is not None and ahead[0] == key and hit[0] == key:
+                return hit[1], hit[2]
         # a trainable texture is rebuilt on every step (its optimiser updates it in between, possibly through .data,
         # which no version counter sees); a frozen one (the IrT, requires_grad=False) only when it was replaced
         if hit is not None and hit[0] == key and not tex.requires_grad:
@@ -395,6 +409,27 @@ class MatWorkspace:
                        "texir_texture_mip_build_fast")
         self._pyr[name] = (key, mips, L)
         return mips, L
+
+    def prefetch(self, textures: dict, max_mip_level: Optional[int]) -> None:
+        """build the pyramids of `textures` (name -> tensor) NOW, on a side stream, so that they run beside whatever the
+        caller launches next on the current stream -- the G-buffer walk of the same step, which leaves most warp slots of
+        the GPU empty.  The pyramid() call of the step then only waits for the event.  TEXIR_MAT_PREFETCH=0 turns it off."""
+        if not textures or not _PREFETCH:
+            return
+        dev = next(iter(textures.values())).device
+        main = torch.cuda.current_stream(dev)
+        side = self._side.get(dev)
+        if side is None:
+            side = self._side[dev] = torch.cuda.Stream(device=dev)
+        side.wait_stream(main)          # the optimiser's update of the textures is on the current stream
+        with torch.cuda.stream(side):
+            for name, tex in textures.items():
+                self._ahead.pop(name, None)
+                self.pyramid(name, tex, max_mip_level)
+        ev = torch.cuda.Event()
+        ev.record(side)
+        for name, tex in textures.items():
+            self._ahead[name] = ((tex.data_ptr(), tex._version, tuple(tex.shape), max_mip_level), ev)
 
     def scatter_target(self, name: str, shape, L: int, dev):
         H, W, C = shape

@@ -85,10 +85,54 @@ def _draw_cpu(b: int, dev: torch.device, idx: int) -> torch.Tensor:
     return out
 
 
+_mt_pending = None  # (done event, h_out, state tensor, its numpy view): a device draw whose state is not back in torch yet
+_defer_depth = 0    # > 0 inside deferred_rng_commit(): draw_shift leaves the hand-back of the state to the end of the block
+
+
+def finish_pending() -> None:
+    """hand the generator state of a deferred device draw back to torch (waits for that draw's kernel)"""
+    global _mt_pending
+    if _mt_pending is None:
+        return
+    done, h_out, st, a = _mt_pending
+    _mt_pending = None
+    done.synchronize()
+    _mt_store_state(a, h_out)
+    torch.set_rng_state(st)
+
+
+class deferred_rng_commit:
+    """``with deferred_rng_commit():`` -- device draws inside the block do not make the host wait for their kernel; the
+    CPU generator receives its advanced state when the block ends (or at the next draw).  Only for blocks that do not
+    touch torch's CPU generator themselves: MaterialModel.forward wraps its own body in it, so the state is in place
+    before the caller's code runs again."""
+
+    def __enter__(self):
+        global _defer_depth
+        _defer_depth += 1
+        return self
+
+    def __exit__(self, *exc):
+        global _defer_depth
+        _defer_depth -= 1
+        if _defer_depth == 0:
+            finish_pending()
+        return False
+
+
+def _mt_store_state(a, h_out) -> None:
+    w = h_out.numpy().view(np.uint32)
+    a[_OFF_STATE:_OFF_STATE + 8 * _MT_N] = w[:_MT_N].astype(np.uint64).view(np.uint8)
+    a[_OFF_LEFT:_OFF_LEFT + 4] = np.array([int(w[_MT_N])], np.int32).view(np.uint8)
+    a[_OFF_NEXT:_OFF_NEXT + 8] = np.array([int(w[_MT_N + 1])], np.uint64).view(np.uint8)
+
+
 def _draw_mt_device(n: int, dev: torch.device, idx: int, state: Optional[torch.Tensor] = None, commit: bool = True):
     """n values of torch.rand (CPU default generator, or the generator state `state`) produced ON THE DEVICE by
     texir_mt19937_uniform from the generator's own mt19937 state, and the host generator advanced to where torch.rand
     would have left it (commit).  -> (float32 [n] on dev, new state tensor)"""
+    global _mt_pending
+    finish_pending()
     st = torch.get_rng_state() if state is None else state.clone()
     a = st.numpy()
     left = int(a[_OFF_LEFT:_OFF_LEFT + 4].view(np.int32)[0])
@@ -110,15 +154,15 @@ def _draw_mt_device(n: int, dev: torch.device, idx: int, state: Optional[torch.T
         ctx["h_out"].copy_(ctx["d_out"], non_blocking=True)
         done = torch.cuda.Event()
         done.record(ctx["stream"])
-    done.synchronize()                     # about one kernel (0.1 ms): the generator state comes back to the host
-    w = ctx["h_out"].numpy().view(np.uint32)
-    a[_OFF_STATE:_OFF_STATE + 8 * _MT_N] = w[:_MT_N].astype(np.uint64).view(np.uint8)
-    a[_OFF_LEFT:_OFF_LEFT + 4] = np.array([int(w[_MT_N])], np.int32).view(np.uint8)
-    a[_OFF_NEXT:_OFF_NEXT + 8] = np.array([int(w[_MT_N + 1])], np.uint64).view(np.uint8)
-    if commit:
-        torch.set_rng_state(st)
     main.wait_event(done)
     out.record_stream(main)
+    if commit and state is None and _defer_depth > 0:
+        _mt_pending = (done, ctx["h_out"], st, a)   # the caller's block ends with finish_pending()
+        return out, st
+    done.synchronize()                     # about one kernel (0.1 ms): the generator state comes back to the host
+    _mt_store_state(a, ctx["h_out"])
+    if commit:
+        torch.set_rng_state(st)
     return out, st
 
 
@@ -146,6 +190,7 @@ def draw_shift(b: int, device) -> torch.Tensor:
     the generator's stream on the device (texir_mt19937_uniform) and hand the advanced state back to torch.
     TEXIR_SHIFT_DEVICE=0 keeps everything on the host."""
     global _mt_ok
+    finish_pending()
     dev = torch.device(device)
     if dev.type != "cuda":
         return torch.rand(b, 1, 2).to(dev)
