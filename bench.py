@@ -576,7 +576,7 @@ def bench_material_stage(scene, sc, dev, args, texture, timer):
             out[key] = {"ms": ms / reps, "host_ms_per_step": wall, "launches": per_step_launches, "timed_steps": reps,
                         "ray_samples_per_s": P * nspec / (ms / reps * 1e-3)}
             if stage == 2 and nspec == 16:
-                out[key]["breakdown_ms"] = train_step_breakdown(mm, mvp, cam, g_img, dev)
+                out[key]["breakdown"] = train_step_breakdown(train_step, dev)
                 # the same step with the view's G-buffer kept between steps (opt-in: MaterialModel(cache_gbuffers=True),
                 # valid because geometry and cameras are constant during the reference's optimisation)
                 mm.cache_gbuffers = True
@@ -599,29 +599,34 @@ def bench_material_stage(scene, sc, dev, args, texture, timer):
     return out
 
 
-def train_step_breakdown(mm, mvp, cam, g_img, dev):
-    """CUDA-event split of one stage-2 step (median of 15): G-buffer / pyramids+fetch+render (forward) / backward kernel + folds"""
+def train_step_breakdown(step, dev, reps=20):
+    """device time per kernel of one training step, microseconds (torch profiler / CUPTI over `reps` steps); kernels on
+    different streams overlap, so the parts add up to more than the step"""
     import torch
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-    parts = [[], [], []]
-    for _ in range(15):
-        mm.zero_grad(set_to_none=True)
-        torch.cuda.synchronize(dev)
-        ev[0].record()
-        gb = mm.gbuffers(mvp, cam)
-        ev[1].record()
-        normal, pos = gb["normal"].detach(), gb["position"].detach()
-        res, _, _ = mm._render_textured(normal, None, None, None, pos + 1e-2 * normal, cam, None, gb["texc"].reshape(-1, 2),
-                                        gb["texd"].reshape(-1, 4), 2)
-        ev[2].record()
-        res["rgb"].backward(g_img)
-        ev[3].record()
-        torch.cuda.synchronize(dev)
-        for k in range(3):
-            parts[k].append(ev[k].elapsed_time(ev[k + 1]))
-    med = [statistics.median(p) for p in parts]
-    return {"gbuffer": med[0], "pyramids_fetch_render": med[1], "backward_and_folds": med[2],
-            "note": "each part is timed after a device synchronise, so it includes the host time to launch it"}
+    try:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(reps):
+                step()
+            torch.cuda.synchronize(dev)
+        parts = {}
+        for e in prof.key_averages():
+            t = getattr(e, "self_device_time_total", None)
+            if t is None:
+                t = getattr(e, "self_cuda_time_total", 0.0)
+            if t <= 0:
+                continue
+            name = e.key
+            for cut in ("void ", "(anonymous namespace)::", "texir::"):
+                name = name.replace(cut, "")
+            name = name.split("(")[0].strip()
+            parts[name] = parts.get(name, 0.0) + t / reps
+        top = dict(sorted(parts.items(), key=lambda kv: -kv[1])[:14])
+        return {"us_per_step": {k: round(v, 1) for k, v in top.items()}, "sum_us": round(sum(parts.values()), 1),
+                "note": "device time per kernel from the torch profiler (CUPTI), %d steps; the mt19937 shift kernel and "
+                        "the pyramid builds run on side streams beside the G-buffer walk" % reps}
+    except Exception as exc:   # a box without CUPTI access still gets the step time above
+        return {"unavailable": repr(exc)[:200]}
 
 
 def bench_mat_sharded(scene, sc, dev, args, texture, timer, rank, world):
