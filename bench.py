@@ -575,6 +575,19 @@ def bench_material_stage(scene, sc, dev, args, texture, timer):
             key = "train_step_stage%d_%dspp" % (stage, nspec)
             out[key] = {"ms": ms / reps, "host_ms_per_step": wall, "launches": per_step_launches, "timed_steps": reps,
                         "ray_samples_per_s": P * nspec / (ms / reps * 1e-3)}
+            # the same step captured once as a CUDA graph and replayed (texir_code_b200.graphed.GraphedMatStep): one launch
+            # call per step, the shift still drawn from torch's CPU generator stream
+            try:
+                from texir_code_b200.graphed import GraphedMatStep
+                gs = GraphedMatStep(mm, stage, lambda o, gt: (o["rgb"] * gt).sum(), example=(mvp, cam, g_img))
+                w0 = time.perf_counter()
+                ms_g, _ = timer.run(gs.replay, reps, 3)
+                out[key]["ms_graphed"] = ms_g / reps
+                out[key]["host_ms_per_step_graphed"] = (time.perf_counter() - w0) / (reps + 3) * 1e3
+                del gs
+            except Exception as exc:
+                out[key]["ms_graphed"] = None
+                out[key]["graphed_unavailable"] = repr(exc)[:300]
             if stage == 2 and nspec == 16:
                 out[key]["breakdown"] = train_step_breakdown(train_step, dev)
                 # the same step with the view's G-buffer kept between steps (opt-in: MaterialModel(cache_gbuffers=True),
@@ -688,6 +701,22 @@ def bench_mat_sharded(scene, sc, dev, args, texture, timer, rank, world):
         ms, _ = timer.run(step_gather, reps, 3)
         out["stage2_%dspp" % nspec]["ms_per_step_gather_sync"] = ms / reps
         out["stage2_%dspp" % nspec]["gather_bytes"] = 6 * 128 * 128 * 11 * 4
+        # both synchronisations with the rank's whole step (and the collective) captured as ONE CUDA graph
+        try:
+            from texir_code_b200.graphed import GraphedMatStep
+            lf = lambda o, gt: (o["rgb"] * gt).sum()
+            gs = GraphedMatStep(mm, 2, lf, example=(mvp, cam, g_loc))
+            ms, _ = timer.run(gs.replay, reps, 3)
+            out["stage2_%dspp" % nspec]["ms_per_step_graphed_gather_sync"] = ms / reps
+            del gs
+            mm.grad_sync = "allreduce"
+            gs = GraphedMatStep(mm, 2, lf, example=(mvp, cam, g_loc), sync=lambda: parallel.allreduce_gradients(params))
+            ms, _ = timer.run(gs.replay, reps, 3)
+            out["stage2_%dspp" % nspec]["ms_per_step_graphed"] = ms / reps
+            del gs
+        except Exception as exc:
+            out["stage2_%dspp" % nspec]["graphed_unavailable"] = repr(exc)[:300]
+        mm.grad_sync = "gather"
         mm.shift_rng, mm.cache_gbuffers = "device", True      # opt-ins: shift from the CUDA generator, G-buffer kept per view
         torch.cuda.manual_seed(1234)
         step_gather()

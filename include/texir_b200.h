@@ -313,9 +313,14 @@ TEXIR_API int texir_mat_scatter_rows(const float* rows, int64_t P, float* g_tex_
 /* ---- the reference's shift stream on the device: n values of torch.rand (float32, CPU default generator:
  * at::mt19937 + uniform_real_distribution<float>, utils/sample_util.py:102) from the generator state
  * (state_in: the 624 state words; left / next: the engine's counters, all from torch.get_rng_state()), bit for bit, and
- * the advanced state (state_out: 624 words, then left, next) for torch.set_rng_state.  One CTA; device pointers. */
+ * the advanced state (state_out: 624 words, then left, next) for torch.set_rng_state.  One CTA; device pointers.
+ * left == -1: the counters are read from state_in[624], state_in[625] instead (the form a CUDA graph replays: kernel
+ * arguments are frozen at capture); an inconsistent pair yields zeros and state_out[624] = state_out[625] = 0xFFFFFFFF. */
 TEXIR_API int texir_mt19937_uniform(const uint32_t* state_in, int left, int next, int64_t n, float* out,
                                     uint32_t* state_out, void* stream);
+/* the engine bookkeeping of the same n draws on the HOST (no numbers produced): state[624], *left, *next advanced in
+ * place to where torch.rand(n) leaves the generator -- lets the caller hand torch its state without a device round trip. */
+TEXIR_API int texir_mt19937_advance_host(uint32_t* state, int* left, int* next, int64_t n);
 
 /* ---- peer memory of the multi-GPU path: one process per GPU; a rank exports a device buffer as a 64-byte
  *      handle (CUDA IPC), the other ranks map it over NVLink / NVSwitch and kernels store into it directly.

@@ -1,0 +1,5 @@
+set -x
+cd $GRAFT_REPO_ROOT
+python -c "import __graft_entry__ as g; g.build()" > gpurun_out/r02_build.log 2>&1; tail -1 gpurun_out/r02_build.log
+timeout 900 python -m pytest tests/test_gpu_rgbe_conf.py tests/test_gpu_matstage.py -m gpu -q -x -p no:cacheprovider > gpurun_out/r02_gpu_tests19.log 2>&1; tail -3 gpurun_out/r02_gpu_tests19.log | cut -c1-300
+timeout 300 python profiles/r02_train_step_trace.py > gpurun_out/r02_train_trace19.log 2>&1; head -26 gpurun_out/r02_train_trace19.log | cut -c1-75,150-215

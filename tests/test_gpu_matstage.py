@@ -416,3 +416,56 @@ def test_two_ranks_sharded_mat_step_allreduce_and_gather(tx, cuda_device, tmp_pa
         assert p.returncode == 0, o[-3000:]
         line = [l for l in o.splitlines() if l.startswith("RESULT")][-1].split()
         assert line[1:] == [str(r), "True", "True", "True", "True"], o[-3000:]
+
+
+def test_graphed_step_is_the_eager_step(tx, cuda_device):
+    """graphed.GraphedMatStep: zero_grad + forward + loss + backward captured once, replayed with new inputs.  Against the
+    same steps run eagerly from the same seed: the loss bit for bit (the forward is deterministic), the gradients to the
+    rounding of their atomics, and torch's CPU generator in the identical state after every step (the shift stream
+    travels through the graph: sample_util.GraphRng)"""
+    from test_host_logic import _reference_cube_mvps
+    from texir_code_b200 import graphed, models, sample_util, synth
+    sc = synth.make_room_scene(4000, seed=3, tex_res=256, clutter=6)
+    tex = torch.from_numpy(synth.make_radiance_texture(256))
+    rng = np.random.default_rng(0)
+    views = []
+    for k in range(4):
+        c2w = np.eye(4, dtype=np.float32)
+        c2w[:3, 3] = rng.uniform(-0.5, 0.5, 3)
+        mvp, cam = _reference_cube_mvps(c2w)
+        views.append((mvp.to(cuda_device), cam.to(cuda_device), torch.rand(6, 64, 64, 3, device=cuda_device)))
+
+    def make():
+        torch.manual_seed(0)
+        mm = models.MaterialModel(sc.vertices, sc.triangles, sc.triangle_uvs, tex, sample_l=[32, 16], materials_a_res=128,
+                                  materials_r_res=256, cube_res=64, irrt=torch.rand(64, 64, 3) + 0.5, device=cuda_device)
+        mm._warned_normals = True
+        return mm
+
+    loss_fn = lambda out, gt: ((out["rgb"] - gt) ** 2).mean() + 0.1 * out["roughness"].mean()
+    for stage in (2, 1):
+        eager = make()
+        torch.manual_seed(77)
+        ref = []
+        for mvp, cam, gt in views:
+            eager.zero_grad(set_to_none=True)
+            loss = loss_fn(eager(mvp, 0, cam, stage), gt)
+            loss.backward()
+            ref.append((loss.detach().clone(), None if eager.materials_a.grad is None else eager.materials_a.grad.clone(),
+                        eager.materials_r.grad.clone(), torch.get_rng_state()))
+        mm = make()
+        step = graphed.GraphedMatStep(mm, stage, loss_fn, example=views[0])
+        n0 = tx.launch_count()
+        torch.manual_seed(77)
+        for (mvp, cam, gt), (loss_w, ga_w, gr_w, state_w) in zip(views, ref):
+            loss = step(mvp, cam, gt)
+            assert torch.equal(loss, loss_w)
+            sample_util.finish_pending()
+            assert torch.equal(torch.get_rng_state(), state_w)
+            if ga_w is None:
+                assert mm.materials_a.grad is None or float(mm.materials_a.grad.abs().max()) == 0.0
+            else:
+                assert torch.allclose(mm.materials_a.grad, ga_w, rtol=1e-4, atol=1e-9)
+            assert torch.allclose(mm.materials_r.grad, gr_w, rtol=1e-4, atol=1e-9)
+            assert float(gr_w.abs().max()) > 0
+        assert tx.launch_count() == n0          # replays launch nothing from Python: the graph holds the kernels

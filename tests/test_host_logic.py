@@ -315,3 +315,28 @@ def test_draw_shift_is_the_reference_stream_on_any_path():
     b = torch.rand(5, 1, 2)
     torch.manual_seed(11)
     assert torch.equal(draw_shift(7, "cpu"), a) and torch.equal(draw_shift(5, "cpu"), b)
+
+
+def test_mt19937_advance_host_is_where_torch_rand_leaves_the_generator():
+    """texir_mt19937_advance_host (the host half of the graphed shift draw): state, left and next after n draws must be
+    torch's own after torch.rand(n) -- from a fresh seed, mid-block, on block boundaries, for 0 and 196 608 draws"""
+    import ctypes
+    import torch
+    from texir_code_b200 import _lib
+    lib = _lib.load()
+    for seed, pre, n in ((1, 0, 5000), (7, 333, 196608), (9, 623, 1), (3, 624, 625), (4, 100, 3), (5, 0, 0), (6, 1247, 624)):
+        torch.manual_seed(seed)
+        if pre:
+            torch.rand(pre)
+        st = torch.get_rng_state().numpy().copy()
+        state = st[24:24 + 8 * 624].view(np.uint64).astype(np.uint32)
+        left = ctypes.c_int(int(st[8:12].view(np.int32)[0]))
+        nxt = ctypes.c_int(int(st[16:24].view(np.uint64)[0]))
+        if n:
+            torch.rand(n)
+        assert lib.texir_mt19937_advance_host(state.ctypes.data, ctypes.byref(left), ctypes.byref(nxt), n) == 0
+        st2 = torch.get_rng_state().numpy()
+        assert np.array_equal(state, st2[24:24 + 8 * 624].view(np.uint64).astype(np.uint32))
+        assert left.value == int(st2[8:12].view(np.int32)[0]) and nxt.value == int(st2[16:24].view(np.uint64)[0])
+    bad = ctypes.c_int(9999)
+    assert lib.texir_mt19937_advance_host(state.ctypes.data, ctypes.byref(bad), ctypes.byref(nxt), 5) != 0

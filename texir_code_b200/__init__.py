@@ -8,6 +8,7 @@ Public surface (mirrors the reference's names for this path, see DESIGN.md / INT
     models.HotPathMixin / MaterialModel / TracerO3d
     postprocess.pad_texture / padding_texture / imwrite_hdr / imread_hdr / save_irr_texture   (IrT post-processing)
     parallel.shard_bounds / gather_points / allreduce_gradients / sharded_irradiance
+    graphed.GraphedMatStep                      (one Mat-stage optimisation step captured as a CUDA graph)
 
 Everything computes in libtexir_b200.so (hand-written CUDA behind the C ABI of include/texir_b200.h);
 nothing here falls back to the CPU.
@@ -32,8 +33,9 @@ def __getattr__(name):  # lazy: importing the package must not require torch.cud
         "pad_texture": ("postprocess", "pad_texture"), "padding_texture": ("postprocess", "padding_texture"),
         "imwrite_hdr": ("postprocess", "imwrite_hdr"), "imread_hdr": ("postprocess", "imread_hdr"),
         "save_irr_texture": ("postprocess", "save_irr_texture"),
+        "GraphedMatStep": ("graphed", "GraphedMatStep"),
     }
-    if name in ("scene", "sample_util", "ops", "models", "parallel", "synth", "build", "postprocess"):
+    if name in ("scene", "sample_util", "ops", "models", "parallel", "synth", "build", "postprocess", "graphed", "conf_models"):
         return importlib.import_module("." + name, __name__)
     if name in table:
         mod, attr = table[name]
@@ -44,4 +46,4 @@ def __getattr__(name):  # lazy: importing the package must not require torch.cud
 __all__ = ["TexirError", "launch_count", "Scene", "RaycastingScene", "generate_dir", "sample_hemisphere", "query_irf",
            "trace", "specular_reflectance", "diffuse_reflectance", "shade", "irradiance", "texture_fetch", "radiance_samples", "gbuffer", "gbuffer_mvp", "point_order",
            "HotPathMixin", "MaterialModel", "TracerO3d", "pad_texture", "padding_texture", "imwrite_hdr", "imread_hdr",
-           "save_irr_texture"]
+           "save_irr_texture", "GraphedMatStep"]

@@ -86,6 +86,7 @@ SIGNATURES = {
     "texir_mat_fetch": (c_int, [_P, _P, c_int, c_int, c_int] * 3 + [_P, _P, c_int64, _P, _P, _P, _P, _P]),
     "texir_mat_scatter_rows": (c_int, [_P, c_int64, _P, _P, c_int, c_int, c_int, _P, _P, c_int, c_int, c_int, _P]),
     "texir_mt19937_uniform": (c_int, [_P, c_int, c_int, c_int64, _P, _P, _P]),
+    "texir_mt19937_advance_host": (c_int, [_P, _P, _P, c_int64]),
     "texir_peer_alloc": (c_int, [c_int, c_int64, POINTER(c_void_p), _P]),
     "texir_peer_free": (c_int, [c_int, _P]),
     "texir_peer_open": (c_int, [c_int, _P, POINTER(c_void_p)]),

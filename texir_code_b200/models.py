@@ -245,7 +245,8 @@ class MaterialModel(HotPathMixin, nn.Module):
             roughness = roughness.reshape(*normal.shape[:-1], 1)
         return self.render(normal, albedo, roughness, points, cam_position, irr)
 
-    def _render_textured(self, normal, albedo, roughness, roughness_womipmap, points, cam_position, irr, texc, texd, stage):
+    def _render_textured(self, normal, albedo, roughness, roughness_womipmap, points, cam_position, irr, texc, texd, stage,
+                         shift_spec=None):
         """stages 1 and 2 of forward(): the result dict of render() plus roughness / roughness_womipmap.  Fused: one
         autograd node does the four fetches, the render and -- in its backward -- the scatter of every output's gradient
         into the material textures (ops.mat_stage).  Not fused (or relighting): the reference's own composition."""
@@ -257,7 +258,11 @@ class MaterialModel(HotPathMixin, nn.Module):
                 res = self.render(normal, albedo, roughness, points, cam_position, irr)
             return res, roughness, roughness_womipmap
         n, p = normal.reshape(-1, 3), points.reshape(-1, 3)
-        shift_spec = self._draw_shift(n.shape[0], n.device)
+        if shift_spec is None:
+            shift_spec = self._draw_shift(n.shape[0], n.device)
+        elif shift_spec.shape[0] != n.shape[0]:
+            raise RuntimeError("the shift drawn ahead of the G-buffer covers %d pixels, the G-buffer has %d"
+                               % (shift_spec.shape[0], n.shape[0]))
         rgb, alb, rough, rough_w, _ = ops.mat_stage(
             self._scene(), self.mat_ws, self.materials_a, self.materials_r, self.irrt, n, p, cam_position, texc, texd,
             shift_spec, stage=stage, num_spec=int(self.sample_l[1]), max_mip_level=self.max_mip_level,
@@ -320,8 +325,13 @@ class MaterialModel(HotPathMixin, nn.Module):
                 raise ValueError("MaterialModel.forward needs %s (constructor: materials_a_res / materials_r_res / irrt)" % name)
         dev = self.scene.device
         fused = getattr(self, "fused", True) and not getattr(self, "relighting", False)
+        shift_spec = None
         if stage in (1, 2) and fused:
-            # the pyramids of the textures do not depend on the view: build them beside the G-buffer walk (side stream)
+            # neither the shift of the step's one generate_dir call nor the pyramids of the textures depend on the view:
+            # the shift kernel (its own stream) and the pyramid builds (side stream) run beside the G-buffer walk.  Nothing
+            # else draws from the generator before the render, so drawing first leaves the reference's stream intact.
+            world = self.shard[1] if self.shard is not None else 1
+            shift_spec = self._draw_shift(int(mvp.shape[0]) * self.cube_res * self.cube_res // world, dev)
             self.mat_ws.prefetch({"a": self.materials_a, "r": self.materials_r, "i": self.irrt}, self.max_mip_level)
         gb = self.gbuffers(mvp, cam_position, id)       # (keyed on the caller's own tensors when cache_gbuffers is on)
         cam_position = cam_position.to(dev)
@@ -353,7 +363,7 @@ class MaterialModel(HotPathMixin, nn.Module):
         elif stage in (1, 2):
             res, roughness, roughness_womipmap = self._render_textured(normal, albedo, roughness, roughness_womipmap,
                                                                        pos + 1e-2 * normal, cam_position, irr, texc, texd,
-                                                                       stage)
+                                                                       stage, shift_spec)
         else:
             raise ValueError("stage must be -1, 0, 1 or 2")
         res.update({"empty_mask": mask, "roughness_womipmap": roughness_womipmap, "roughness": roughness})

@@ -12,6 +12,7 @@ generator reproduces the reference's sample set.
 """
 from __future__ import annotations
 
+import ctypes
 import os
 from typing import Optional
 
@@ -122,9 +123,93 @@ class deferred_rng_commit:
 
 def _mt_store_state(a, h_out) -> None:
     w = h_out.numpy().view(np.uint32)
+    if int(w[_MT_N]) == 0xFFFFFFFF:
+        raise _lib.TexirError("texir_mt19937_uniform: the generator state handed to the device was inconsistent")
     a[_OFF_STATE:_OFF_STATE + 8 * _MT_N] = w[:_MT_N].astype(np.uint64).view(np.uint8)
     a[_OFF_LEFT:_OFF_LEFT + 4] = np.array([int(w[_MT_N])], np.int32).view(np.uint8)
     a[_OFF_NEXT:_OFF_NEXT + 8] = np.array([int(w[_MT_N + 1])], np.uint64).view(np.uint8)
+
+
+_graph_rng = None   # the GraphRng whose capture is in progress: draw_shift routes every draw through it
+
+
+class GraphRng:
+    """The CPU generator's stream inside a CUDA graph (graphed.GraphedMatStep).  Kernel arguments are frozen at capture,
+    so the whole engine state -- 624 words, left, next -- travels through device memory, and every draw of the captured
+    step advances it there (texir_mt19937_uniform, left = -1).  Per replay
+    the host copies torch's current state into the device buffer the graph's first draw reads (an ordinary asynchronous copy
+    on the replaying stream, from a ring of pinned buffers) and advances torch's generator ITSELF by the step's draws
+    (texir_mt19937_advance_host: the twists only, no numbers -- about 0.1 ms of host time that overlaps the previous
+    replay), so nothing waits for the device and replays queue back to back."""
+
+    def __init__(self, device):
+        dev = torch.device(device)
+        self.dev = dev
+        self.idx = dev.index if dev.index is not None else torch.cuda.current_device()
+        self.h_ring = [[torch.empty(_MT_N + 2, dtype=torch.int32).pin_memory(), None] for _ in range(4)]  # [buffer, copy-done event]
+        self.slot = 0
+        with torch.cuda.device(self.idx):
+            self.d = [torch.empty(_MT_N + 2, dtype=torch.int32, device=dev) for _ in range(2)]
+            self.stream = torch.cuda.Stream(device=self.idx, priority=-1)
+        self.cur, self.counts = 0, []
+
+    def __enter__(self):            # wrap the capture in it
+        global _graph_rng
+        finish_pending()
+        _graph_rng, self.cur, self.counts = self, 0, []
+        return self
+
+    def __exit__(self, *exc):
+        global _graph_rng
+        _graph_rng = None
+        return False
+
+    def draw(self, n: int) -> torch.Tensor:
+        main = torch.cuda.current_stream(self.idx)
+        with torch.cuda.device(self.idx):
+            out = torch.empty(n, dtype=torch.float32, device=self.dev)
+            self.stream.wait_stream(main)     # a capture only admits streams that branch off the capturing one
+            with torch.cuda.stream(self.stream):
+                _lib.check(_lib.load().texir_mt19937_uniform(_ptr(self.d[self.cur]), -1, 0, n, _ptr(out), _ptr(self.d[self.cur ^ 1]),
+                                                             _stream_ptr(self.dev)), "texir_mt19937_uniform")
+                self.cur ^= 1
+                self.counts.append(int(n))
+            main.wait_stream(self.stream)
+        return out
+
+    def before_replay(self) -> None:
+        """torch's generator state into the graph's input buffer; torch's generator advanced by the step's draws"""
+        if not self.counts:
+            return
+        finish_pending()
+        st = torch.get_rng_state()
+        a = st.numpy()
+        buf, ev = self.h_ring[self.slot]
+        if ev is not None:
+            ev.synchronize()                 # four replays ago: long done
+        w = buf.numpy().view(np.uint32)
+        w[:_MT_N] = a[_OFF_STATE:_OFF_STATE + 8 * _MT_N].view(np.uint64).astype(np.uint32)
+        left = ctypes.c_int(int(a[_OFF_LEFT:_OFF_LEFT + 4].view(np.int32)[0]))
+        nxt = ctypes.c_int(int(a[_OFF_NEXT:_OFF_NEXT + 8].view(np.uint64)[0]))
+        w[_MT_N], w[_MT_N + 1] = np.uint32(left.value & 0xFFFFFFFF), np.uint32(nxt.value)
+        with torch.cuda.device(self.idx):
+            self.d[0].copy_(buf, non_blocking=True)          # stream-ordered before the replay that follows
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.idx))
+        self.h_ring[self.slot][1] = ev
+        self.slot = (self.slot + 1) % len(self.h_ring)
+        adv = w[:_MT_N].copy()
+        lib = _lib.load()
+        for n in self.counts:
+            _lib.check(lib.texir_mt19937_advance_host(adv.ctypes.data, ctypes.byref(left), ctypes.byref(nxt), n),
+                       "texir_mt19937_advance_host")
+        a[_OFF_STATE:_OFF_STATE + 8 * _MT_N] = adv.astype(np.uint64).view(np.uint8)
+        a[_OFF_LEFT:_OFF_LEFT + 4] = np.array([left.value], np.int32).view(np.uint8)
+        a[_OFF_NEXT:_OFF_NEXT + 8] = np.array([nxt.value], np.uint64).view(np.uint8)
+        torch.set_rng_state(st)
+
+    def after_replay(self) -> None:
+        pass
 
 
 def _draw_mt_device(n: int, dev: torch.device, idx: int, state: Optional[torch.Tensor] = None, commit: bool = True):
@@ -190,6 +275,8 @@ def draw_shift(b: int, device) -> torch.Tensor:
     the generator's stream on the device (texir_mt19937_uniform) and hand the advanced state back to torch.
     TEXIR_SHIFT_DEVICE=0 keeps everything on the host."""
     global _mt_ok
+    if _graph_rng is not None:
+        return _graph_rng.draw(2 * b).view(b, 1, 2)
     finish_pending()
     dev = torch.device(device)
     if dev.type != "cuda":
