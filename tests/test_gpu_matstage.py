@@ -454,7 +454,11 @@ def test_graphed_step_is_the_eager_step(tx, cuda_device):
             ref.append((loss.detach().clone(), None if eager.materials_a.grad is None else eager.materials_a.grad.clone(),
                         eager.materials_r.grad.clone(), torch.get_rng_state()))
         mm = make()
+        # a living autograd graph from an eager call on the default stream pins the parameters' AccumulateGrad nodes to
+        # that stream; the capture must not depend on them (it enters the textures as fresh leaves)
+        keep = mm(views[0][0], 0, views[0][1], stage)
         step = graphed.GraphedMatStep(mm, stage, loss_fn, example=views[0])
+        assert keep["rgb"].grad_fn is not None
         n0 = tx.launch_count()
         torch.manual_seed(77)
         for (mvp, cam, gt), (loss_w, ga_w, gr_w, state_w) in zip(views, ref):

@@ -61,10 +61,19 @@ class GraphedMatStep:
         model.cache_gbuffers = self._cached
 
     def _body(self):
-        self.model.zero_grad(set_to_none=True)
-        out = self.model(self.mvp, 0, self.cam, self.stage)
+        # The trainable textures enter the step as FRESH leaves over the same storage.  A parameter's AccumulateGrad node
+        # remembers the stream it was created on; one that survives from an earlier eager step (default stream) makes the
+        # engine synchronise the capturing stream with the legacy stream, which invalidates the capture.  A fresh leaf gets
+        # its node inside the capture, on the capturing stream, whatever ran before.
+        model = self.model
+        model.zero_grad(set_to_none=True)
+        named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
+        fresh = {n: p.detach().requires_grad_(True) for n, p in named}
+        out = torch.func.functional_call(model, fresh, (self.mvp, 0, self.cam, self.stage))
         loss = self.loss_fn(out, self.target)
         loss.backward()
+        for n, p in named:
+            p.grad = fresh[n].grad
         if self.sync is not None:
             self.sync()
         return loss.detach(), {k: (v.detach() if torch.is_tensor(v) else v) for k, v in out.items()}
