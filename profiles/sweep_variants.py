@@ -22,7 +22,9 @@ for name in names:
         extra = ""
         if mat:
             m = d["mat_stage"]
-            extra = "  mat stash %.3f ms recompute %.3f ms relight %.1f ms" % (m["fwd_bwd_stash_ms"], m["fwd_bwd_recompute_ms"], m["relight_3072_1024_ms"])
+            extra = "  mat stash %.3f ms recompute %.3f ms relight %.1f ms step16 %.4f ms step256 %.3f ms" % (
+                m["fwd_bwd_stash_256spp"]["ms"], m["fwd_bwd_recompute_256spp"]["ms"], m["relight_3072_1024_ms"],
+                m["train_step_stage2_16spp"]["ms"], m["train_step_stage2_256spp"]["ms"])
         print("%-26s %.4e ray-samples/s  kernel %.2f ms  checksum %.6f  clocks %s%s" % (
             name, d["value"], d["roofline"]["kernel_ms"], d["e2e"]["checksum"], d["clocks"]["sm_mhz"], extra), flush=True)
     except Exception as exc:

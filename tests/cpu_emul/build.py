@@ -45,6 +45,7 @@ def load():
     lib.emul_simulate_stream.argtypes = [vp, vp, i32, i32, vp]
     lib.emul_cast_rays_front.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp]
     lib.emul_cast_rays_free.argtypes = [vp, vp, i64, vp, vp, vp]
+    lib.emul_pop_stats.argtypes = [vp, vp, i64, vp]
     lib.emul_mip_levels.argtypes = [i32, i32, i32]
     lib.emul_mip_elems.restype = i64
     lib.emul_mip_elems.argtypes = [i32, i32, i32, i32]

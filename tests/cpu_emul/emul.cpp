@@ -517,4 +517,64 @@ void emul_cast_rays_free(EmulScene* s, const float* rays, int64_t R, float* t, u
     }
 }
 
+// What a traversal stack that also remembers each postponed child's entry distance would save: out[0] = node steps,
+// out[1] = pops of inner nodes, out[2] = of those, pops whose stored tnear already exceeds the closest hit (today they
+// cost a whole node step that finds neither child), out[3] = pops of leaves, out[4] = of those, culled the same way
+// (today: their triangles are tested), out[5] = triangle tests.   (profiles/simulate_stack_tnear.py)
+void emul_pop_stats(EmulScene* es, const float* rays, int64_t R, int64_t* out) {
+    const SceneView& s = es->view;
+    for (int k = 0; k < 6; ++k) out[k] = 0;
+    for (int64_t q = 0; q < R; ++q) {
+        RayQ r;
+        rayq_setup(s, r, v3(rays[6 * q], rays[6 * q + 1], rays[6 * q + 2]), v3(rays[6 * q + 3], rays[6 * q + 4], rays[6 * q + 5]));
+        Hit hit;
+        hit_reset(hit);
+        int stack[kStackSize];
+        float tstack[kStackSize];
+        int n = 0;
+        int node = 0;
+        const uint32_t fx = r.selx ^ 0x0022u, fy = r.sely ^ 0x0022u, fz = r.selz ^ 0x0022u;
+        for (;;) {
+            while (node >= 0) {
+                ++out[0];
+                const uint4* np = s.qnodes2 + 2 * (size_t)node;
+                const uint4 q0 = np[0], q1 = np[1];
+                const float t0n = fmaxf(fmaxf(qplane_(q0.x, r.selx, r.S.x, r.O.x), qplane_(q0.y, r.sely, r.S.y, r.O.y)),
+                                        fmaxf(qplane_(q0.z, r.selz, r.S.z, r.O.z), 0.0f));
+                const float t0f = fminf(fminf(qplane_(q0.x, fx, r.S.x, r.O.x), qplane_(q0.y, fy, r.S.y, r.O.y)),
+                                        fminf(qplane_(q0.z, fz, r.S.z, r.O.z), hit.t));
+                const float t1n = fmaxf(fmaxf(qplane_(q0.w, r.selx, r.S.x, r.O.x), qplane_(q1.x, r.sely, r.S.y, r.O.y)),
+                                        fmaxf(qplane_(q1.y, r.selz, r.S.z, r.O.z), 0.0f));
+                const float t1f = fminf(fminf(qplane_(q0.w, fx, r.S.x, r.O.x), qplane_(q1.x, fy, r.S.y, r.O.y)),
+                                        fminf(qplane_(q1.y, fz, r.S.z, r.O.z), hit.t));
+                const int c0 = (int)q1.z, c1 = (int)q1.w;
+                const bool h0 = t0n <= t0f, h1 = t1n <= t1f;
+                if (h0 && h1) {
+                    const bool swap = t1n < t0n;
+                    stack[n] = swap ? c0 : c1;
+                    tstack[n++] = swap ? t0n : t1n;
+                    node = swap ? c1 : c0;
+                } else if (h0) {
+                    node = c0;
+                } else if (h1) {
+                    node = c1;
+                } else {
+                    if (n == 0) { node = kQSentinel; break; }
+                    --n;
+                    node = stack[n];
+                    if (node >= 0) { ++out[1]; out[2] += tstack[n] > hit.t; } else { ++out[3]; out[4] += tstack[n] > hit.t; }
+                }
+            }
+            if (node == kQSentinel) break;
+            const int ref = ~node, first = ref >> 3, cnt = (ref & 7) + 1;
+            for (int i = 0; i < cnt; ++i) test_slot(s.tris2, first + i, r.o, r.d, hit);
+            out[5] += cnt;
+            if (n == 0) break;
+            --n;
+            node = stack[n];
+            if (node >= 0) { ++out[1]; out[2] += tstack[n] > hit.t; } else { ++out[3]; out[4] += tstack[n] > hit.t; }
+        }
+    }
+}
+
 }  // extern "C"

@@ -401,9 +401,12 @@ TX_HD Hit trace(const SceneView& s, V3 o, V3 d) {
 // sample-order permutation: lanes of a warp take 32 consecutive j for a fixed residue c, i.e.
 // indices i = (j << a) + c.  For the Hammersley set this is a compact patch of the unit square
 // (s0 in a band of 32*2^a/N, s1 in a band of 2^-a), so the 32 rays of a warp iteration are coherent.
+// Patch shape: 2^a residues, at least 32 samples per residue, a <= 4 -- measured on B200 (profiles/r02_abits_sweep.txt,
+// r02_prefetch_sweep2.txt): at N = 2048 a = 2 / 3 / 4 / 5 give 3.66 / 3.89 / 3.91 / 3.69e9 ray-samples/s (round 1 used the
+// square patch, a = 3); the relighting shape (3072 + 1024 samples) gains 2.6 % from a = 4, N = 256 is flat.
 TX_HD int coherent_bits(int N) {
     int a = 0;
-    while (a < 4 && (32 << (2 * (a + 1))) <= N) ++a;  // 2^(2a) <= N/32
+    while (a < 4 && (N >> (a + 1)) >= 32) ++a;
     return a;
 }
 

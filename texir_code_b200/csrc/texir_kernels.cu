@@ -1006,6 +1006,16 @@ struct ShadePointSmem {
 #endif
 // G = lanes per point: 32 (N >= 32), or 16 with two points per warp (the reference trains at 16 specular samples,
 // configs/syn.conf:24)
+#if TX_SHADE_TNEAR
+#define TX_SHADE_TRACE trace_qbvh2_t   // the walk whose stack entries carry their entry distance (texir_walk.h)
+#else
+#define TX_SHADE_TRACE trace_qbvh2_front
+#endif
+#if TX_SHADE_TNEAR >= 2                // ... also where no shared first descent is used (N = 16)
+#define TX_SHADE_TRACE0(s, o, d) trace_qbvh2_t(s, o, d, nullptr, 0, 0)
+#else
+#define TX_SHADE_TRACE0(s, o, d) trace<KIND>(s, o, d)
+#endif
 template <int KIND, bool TANGENT, bool FRONT = false, int G = 32>
 __global__ void __launch_bounds__(128, TX_SHADE_LEAN_MINB) k_shade_lean(SceneView s, ShadeArgs a) {
     constexpr int PTS = 128 / G;  // points per CTA
@@ -1065,9 +1075,9 @@ __global__ void __launch_bounds__(128, TX_SHADE_LEAN_MINB) k_shade_lean(SceneVie
                     l = reflect_dir(ds.d, sp.v, &vdh_raw);
                     w = spec_weight<TANGENT>(sp, f, ds, l, vdh_raw, &dw);
                 }
-                Hit h = FRONT ? trace_qbvh2_front(s, o, l, sm_front[wid], ((volatile int*)sm_front_n)[wid],
-                                                  ((volatile int*)sm_front_start)[wid])
-                              : trace<KIND>(s, o, l);
+                Hit h = FRONT ? TX_SHADE_TRACE(s, o, l, sm_front[wid], ((volatile int*)sm_front_n)[wid],
+                                               ((volatile int*)sm_front_start)[wid])
+                              : TX_SHADE_TRACE0(s, o, l);
                 V3 L = fetch_radiance(s, h);
                 sm_acc[0][tid] += L.x * w;
                 sm_acc[1][tid] += L.y * w;
@@ -1095,9 +1105,9 @@ __global__ void __launch_bounds__(128, TX_SHADE_LEAN_MINB) k_shade_lean(SceneVie
                     wgt = (a.mode_diff == MODE_COSINE) ? 1.0f
                                                        : clamp01(rn_dot(v3(q->sp.n.x, q->sp.n.y, q->sp.n.z), d));
                 }
-                Hit h = FRONT ? trace_qbvh2_front(s, o, d, sm_front[wid], ((volatile int*)sm_front_n)[wid],
-                                                  ((volatile int*)sm_front_start)[wid])
-                              : trace<KIND>(s, o, d);
+                Hit h = FRONT ? TX_SHADE_TRACE(s, o, d, sm_front[wid], ((volatile int*)sm_front_n)[wid],
+                                               ((volatile int*)sm_front_start)[wid])
+                              : TX_SHADE_TRACE0(s, o, d);
                 V3 L = fetch_radiance(s, h);
                 sm_acc[3][tid] += L.x * wgt;
                 sm_acc[4][tid] += L.y * wgt;

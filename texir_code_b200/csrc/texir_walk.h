@@ -168,6 +168,33 @@ TX_HD float qplane_(uint32_t w, uint32_t sel, float S, float O) {
     return tx_fma(int_as_float_((int)byte_perm_(w, 0x4B000000u, sel)), S, O);
 }
 
+// Measured on B200 (profiles/r02_prefetch_sweep.txt, same checksum everywhere): prefetching the POSTPONED child's node
+// into L1 when it is pushed gives +2.4 % on the IrT (3.891e9 -> 3.983e9) and 1.5 ... 2 % on the Mat-stage legs -- the
+// pop then finds its node in L1; also prefetching a postponed leaf's triangle (= 2: -3 %) or a found leaf's triangle on
+// the way out of the node loop (TX_PREFETCH_LEAF: -5 ... -8 %, the test sits in every node step) costs more than it hides.
+#ifndef TX_PREFETCH_PUSH
+#define TX_PREFETCH_PUSH 1
+#endif
+#ifndef TX_PREFETCH_UV
+#define TX_PREFETCH_UV 0
+#endif
+#ifndef TX_PREFETCH_FRONT
+#define TX_PREFETCH_FRONT 0
+#endif
+#ifndef TX_PREFETCH_LEAF
+#define TX_PREFETCH_LEAF 0
+#endif
+// first triangle record (48 bytes: two 32-byte sectors) of a leaf reference into L1
+TX_HD void qprefetch_leaf(const SceneView& s, int leaf_ref) {
+#ifdef __CUDA_ARCH__
+    const char* p = (const char*)(s.tris2 + 3 * (size_t)((~leaf_ref) >> 3));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p + 32));
+#else
+    (void)s; (void)leaf_ref;
+#endif
+}
+
 #ifndef TX_STACK_TOP
 #define TX_STACK_TOP 0
 #endif
@@ -207,7 +234,16 @@ TX_HD int qbvh2_step(const SceneView& s, const RayQ& r, float tbest, int node, i
 #else
     if (h0 && h1) {
         const bool swap = t1n < t0n;
-        *sp++ = swap ? c0 : c1;
+        const int far_child = swap ? c0 : c1;
+#if TX_PREFETCH_PUSH && defined(__CUDA_ARCH__)
+        // the postponed child's node is fetched into L1 now, so that the pop finds it there (-DTX_PREFETCH_PUSH=1;
+        // = 2: a postponed LEAF's first triangle too)
+        if (far_child >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(s.qnodes2 + 2 * (size_t)far_child));
+#if TX_PREFETCH_PUSH >= 2
+        else qprefetch_leaf(s, far_child);
+#endif
+#endif
+        *sp++ = far_child;
         return swap ? c1 : c0;
     }
     if (h0) return c0;
@@ -282,6 +318,7 @@ TX_HD int qbvh2_step_top(const SceneView& s, const RayQ& r, float tbest, int nod
 #ifndef TX_SPECULATIVE
 #define TX_SPECULATIVE 0
 #endif
+
 // The QBVH2 walk keeps its stack pointer as an address (no index scaling per push / pop) and ends on a NEGATIVE
 // sentinel that no leaf reference can equal (leaf = ~((first_slot << 3) | (count - 1)) with first_slot < 2^27), so the
 // node loop tests `node >= 0` only.
@@ -299,7 +336,18 @@ TX_HD int qstack_pop(int*& sp, int& top) {
 TX_HD void qbvh2_leaf(const SceneView& s, const RayQ& r, int node, Hit& hit) {
     const int ref = ~node;
     const int first = ref >> 3, cnt = (ref & 7) + 1;
+#if TX_PREFETCH_UV && defined(__CUDA_ARCH__)
+    const uint32_t before = hit.prim;
+#endif
     for (int i = 0; i < cnt; ++i) test_slot(s.tris2, first + i, r.o, r.d, hit);
+#if TX_PREFETCH_UV && defined(__CUDA_ARCH__)
+    // a new closest hit: its UV record (48 bytes of float64, the first thing the radiance fetch reads) into L2 / L1 now
+    if (hit.prim != before && s.tri_uvs) {
+        const char* p = (const char*)(s.tri_uvs + 6 * (size_t)hit.prim);
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(p + 32));
+    }
+#endif
 }
 
 TX_HD Hit trace_qbvh2(const SceneView& s, V3 o, V3 d) {
@@ -348,7 +396,12 @@ TX_HD Hit trace_qbvh2(const SceneView& s, V3 o, V3 d) {
             if (__popc(__activemask()) < TX_NODE_EXIT_BELOW) break;
         }
 #else
-        while (node >= 0) node = qbvh2_step(s, r, hit.t, node, sp, top);
+        while (node >= 0) {
+            node = qbvh2_step(s, r, hit.t, node, sp, top);
+#if TX_PREFETCH_LEAF
+            if (node < 0 && node != kQSentinel) qprefetch_leaf(s, node);   // fetched while the other lanes still walk
+#endif
+        }
 #endif
         if (node < 0 && node != kQSentinel) {
             qbvh2_leaf(s, r, node, hit);
@@ -381,6 +434,96 @@ TX_HD Hit trace_qbvh2_free(const SceneView& s, V3 o, V3 d) {
         } else {
             qbvh2_leaf(s, r, node, hit);
             node = qstack_pop(sp, top);
+        }
+    }
+    return hit;
+}
+
+// Stack entries that also carry the entry distance of the postponed child: a pop drops every entry whose distance
+// already exceeds the closest hit -- otherwise such an entry costs a whole node step that finds neither child (model,
+// profiles/simulate_stack_tnear.py: 1.9 of a ray's 40 node steps).  Same hits; 8-byte entries, twice the stack lines in
+// L1.  Measured on B200 (profiles/r02_tnear_sweep.txt): the 40-register IrT kernel LOSES 1 % (12 CTAs per SM: the stacks
+// take the L1 the nodes need), the 48-register render kernels gain 0.7 ... 3.5 % -- so the render kernels use it
+// (TX_SHADE_TNEAR, default 1) and the IrT kernel does not (-DTX_STACK_TNEAR=1 forces it everywhere).
+#ifndef TX_STACK_TNEAR
+#define TX_STACK_TNEAR 0
+#endif
+#ifndef TX_SHADE_TNEAR
+#define TX_SHADE_TNEAR 1
+#endif
+struct alignas(8) QEnt {
+    int ref;
+    float t;
+};
+TX_HD int qpop_t(QEnt*& sp, float tbest) {
+    QEnt e;
+    do {
+        e = *--sp;
+    } while (e.t > tbest);  // the sentinel carries t = 0
+    return e.ref;
+}
+TX_HD int qbvh2_step_t(const SceneView& s, const RayQ& r, float tbest, int node, QEnt*& sp) {
+    const uint4* np = s.qnodes2 + 2 * (size_t)node;
+    const uint4 q0 = ld_nc_u4(np + 0), q1 = ld_nc_u4(np + 1);
+    const uint32_t fx = r.selx ^ 0x0022u, fy = r.sely ^ 0x0022u, fz = r.selz ^ 0x0022u;
+    const float t0n = fmaxf(fmaxf(qplane_(q0.x, r.selx, r.S.x, r.O.x), qplane_(q0.y, r.sely, r.S.y, r.O.y)),
+                            fmaxf(qplane_(q0.z, r.selz, r.S.z, r.O.z), 0.0f));
+    const float t0f = fminf(fminf(qplane_(q0.x, fx, r.S.x, r.O.x), qplane_(q0.y, fy, r.S.y, r.O.y)),
+                            fminf(qplane_(q0.z, fz, r.S.z, r.O.z), tbest));
+    const float t1n = fmaxf(fmaxf(qplane_(q0.w, r.selx, r.S.x, r.O.x), qplane_(q1.x, r.sely, r.S.y, r.O.y)),
+                            fmaxf(qplane_(q1.y, r.selz, r.S.z, r.O.z), 0.0f));
+    const float t1f = fminf(fminf(qplane_(q0.w, fx, r.S.x, r.O.x), qplane_(q1.x, fy, r.S.y, r.O.y)),
+                            fminf(qplane_(q1.y, fz, r.S.z, r.O.z), tbest));
+    const int c0 = (int)q1.z, c1 = (int)q1.w;
+    const bool h0 = t0n <= t0f, h1 = t1n <= t1f;
+    if (h0 && h1) {
+        const bool swap = t1n < t0n;
+        QEnt e;
+        e.ref = swap ? c0 : c1;
+        e.t = swap ? t0n : t1n;
+#if TX_PREFETCH_PUSH && defined(__CUDA_ARCH__)
+        if (e.ref >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(s.qnodes2 + 2 * (size_t)e.ref));
+#endif
+        *sp++ = e;
+        return swap ? c1 : c0;
+    }
+    if (h0) return c0;
+    if (h1) return c1;
+    return qpop_t(sp, tbest);
+}
+TX_HD Hit trace_qbvh2_t(const SceneView& s, V3 o, V3 d, const uint4* entries, int count, int start) {
+    RayQ r;
+    rayq_setup(s, r, o, d);
+    Hit hit;
+    hit_reset(hit);
+    QEnt stack[kStackSize];
+    QEnt* sp = stack;
+    {
+        QEnt e;
+        e.ref = kQSentinel;
+        e.t = 0.f;
+        *sp++ = e;
+    }
+    const uint32_t fx = r.selx ^ 0x0022u, fy = r.sely ^ 0x0022u, fz = r.selz ^ 0x0022u;
+    for (int k = 0; k < count; ++k) {
+        const uint4 en = entries[k];
+        const float tn = fmaxf(fmaxf(qplane_(en.x, r.selx, r.S.x, r.O.x), qplane_(en.y, r.sely, r.S.y, r.O.y)),
+                               fmaxf(qplane_(en.z, r.selz, r.S.z, r.O.z), 0.0f));
+        const float tf = fminf(fminf(qplane_(en.x, fx, r.S.x, r.O.x), qplane_(en.y, fy, r.S.y, r.O.y)),
+                               qplane_(en.z, fz, r.S.z, r.O.z));
+        if (tn <= tf) {
+            QEnt e;
+            e.ref = (int)en.w;
+            e.t = tn;
+            *sp++ = e;
+        }
+    }
+    int node = start;
+    while (node != kQSentinel) {
+        while (node >= 0) node = qbvh2_step_t(s, r, hit.t, node, sp);
+        if (node < 0 && node != kQSentinel) {
+            qbvh2_leaf(s, r, node, hit);
+            node = qpop_t(sp, hit.t);
         }
     }
     return hit;
@@ -430,6 +573,9 @@ TX_HD void qbvh2_point_front(const SceneView& s, V3 o, uint4* entries, int* coun
 }
 
 TX_HD Hit trace_qbvh2_front(const SceneView& s, V3 o, V3 d, const uint4* entries, int count, int start) {
+#if TX_STACK_TNEAR
+    return trace_qbvh2_t(s, o, d, entries, count, start);
+#endif
     RayQ r;
     rayq_setup(s, r, o, d);
     Hit hit;
@@ -449,6 +595,9 @@ TX_HD Hit trace_qbvh2_front(const SceneView& s, V3 o, V3 d, const uint4* entries
             const float tf = fminf(fminf(qplane_(wx, fx, r.S.x, r.O.x), qplane_(wy, fy, r.S.y, r.O.y)),
                                    qplane_(wz, fz, r.S.z, r.O.z));
             if (tn <= tf) {
+#if TX_PREFETCH_FRONT && defined(__CUDA_ARCH__)
+                if (ref >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(s.qnodes2 + 2 * (size_t)ref));
+#endif
 #if TX_STACK_TOP
                 *sp++ = top;
                 top = ref;
@@ -460,7 +609,12 @@ TX_HD Hit trace_qbvh2_front(const SceneView& s, V3 o, V3 d, const uint4* entries
     }
     int node = start;
     while (node != kQSentinel) {
-        while (node >= 0) node = qbvh2_step(s, r, hit.t, node, sp, top);
+        while (node >= 0) {
+            node = qbvh2_step(s, r, hit.t, node, sp, top);
+#if TX_PREFETCH_LEAF
+            if (node < 0 && node != kQSentinel) qprefetch_leaf(s, node);   // fetched while the other lanes still walk
+#endif
+        }
         if (node < 0 && node != kQSentinel) {
             qbvh2_leaf(s, r, node, hit);
             node = qstack_pop(sp, top);
