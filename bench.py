@@ -319,14 +319,16 @@ def run_ours(args):
         h_out.copy_(e, non_blocking=True)
 
     # ---- device-resident timing (value) ------------------------------------------------------------
-    for _ in range(args.warmup):
-        step_resident()
-    timer.barrier()
+    # the clock sampler (an nvidia-smi process) is started BEFORE the warm-up steps: spawning it takes tens of
+    # milliseconds on a busy host, and a GPU left idle that long re-enters the timed region at ramping clocks
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        step_resident()
+    timer.barrier()
     n_launch0 = launch_count()
-    elapsed_ms, _ = timer.run(step_resident, args.steps, 0)
+    elapsed_ms, step_ms = timer.run(step_resident, args.steps, 0, per_step=True)
     launches = launch_count() - n_launch0
     clocks = sampler.stop() if rank == 0 else {}
     value = P * SPP * args.steps / (elapsed_ms * 1e-3)
@@ -412,7 +414,7 @@ def run_ours(args):
         tr = ncu_traffic("dram_bytes_per_ray_sample")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "ms_per_step": elapsed_ms / args.steps, "step_ms": [round(x, 3) for x in step_ms], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {
                 "workload": workload_text(P),
