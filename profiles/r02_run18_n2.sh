@@ -1,0 +1,6 @@
+set -x
+cd $GRAFT_REPO_ROOT
+nvidia-smi --query-gpu=index,name --format=csv,noheader | head -8
+python -c "import __graft_entry__ as g; g.build()" > gpurun_out/r02_build.log 2>&1; tail -1 gpurun_out/r02_build.log
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1"
+timeout 900 $TR --master-port 29541 bench.py --gpus 2 --steps 5 --warmup 3 > gpurun_out/r02_bench_n2.json 2> gpurun_out/r02_bench_n2.err; tail -3 gpurun_out/r02_bench_n2.err | cut -c1-300; cat gpurun_out/r02_bench_n2.json | cut -c1-6000

@@ -1876,6 +1876,21 @@ int texir_point_order(const texir_scene* sc, const float* pos, int64_t P, int32_
     TX_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys, order, order, (int)P, 0, 30, st));
     const size_t key_bytes = ((size_t)P * 4 + 255) & ~(size_t)255;
     char* ws = nullptr;
+    {   // keep the device's stream-ordered pool from handing its memory back to the OS at every synchronise (the default
+        // release threshold is 0): the next call would pay milliseconds of cuMemCreate / map on the host first
+        static bool kept[64] = {};
+        const int dv = sc->info.device;
+        if (dv >= 0 && dv < 64 && !kept[dv]) {
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, dv) == cudaSuccess) {
+                uint64_t thr = 0, want = 256ull << 20;
+                if (cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr) == cudaSuccess && thr < want)
+                    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &want);
+            }
+            cudaGetLastError();
+            kept[dv] = true;
+        }
+    }
     TX_CUDA(cudaMallocAsync((void**)&ws, 3 * key_bytes + tmp_bytes, st));
     uint32_t* k_in = (uint32_t*)ws;
     uint32_t* k_out = (uint32_t*)(ws + key_bytes);
