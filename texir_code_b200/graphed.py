@@ -21,7 +21,8 @@ cudaGraphLaunch per step.  The Cranley-Patterson shift still comes from torch's 
 What is frozen at capture: tensor shapes, `stage`, sample counts, the model's textures as OBJECTS (their values may change:
 the pyramids of the trainable ones are rebuilt inside the graph; the frozen IrT's pyramid and the radiance texture of the
 scene are not re-read -- build a new GraphedMatStep after swapping them), and cache_gbuffers (ignored: the G-buffer is part
-of the graph).
+of the graph).  Construction runs `warmup` eager steps before the capture: the parameters' .grad are overwritten and
+torch's CPU generator advances by those steps' draws -- seed after constructing if a run has to be reproducible.
 """
 from __future__ import annotations
 
@@ -45,20 +46,22 @@ class GraphedMatStep:
         self.rng = sample_util.GraphRng(dev)
         self._cached = getattr(model, "cache_gbuffers", False)
         model.cache_gbuffers = False
-        # warm-up on a side stream (allocator, lazy initialisation, NCCL communicators), eager: the generator advances
-        side = torch.cuda.Stream(device=dev)
-        side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):
-            for _ in range(max(1, warmup)):
-                self._body()
-        torch.cuda.current_stream(dev).wait_stream(side)
-        torch.cuda.synchronize(dev)
-        sample_util.finish_pending()
-        model.zero_grad(set_to_none=True)     # the capture allocates the gradients inside the graph's pool
-        self.graph = torch.cuda.CUDAGraph()
-        with self.rng, torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
-            self.loss, self.out = self._body()
-        model.cache_gbuffers = self._cached
+        try:
+            # warm-up on a side stream (allocator, lazy initialisation, NCCL communicators), eager: the generator advances
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for _ in range(max(1, warmup)):
+                    self._body()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            sample_util.finish_pending()
+            model.zero_grad(set_to_none=True)     # the capture allocates the gradients inside the graph's pool
+            self.graph = torch.cuda.CUDAGraph()
+            with self.rng, torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
+                self.loss, self.out = self._body()
+        finally:
+            model.cache_gbuffers = self._cached
 
     def _body(self):
         # The trainable textures enter the step as FRESH leaves over the same storage.  A parameter's AccumulateGrad node
