@@ -11,6 +11,7 @@
 //   k_mat_fetch        albedo (mip), roughness (mip), roughness (bilinear) and irradiance (mip) of a pixel in one pass
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <string>
 
 #include "../../include/texir_b200.h"
@@ -369,6 +370,9 @@ int texir_texture_mip_fold_into(float* g_tex, float* g_mips, int H, int W, int C
     }
     const int64_t threads = (int64_t)H * (W / 4);
     const unsigned grid = (unsigned)((threads + 255) / 256);
+    // (sixteen texels of a row per thread -- the chain above level 4 shared by 16 texels, 19 loads instead of 56 -- was
+    // measured at 129 us against 64 us for the 4096^2 x 1 texture: lanes 64 bytes apart halve the sector use of every
+    // 128-bit access)
     if (C == 1)
         k_mip_fold_gather<1><<<grid, 256, 0, st>>>(g_tex, g_mips, lv, H, W, out, clear);
     else
