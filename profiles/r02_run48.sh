@@ -1,0 +1,4 @@
+set -x
+cd $GRAFT_REPO_ROOT
+python -c "import __graft_entry__ as g; g.build()" > gpurun_out/r02_build.log 2>&1; tail -1 gpurun_out/r02_build.log
+timeout 900 python -m pytest tests/test_gpu_matstage.py -m gpu -q -x -p no:cacheprovider > gpurun_out/r02_gpu_tests48.log 2>&1; tail -3 gpurun_out/r02_gpu_tests48.log | cut -c1-300
