@@ -1,5 +1,5 @@
 set -x
-cd $GRAFT_REPO_ROOT
+cd $GRAFT_REPO_ROOT   # (these scripts ran as profiles/r02_runNN.sh; paths inside are repository-relative)
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv
 python -c "import __graft_entry__ as g; g.build()" > gpurun_out/r02_build.log 2>&1; tail -2 gpurun_out/r02_build.log
 rm -f gpurun_out/parity_large.jsonl
