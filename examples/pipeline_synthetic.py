@@ -20,6 +20,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import texir_code_b200 as tx  # noqa: E402
 from texir_code_b200 import postprocess, synth  # noqa: E402
+from texir_code_b200.graphed import GraphedMatStep  # noqa: E402
 
 
 def cube_mvps(cam):
@@ -43,6 +44,8 @@ def main():
     ap.add_argument("--irt", type=int, default=256, help="IrT resolution (the reference uses 1024)")
     ap.add_argument("--spp", type=int, default=256, help="IrT samples per texel (the reference uses 2048)")
     ap.add_argument("--steps", type=int, default=30, help="optimiser steps per stage")
+    ap.add_argument("--graphed", action="store_true",
+                    help="stages 1 and 2: forward + loss + backward replayed as ONE CUDA graph (texir_code_b200.GraphedMatStep)")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     sc = synth.make_room_scene(args.tris, seed=666, clutter=16)
@@ -88,18 +91,27 @@ def main():
         model.materials_a.copy_(init_a)
         model.materials_r.copy_(init_r)
     opt = torch.optim.Adam([model.materials_a, model.materials_r], lr=2e-2)
+    loss_fn = lambda out, gt: (torch.log1p(out["rgb"]) - torch.log1p(gt)).abs().mean()   # models/loss.py:81-99
     for stage in (0, 1, 2):                                                         # train_material.py's schedule
         losses = []
         warm = min(3, args.steps - 1)                                               # first steps load kernels / grow pools
+        step = None
+        if args.graphed and stage in (1, 2):
+            # captured once per stage; the gradients live in the graph's memory and every replay overwrites them, so the
+            # loop below must not call zero_grad(set_to_none=True)
+            step = GraphedMatStep(model, stage, loss_fn, example=(mvp, cam, target))
         for it in range(args.steps):
             if it == warm:
                 torch.cuda.synchronize()
                 t0 = time.perf_counter()
-            opt.zero_grad(set_to_none=True)
             torch.manual_seed(7)                                                    # same sample set as the target
-            out = model(mvp, 0, cam, stage)
-            loss = (torch.log1p(out["rgb"]) - torch.log1p(target)).abs().mean()    # models/loss.py:81-99
-            loss.backward()
+            if step is not None:
+                loss = step(mvp, cam, target)
+            else:
+                opt.zero_grad(set_to_none=True)
+                out = model(mvp, 0, cam, stage)
+                loss = loss_fn(out, target)
+                loss.backward()
             opt.step()
             with torch.no_grad():
                 model.materials_r.clamp_(0.01, 0.8)                                # train_material.py:458

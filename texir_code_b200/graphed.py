@@ -16,7 +16,8 @@ cudaGraphLaunch per step.  The Cranley-Patterson shift still comes from torch's 
     step = GraphedMatStep(model, stage=2, loss_fn=lambda out, gt: (out['rgb'] - gt).abs().mean(), example=(mvp, cam, gt))
     for it in range(n):
         loss = step(mvp_i, cam_i, gt_i)        # gradients are in model.materials_*.grad
-        optimizer.step()
+        optimizer.step()                       # (no zero_grad(set_to_none=True) in between: the .grad tensors are the
+                                               #  graph's own memory, every replay overwrites them)
 
 What is frozen at capture: tensor shapes, `stage`, sample counts, the model's textures as OBJECTS (their values may change:
 the pyramids of the trainable ones are rebuilt inside the graph; the frozen IrT's pyramid and the radiance texture of the
