@@ -45,7 +45,7 @@ def main():
     ap.add_argument("--spp", type=int, default=256, help="IrT samples per texel (the reference uses 2048)")
     ap.add_argument("--steps", type=int, default=30, help="optimiser steps per stage")
     ap.add_argument("--graphed", action="store_true",
-                    help="stages 1 and 2: forward + loss + backward replayed as ONE CUDA graph (texir_code_b200.GraphedMatStep)")
+                    help="forward + loss + backward of every stage replayed as ONE CUDA graph (texir_code_b200.GraphedMatStep)")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     sc = synth.make_room_scene(args.tris, seed=666, clutter=16)
@@ -96,7 +96,7 @@ def main():
         losses = []
         warm = min(3, args.steps - 1)                                               # first steps load kernels / grow pools
         step = None
-        if args.graphed and stage in (1, 2):
+        if args.graphed:
             # captured once per stage; the gradients live in the graph's memory and every replay overwrites them, so the
             # loop below must not call zero_grad(set_to_none=True)
             step = GraphedMatStep(model, stage, loss_fn, example=(mvp, cam, target))

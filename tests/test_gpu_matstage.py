@@ -444,7 +444,7 @@ def test_graphed_step_is_the_eager_step(tx, cuda_device):
         return mm
 
     loss_fn = lambda out, gt: ((out["rgb"] - gt) ** 2).mean() + 0.1 * out["roughness"].mean()
-    for stage in (2, 1):
+    for stage in (2, 1, 0):
         eager = make()
         torch.manual_seed(77)
         ref = []

@@ -9,7 +9,7 @@ The reference's training step (trainer/train_material.py:436-450) is
 
 At the training sample count (16 spp, configs/syn.conf:24) the device needs 0.75 ms for the first three lines and the
 Python side about as long to issue them -- on a busy host, or with one process per GPU, longer.  GraphedMatStep captures
-zero_grad + forward + loss + backward (+ the gradient synchronisation of a sharded model) ONCE and replays it: one
+zero_grad + forward + loss + backward (+ the gradient synchronisation of a sharded model) of stage 0, 1 or 2 ONCE and replays it: one
 cudaGraphLaunch per step.  The Cranley-Patterson shift still comes from torch's CPU generator, bit for bit
 (sample_util.GraphRng: the engine state is copied in before every replay; the host advances torch's generator itself).
 
@@ -39,8 +39,8 @@ class GraphedMatStep:
         """example = (mvp [V,4,4], cam_position [3], target): tensors of the shapes every later call will have (CUDA);
         loss_fn(result dict of model.forward, target) -> scalar; sync(): gradient synchronisation to run after backward
         inside the graph (e.g. lambda: parallel.allreduce_gradients(model) for a pixel-sharded model)."""
-        if stage not in (1, 2):
-            raise ValueError("GraphedMatStep covers the ray-traced stages 1 and 2")
+        if stage not in (0, 1, 2):
+            raise ValueError("GraphedMatStep covers the optimisation stages 0, 1 and 2")
         dev = model.scene.device
         self.model, self.stage, self.loss_fn, self.sync = model, stage, loss_fn, sync
         self.mvp, self.cam, self.target = (t.detach().to(dev).clone() for t in example)
