@@ -46,6 +46,7 @@ def load():
     lib.emul_cast_rays_front.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp]
     lib.emul_cast_rays_free.argtypes = [vp, vp, i64, vp, vp, vp]
     lib.emul_pop_stats.argtypes = [vp, vp, i64, vp]
+    lib.emul_cast_rays_tnear.argtypes = [vp, vp, i64, i32, vp, vp, vp]
     lib.emul_mip_levels.argtypes = [i32, i32, i32]
     lib.emul_mip_elems.restype = i64
     lib.emul_mip_elems.argtypes = [i32, i32, i32, i32]

@@ -577,4 +577,20 @@ void emul_pop_stats(EmulScene* es, const float* rays, int64_t R, int64_t* out) {
     }
 }
 
+// closest hits through the walk whose stack entries carry their entry distance (texir_walk.h, trace_qbvh2_t: the render
+// kernels' walk); use_front != 0: all rays start at org[0..3) and go through the shared first descent
+void emul_cast_rays_tnear(EmulScene* s, const float* rays, int64_t R, int use_front, float* t, uint32_t* id, float* uv) {
+    uint4 entries[kMaxFront];
+    int count = 0, start = 0;
+    if (use_front && R > 0) qbvh2_point_front(s->view, v3(rays[0], rays[1], rays[2]), entries, &count, &start);
+    for (int64_t q = 0; q < R; ++q) {
+        const float* r = rays + 6 * q;
+        Hit h = trace_qbvh2_t(s->view, v3(r[0], r[1], r[2]), v3(r[3], r[4], r[5]), entries, count, start);
+        t[q] = h.t;
+        id[q] = h.prim;
+        uv[2 * q] = h.u;
+        uv[2 * q + 1] = h.v;
+    }
+}
+
 }  // extern "C"

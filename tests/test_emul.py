@@ -247,3 +247,31 @@ def test_free_running_walk_bit_exact_vs_plain_walk(emul):
     t1, i1, u1 = np.empty(2, np.float32), np.empty(2, np.uint32), np.empty((2, 2), np.float32)
     emul.emul_cast_rays_free(one.h, rays.ctypes.data, 2, t1.ctypes.data, i1.ctypes.data, u1.ctypes.data)
     assert i1.tolist() == [0, 0xFFFFFFFF] and t1[0] == 1.0 and np.isinf(t1[1])
+
+
+def test_entry_distance_stack_walk_bit_exact_vs_plain_walk(emul):
+    """texir_walk.h trace_qbvh2_t (the render kernels' walk: stack entries carry the postponed child's entry distance and a
+    pop drops what the closest hit has overtaken): dropping such entries must not change a single hit -- with and without
+    the shared first descent, rays from surface points, from outside, degenerate directions"""
+    from texir_code_b200 import synth
+    rng = np.random.default_rng(9)
+    for num_tris, clutter in ((4000, 6), (60000, 16)):
+        sc = synth.make_room_scene(num_tris, seed=666, clutter=clutter)
+        es = EmulScene(emul, sc.vertices, sc.triangles)
+        pos, _ = synth.sample_surface_points(sc, 12, seed=5, seam_fraction=0.0)
+        for p in np.concatenate([pos, np.array([[0, 0, 0], [50, 0, 0]], np.float32)]).astype(np.float32):
+            d = rng.normal(size=(512, 3)).astype(np.float32)
+            d[:4] = [[0, 0, 0], [1, 0, 0], [0, np.inf, 0], [np.nan, 0, 1]]
+            rays = np.ascontiguousarray(np.concatenate([np.repeat(p[None], 512, 0), d], 1), np.float32)
+            t0, i0, u0 = np.empty(512, np.float32), np.empty(512, np.uint32), np.empty((512, 2), np.float32)
+            emul.emul_cast_rays_fast(es.h, 1, rays.ctypes.data, 512, t0.ctypes.data, i0.ctypes.data, u0.ctypes.data)
+            for use_front in (0, 1):
+                t1, i1, u1 = np.empty(512, np.float32), np.empty(512, np.uint32), np.empty((512, 2), np.float32)
+                emul.emul_cast_rays_tnear(es.h, rays.ctypes.data, 512, use_front, t1.ctypes.data, i1.ctypes.data, u1.ctypes.data)
+                assert np.array_equal(t0.view(np.uint32), t1.view(np.uint32)), use_front
+                assert np.array_equal(i0, i1) and np.array_equal(u0.view(np.uint32), u1.view(np.uint32))
+    one = EmulScene(emul, np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32), np.array([[0, 1, 2]], np.int32))
+    rays = np.ascontiguousarray(np.array([[0.2, 0.2, 1.0, 0, 0, -1], [0.2, 0.2, 1.0, 0, 0, 1]], np.float32))
+    t1, i1, u1 = np.empty(2, np.float32), np.empty(2, np.uint32), np.empty((2, 2), np.float32)
+    emul.emul_cast_rays_tnear(one.h, rays.ctypes.data, 2, 0, t1.ctypes.data, i1.ctypes.data, u1.ctypes.data)
+    assert i1.tolist() == [0, 0xFFFFFFFF] and t1[0] == 1.0 and np.isinf(t1[1])
