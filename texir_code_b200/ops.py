@@ -17,7 +17,7 @@ from typing import Optional
 import torch
 
 from . import _lib
-from .scene import Scene, _ptr, _stream_ptr
+from .scene import Scene, _on, _ptr, _stream_ptr
 
 TINY_NUMBER = 1e-6
 TINY_TINY_NUMBER = 1e-14
@@ -25,6 +25,8 @@ TINY_TINY_NUMBER = 1e-14
 
 def _f32c(t: torch.Tensor, dev=None) -> torch.Tensor:
     t = t.detach()
+    if t.dtype is torch.float32 and (dev is None or t.device == dev) and t.is_contiguous():
+        return t                      # the common case: three dispatcher calls saved per tensor, ~15 tensors per step
     if dev is not None and t.device != dev:
         t = t.to(dev)
     return t.to(torch.float32).contiguous()
@@ -64,7 +66,7 @@ def query_irf(scene: Scene, points: torch.Tensor, directions: torch.Tensor, num_
     org = _f32c(org, dev)
     d = _f32c(d, dev)
     rad = torch.empty(P, N, 3, dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
+    with _on(dev):
         _lib.check(_lib.load().texir_query_irf(scene.handle, _ptr(org), _ptr(d), P, N, _ptr(rad), _stream_ptr(dev)),
                    "texir_query_irf")
     return rad
@@ -82,7 +84,7 @@ class _Specular(torch.autograd.Function):
         nn, vv = _f32c(n), _f32c(v)
         rr = _f32c(roughness).reshape(-1)
         out = torch.empty(P, 3, dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
+        with _on(dev):
             _lib.check(_lib.load().texir_specular_reflectance(_ptr(L), _ptr(hh), _ptr(nn), _ptr(vv), _ptr(ll), _ptr(rr),
                                                               P, N, eps, _ptr(out), _stream_ptr(dev)),
                        "texir_specular_reflectance")
@@ -105,7 +107,7 @@ class _Specular(torch.autograd.Function):
             raise NotImplementedError("specular_reflectance: gradients w.r.t. n / v are not provided "
                                       "(the reference detaches the G-buffer, mat_nvdiffrast.py:126,179)")
         g = _f32c(g_out)
-        with torch.cuda.device(dev):
+        with _on(dev):
             _lib.check(_lib.load().texir_specular_reflectance_bwd(_ptr(L), _ptr(hh), _ptr(nn), _ptr(vv), _ptr(ll),
                                                                   _ptr(rr), P, N, ctx.eps, _ptr(g), _ptr(gL), _ptr(gh),
                                                                   _ptr(gl), _ptr(gr), _stream_ptr(dev)),
@@ -127,7 +129,7 @@ class _Diffuse(torch.autograd.Function):
         P, N = int(lighting.shape[0]), int(lighting.shape[1])
         L, ll, nn, aa = _f32c(lighting), _f32c(l), _f32c(n), _f32c(albedo)
         out = torch.empty(P, 3, dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
+        with _on(dev):
             _lib.check(_lib.load().texir_diffuse_reflectance(_ptr(L), _ptr(ll), _ptr(nn), _ptr(aa), P, N, cosine,
                                                              _ptr(out), _stream_ptr(dev)), "texir_diffuse_reflectance")
         ctx.save_for_backward(L, ll, nn, aa)
@@ -146,7 +148,7 @@ class _Diffuse(torch.autograd.Function):
         gl = torch.empty_like(ll) if need[1] else None
         ga = torch.empty_like(aa) if need[3] else None
         g = _f32c(g_out)
-        with torch.cuda.device(dev):
+        with _on(dev):
             _lib.check(_lib.load().texir_diffuse_reflectance_bwd(_ptr(L), _ptr(ll), _ptr(nn), _ptr(aa), P, N, ctx.cosine,
                                                                  _ptr(g), _ptr(gL), _ptr(gl), _ptr(ga),
                                                                  _stream_ptr(dev)), "texir_diffuse_reflectance_bwd")
@@ -195,7 +197,7 @@ class _Shade(torch.autograd.Function):
         rgb = torch.empty(P, 3, dtype=torch.float32, device=dev)
         drgb = torch.empty(P, 3, dtype=torch.float32, device=dev) if (stash and need_r) else None
         ediff = torch.empty(P, 3, dtype=torch.float32, device=dev) if (stash and N_diff > 0 and need_a) else None
-        with torch.cuda.device(dev):
+        with _on(dev):
             _lib.check(_lib.load().texir_shade_fwd(scene.handle, _ptr(nrm), _ptr(alb), _ptr(rough), _ptr(pos), _ptr(camc),
                                                    _ptr(irrc), _ptr(shs), _ptr(shd), P, N_spec, N_diff, mode_spec,
                                                    mode_diff, eps, _ptr(rgb), _ptr(drgb), _ptr(ediff),
@@ -230,7 +232,7 @@ class _Shade(torch.autograd.Function):
         g_alb = torch.empty(P, 3, dtype=torch.float32, device=dev) if need[2] else None
         g_rough = torch.empty(P, dtype=torch.float32, device=dev) if need[3] else None
         g_irr = torch.empty(P, 3, dtype=torch.float32, device=dev) if (need[6] and have_irr) else None
-        with torch.cuda.device(dev):
+        with _on(dev):
             _lib.check(_lib.load().texir_shade_bwd(
                 ctx.scene.handle, _ptr(nrm), _ptr(alb), _ptr(rough), _ptr(pos), _ptr(camc), _ptr(irrc), _ptr(shs),
                 _ptr(shd), P, N_spec, N_diff, mode_spec, mode_diff, eps, _ptr(g),
@@ -277,7 +279,7 @@ class _ShadeTextured(torch.autograd.Function):
         rgb = torch.empty(P, 3, dtype=torch.float32, device=dev)
         drgb = torch.empty(P, 3, dtype=torch.float32, device=dev) if (stash and need_r) else None
         ediff = torch.empty(P, 3, dtype=torch.float32, device=dev) if (stash and N_diff > 0 and need_a) else None
-        with torch.cuda.device(dev):
+        with _on(dev):
             _lib.check(_lib.load().texir_shade_fwd(scene.handle, _ptr(nrm), _ptr(alb), _ptr(rough), _ptr(pos), _ptr(camc),
                                                    _ptr(irrc), _ptr(shs), _ptr(shd), P, N_spec, N_diff, mode_spec,
                                                    mode_diff, eps, _ptr(rgb), _ptr(drgb), _ptr(ediff),
@@ -325,7 +327,7 @@ class _ShadeTextured(torch.autograd.Function):
         gr, gmr, Hr, Wr = target(ctx.shape_r, Lr, need[2])
         if ga is None and gr is None:
             return (None,) * 21
-        with torch.cuda.device(dev):
+        with _on(dev):
             st = _stream_ptr(dev)
             _lib.check(lib.texir_shade_bwd_tex(
                 ctx.scene.handle, _ptr(nrm), _ptr(alb), _ptr(rough), _ptr(pos), _ptr(camc), _ptr(irrc), _ptr(shs), _ptr(shd),
@@ -404,7 +406,7 @@ class MatWorkspace:
         mips = hit[1] if (hit is not None and hit[1].numel() == n and hit[1].device == tex.device) else \
             torch.empty(n, dtype=torch.float32, device=tex.device)
         t = _f32c(tex)
-        with torch.cuda.device(tex.device):
+        with _on(tex.device):
             _lib.check(lib.texir_texture_mip_build_fast(_ptr(t), H, W, C, L, _ptr(mips), _stream_ptr(tex.device)),
                        "texir_texture_mip_build_fast")
         self._pyr[name] = (key, mips, L)
@@ -472,7 +474,7 @@ class _MatStage(torch.autograd.Function):
         rgb = torch.empty(P, 3, **f32)
         drgb = torch.empty(P, 3, **f32) if (stash and need_r) else None
         rough_in = rough_w if stage == 1 else rough
-        with torch.cuda.device(dev):
+        with _on(dev):
             st = _stream_ptr(dev)
             _lib.check(lib.texir_mat_fetch(_ptr(ta), _ptr(ma), Ha, Wa, La, _ptr(tr), _ptr(mr), Hr, Wr, Lr, _ptr(ti), _ptr(mi),
                                            Hi, Wi, Li, _ptr(uv), _ptr(da), P, _ptr(albedo), _ptr(rough), _ptr(rough_w),
@@ -522,7 +524,7 @@ class _MatStage(torch.autograd.Function):
             import torch.distributed as dist
             g_alb_px = torch.zeros(P, 3, dtype=torch.float32, device=dev)
             g_rough_px = torch.zeros(P, dtype=torch.float32, device=dev)
-            with torch.cuda.device(dev):
+            with _on(dev):
                 _lib.check(lib.texir_shade_bwd(ctx.scene.handle, _ptr(nrm), _ptr(albedo), _ptr(rough_in), _ptr(pos), _ptr(camc),
                                                _ptr(irr), _ptr(shs), None, P, N_spec, 0, mode_spec, _lib.MODE_UNIFORM, eps, _ptr(g),
                                                _ptr(drgb), None, _ptr(g_alb_px) if (render_a and need_a) else None,
@@ -536,7 +538,7 @@ class _MatStage(torch.autograd.Function):
             from .parallel import all_gather_rows
             world = dist.get_world_size(ctx.gather_group[1])
             allrows = all_gather_rows(rows, ctx.gather_group[1])
-            with torch.cuda.device(dev):
+            with _on(dev):
                 st = _stream_ptr(dev)
                 _lib.check(lib.texir_mat_scatter_rows(_ptr(allrows), world * P, _ptr(sa), _ptr(sma), Ha, Wa, La if need_a else 0,
                                                       _ptr(sr), _ptr(smr), Hr, Wr, Lr if need_r else 0, st), "texir_mat_scatter_rows")
@@ -548,7 +550,7 @@ class _MatStage(torch.autograd.Function):
                                "texir_texture_mip_fold_into")
             ws.dirty = False
             return (out_a, out_r) + (None,) * 16
-        with torch.cuda.device(dev):
+        with _on(dev):
             st = _stream_ptr(dev)
             _lib.check(lib.texir_shade_bwd_mat(
                 ctx.scene.handle, _ptr(nrm), _ptr(albedo), _ptr(rough_in), _ptr(pos), _ptr(camc), _ptr(irr), _ptr(shs), None,
@@ -596,7 +598,7 @@ def point_order(scene: Scene, position: torch.Tensor) -> torch.Tensor:
     P = int(position.shape[0])
     pos = _f32c(position)
     order = torch.empty(P, dtype=torch.int32, device=dev)
-    with torch.cuda.device(dev):
+    with _on(dev):
         _lib.check(_lib.load().texir_point_order(scene.handle, _ptr(pos), P, _ptr(order), _stream_ptr(dev)),
                    "texir_point_order")
     return order
@@ -621,7 +623,7 @@ def irradiance(scene: Scene, position: torch.Tensor, normal: torch.Tensor, shift
     else:
         order = order.to(device=dev, dtype=torch.int32).contiguous()
         count = int(order.numel())
-    with torch.cuda.device(dev):
+    with _on(dev):
         _lib.check(_lib.load().texir_irradiance_fwd(scene.handle, _ptr(pos), _ptr(nrm), _ptr(sh), _ptr(order), count,
                                                     int(num_samples), _lib.MODES[mode], _ptr(E), _stream_ptr(dev)),
                    "texir_irradiance_fwd")
@@ -638,7 +640,7 @@ def irradiance_peers(scene: Scene, position: torch.Tensor, normal: torch.Tensor,
     pos, nrm = _f32c(position), _f32c(normal)
     sh = _f32c(shift, dev).reshape(P, 2)
     order = order.to(device=dev, dtype=torch.int32).contiguous()
-    with torch.cuda.device(dev):
+    with _on(dev):
         _lib.check(_lib.load().texir_irradiance_fwd_peers(scene.handle, _ptr(pos), _ptr(nrm), _ptr(sh), _ptr(order),
                                                           int(order.numel()), int(num_samples), _lib.MODES[mode], peer_ptrs,
                                                           int(num_peers), _stream_ptr(dev)), "texir_irradiance_fwd_peers")
@@ -656,7 +658,7 @@ def radiance_samples(scene: Scene, position: torch.Tensor, normal: torch.Tensor,
     sh = _f32c(shift, dev).reshape(P, 2)
     rad = torch.empty(P, N, 3, dtype=torch.float32, device=dev)
     dirs = torch.empty(P, N, 3, dtype=torch.float32, device=dev) if return_dirs else None
-    with torch.cuda.device(dev):
+    with _on(dev):
         _lib.check(_lib.load().texir_radiance_samples(scene.handle, _ptr(pos), _ptr(nrm), _ptr(sh), P, N,
                                                       _lib.MODES[mode], _ptr(rad), _ptr(dirs), _stream_ptr(dev)),
                    "texir_radiance_samples")
@@ -681,7 +683,7 @@ def gbuffer(scene: Scene, rays: torch.Tensor, offset: float = 0.0,
     prim = torch.empty(R, dtype=torch.int32, device=dev)
     bary = torch.empty(R, 2, dtype=torch.float32, device=dev)
     mask = torch.empty(R, dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
+    with _on(dev):
         _lib.check(_lib.load().texir_gbuffer(scene.handle, _ptr(r), R, _ptr(pos), _ptr(nrm), _ptr(uv), _ptr(prim),
                                              _ptr(bary), _ptr(mask), _stream_ptr(dev)), "texir_gbuffer")
     if offset:
@@ -696,7 +698,7 @@ def gbuffer(scene: Scene, rays: torch.Tensor, offset: float = 0.0,
         if dd.shape[0] != R:
             raise ValueError("ray_differentials must have one (d dir/dX, d dir/dY) row per ray")
         texd = torch.empty(R, 4, dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
+        with _on(dev):
             _lib.check(_lib.load().texir_gbuffer_uv_da(scene.handle, _ptr(r), _ptr(dd), _ptr(prim), R, _ptr(texd),
                                                        _stream_ptr(dev)), "texir_gbuffer_uv_da")
         out["texd"] = texd.reshape(shape + (4,))
@@ -727,7 +729,7 @@ def gbuffer_mvp(scene: Scene, mvp: torch.Tensor, cam_position: torch.Tensor, res
     prim = torch.empty(R, dtype=torch.int32, device=dev)
     mask = torch.empty(R, **f32)
     rays = torch.empty(R, 6, **f32) if return_rays else None
-    with torch.cuda.device(dev):
+    with _on(dev):
         _lib.check(_lib.load().texir_gbuffer_mvp_shard(scene.handle, _ptr(m), _ptr(cam), V, res, rank, world, int(flip_v),
                                                        _ptr(pos), _ptr(nrm), _ptr(uv), _ptr(texd), _ptr(prim), _ptr(bary),
                                                        _ptr(mask), _ptr(rays), _stream_ptr(dev)), "texir_gbuffer_mvp_shard")
@@ -754,7 +756,7 @@ class _TextureFetch(torch.autograd.Function):
         P = int(uv.shape[0])
         t, u = _f32c(tex), _f32c(uv)
         out = torch.empty(P, C, dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
+        with _on(dev):
             _lib.check(_lib.load().texir_texture_fetch(_ptr(t), H, W, C, _ptr(u), P, _ptr(out), _stream_ptr(dev)),
                        "texir_texture_fetch")
         ctx.save_for_backward(u)
@@ -768,7 +770,7 @@ class _TextureFetch(torch.autograd.Function):
         H, W, C = ctx.shape
         g = _f32c(g_out)
         g_tex = torch.zeros(H, W, C, dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
+        with _on(dev):
             _lib.check(_lib.load().texir_texture_scatter(_ptr(g), H, W, C, _ptr(u), int(u.shape[0]), _ptr(g_tex),
                                                          _stream_ptr(dev)), "texir_texture_scatter")
         return g_tex, None
@@ -809,7 +811,7 @@ def build_mips(tex: torch.Tensor, max_mip_level: Optional[int] = None):
     lib = _lib.load()
     t = _f32c(tex)
     mips = torch.empty(max(int(lib.texir_texture_mip_elems(H, W, C, L)), 1), dtype=torch.float32, device=tex.device)
-    with torch.cuda.device(tex.device):
+    with _on(tex.device):
         _lib.check(lib.texir_texture_mip_build(_ptr(t), H, W, C, L, _ptr(mips), _stream_ptr(tex.device)),
                    "texir_texture_mip_build")
     return mips, L
@@ -824,7 +826,7 @@ class _TextureFetchMip(torch.autograd.Function):
         t, u, d = _f32c(tex), _f32c(uv), _f32c(uv_da)
         mips, L = build_mips(t, max_mip_level)
         out = torch.empty(P, C, dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
+        with _on(dev):
             _lib.check(_lib.load().texir_texture_fetch_mip(_ptr(t), _ptr(mips), H, W, C, L, _ptr(u), _ptr(d), P,
                                                            _ptr(out), None, _stream_ptr(dev)),
                        "texir_texture_fetch_mip")
@@ -841,7 +843,7 @@ class _TextureFetchMip(torch.autograd.Function):
         g_tex = torch.zeros(H, W, C, dtype=torch.float32, device=dev)
         g_mips = torch.zeros(n_mips, dtype=torch.float32, device=dev)
         lib = _lib.load()
-        with torch.cuda.device(dev):
+        with _on(dev):
             _lib.check(lib.texir_texture_scatter_mip(_ptr(g), H, W, C, L, _ptr(u), _ptr(d), int(u.shape[0]),
                                                      _ptr(g_tex), _ptr(g_mips), _stream_ptr(dev)),
                        "texir_texture_scatter_mip")

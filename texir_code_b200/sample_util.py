@@ -231,7 +231,7 @@ def _draw_mt_device(n: int, dev: torch.device, idx: int, state: Optional[torch.T
                 "d_in": torch.empty(_MT_N, dtype=torch.int32, device=dev), "d_out": torch.empty(_MT_N + 2, dtype=torch.int32, device=dev)}
     ctx["h_in"].numpy().view(np.uint32)[:] = a[_OFF_STATE:_OFF_STATE + 8 * _MT_N].view(np.uint64).astype(np.uint32)
     main = torch.cuda.current_stream(idx)
-    with torch.cuda.device(idx), torch.cuda.stream(ctx["stream"]):
+    with torch.cuda.stream(ctx["stream"]):     # (the stream context also makes its device current)
         out = torch.empty(n, dtype=torch.float32, device=dev)
         ctx["d_in"].copy_(ctx["h_in"], non_blocking=True)
         _lib.check(_lib.load().texir_mt19937_uniform(_ptr(ctx["d_in"]), left, nxt, n, _ptr(out), _ptr(ctx["d_out"]),

@@ -12,6 +12,7 @@ RaycastingScene mimics Open3D's class closely enough that every reference model 
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes
 from typing import Optional
 
@@ -25,6 +26,18 @@ INVALID_ID = 0xFFFFFFFF
 
 def _stream_ptr(device: torch.device) -> ctypes.c_void_p:
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+_NO_GUARD = contextlib.nullcontext()
+
+
+def _on(device: torch.device):
+    """device guard for a block of launches: nothing at all when `device` is already the current one (the usual case; a
+    torch.cuda.device() context costs several microseconds per step and call site)"""
+    idx = device.index
+    if idx is None or torch.cuda.current_device() == idx:
+        return _NO_GUARD
+    return torch.cuda.device(device)
 
 
 def _ptr(t: Optional[torch.Tensor]) -> ctypes.c_void_p:
