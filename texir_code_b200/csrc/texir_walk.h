@@ -178,6 +178,10 @@ TX_HD float qplane_(uint32_t w, uint32_t sel, float S, float O) {
 #ifndef TX_PREFETCH_UV
 #define TX_PREFETCH_UV 0
 #endif
+#ifndef TX_PREFETCH_POP
+#define TX_PREFETCH_POP 0
+#endif
+constexpr int kQSentinelValue = (int)0x80000000u;   // == kQSentinel (declared further down)
 #ifndef TX_PREFETCH_FRONT
 #define TX_PREFETCH_FRONT 0
 #endif
@@ -238,8 +242,12 @@ TX_HD int qbvh2_step(const SceneView& s, const RayQ& r, float tbest, int node, i
 #if TX_PREFETCH_PUSH && defined(__CUDA_ARCH__)
         // the postponed child's node is fetched into L1 now, so that the pop finds it there (-DTX_PREFETCH_PUSH=1;
         // = 2: a postponed LEAF's first triangle too)
+#if TX_PREFETCH_PUSH == 3   // into L2 only
+        if (far_child >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(s.qnodes2 + 2 * (size_t)far_child));
+#else
         if (far_child >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(s.qnodes2 + 2 * (size_t)far_child));
-#if TX_PREFETCH_PUSH >= 2
+#endif
+#if TX_PREFETCH_PUSH == 2
         else qprefetch_leaf(s, far_child);
 #endif
 #endif
@@ -248,7 +256,16 @@ TX_HD int qbvh2_step(const SceneView& s, const RayQ& r, float tbest, int node, i
     }
     if (h0) return c0;
     if (h1) return c1;
+#if TX_PREFETCH_POP && defined(__CUDA_ARCH__)
+    {   // the entry that will be popped NEXT is fetched into L1 now (its push-time prefetch is long evicted)
+        const int popped = *--sp;
+        const int below = sp[-1];
+        if (popped != kQSentinelValue && below >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(s.qnodes2 + 2 * (size_t)below));
+        return popped;
+    }
+#else
     return *--sp;
+#endif
 #endif
 }
 
