@@ -2006,6 +2006,34 @@ int texir_gbuffer_uv_da(const texir_scene* sc, const float* rays, const float* d
     return finish_launch("k_gbuffer_uv_da");
 }
 
+// TEXIR_L2_PERSIST=1 (experiment, default off): the quantised node array (17 MB at T = 2^20) is given a persisting L2
+// window on the launching stream, so that the texture / triangle / UV traffic of the same kernel cannot evict the lower
+// tree.  Measured on B200: no effect (535.3 ... 535.8 ms against 535.5 ms, profiles/r02_l2persist_sweep.txt).
+static void l2_persist_nodes(const texir_scene* sc, cudaStream_t st) {
+    static const int on = env_int("TEXIR_L2_PERSIST", 0);
+    if (!on || !sc->d_qnodes2) return;
+    const int dev = sc->info.device;
+    const size_t bytes = (size_t)sc->info.num_nodes2 * 32;
+    static bool limit_set[64] = {};
+    int max_persist = 0, max_window = 0;
+    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+    if (max_persist <= 0 || max_window <= 0) return;
+    if (dev >= 0 && dev < 64 && !limit_set[dev]) {
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min((size_t)max_persist, bytes));
+        limit_set[dev] = true;
+        if (on > 1) fprintf(stderr, "texir: persisting L2 %d B max, window %d B max, nodes %zu B\n", max_persist, max_window, bytes);
+    }
+    cudaStreamAttrValue v{};
+    v.accessPolicyWindow.base_ptr = sc->d_qnodes2;
+    v.accessPolicyWindow.num_bytes = std::min(bytes, (size_t)max_window);
+    v.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)max_persist / (double)v.accessPolicyWindow.num_bytes);
+    v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v);
+    cudaGetLastError();
+}
+
 static int irradiance_launch(const char* fn, const texir_scene* sc, const float* pos, const float* nrm, const float* shift,
                              const int32_t* order, int64_t P, int N, int mode, const PeerOut& E, void* stream) {
     if (check_scene_tex(fn, sc) || check_pn(fn, P, N) || check_mode(fn, mode)) return 1;
@@ -2019,6 +2047,7 @@ static int irradiance_launch(const char* fn, const texir_scene* sc, const float*
     const int64_t warps = (P + (32 / G) - 1) / (32 / G);
     unsigned g = grid_for(warps * 32, 128);
     cudaStream_t st = (cudaStream_t)stream;
+    l2_persist_nodes(sc, st);
     if (sc->info.bvh_kind == TEXIR_BVH8)
         k_irradiance<8><<<g, 128, 0, st>>>(sc->view, pos, nrm, shift, order, P, N, mode, G, ab, E);
     else if (G == 32 && coop8() && sc->d_nodes8)
